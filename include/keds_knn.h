@@ -1,0 +1,133 @@
+/* keds_knn.h -- C ABI of libkeds_knn.so, the B200 (sm_100a) drop-in for the knowledge-retrieval
+ * hot path of KEDs. Plain C: opaque handles, raw pointers, sizes. No C++ or torch types.
+ *
+ * Every entry point names the reference interface it replaces (paths relative to the KEDs tree).
+ * The reference reaches this path through the Faiss Python module; a maintainer binds these
+ * functions with ctypes (keds_b200/_capi.py).
+ *
+ * Pointer residency: `const float*`/output pointers may be host or device memory (detected with
+ * cudaPointerGetAttributes). Host pointers imply staged copies and a stream synchronisation before
+ * return (Faiss' numpy contract). Device pointers make the call stream-ordered and asynchronous.
+ * All matrices are C-contiguous row-major. Return value: 0 on success, negative keds_status
+ * otherwise, with text in keds_last_error(). There is no CPU fallback.
+ */
+#ifndef KEDS_KNN_H
+#define KEDS_KNN_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct keds_index keds_index_t;
+
+enum keds_metric { KEDS_METRIC_IP = 0, KEDS_METRIC_L2 = 1 };
+
+enum keds_status {
+  KEDS_OK = 0,
+  KEDS_ERR_ARG = -1,      /* bad argument (null, d mismatch, k out of range ...) */
+  KEDS_ERR_CUDA = -2,     /* CUDA runtime/driver error, cudaError_t in the message */
+  KEDS_ERR_NO_GPU = -3,   /* no usable sm_100 device */
+  KEDS_ERR_KERNEL = -4,   /* device-side protocol watchdog fired (error word in the message) */
+  KEDS_ERR_OOM = -5
+};
+
+/* search flags */
+#define KEDS_SEARCH_EXACT_ONLY 1u  /* skip the bf16 tensor-core pass, answer with the fp32 scan */
+#define KEDS_SEARCH_NO_FALLBACK 2u /* debugging: do not run the exact fallback for flagged queries */
+
+typedef struct keds_search_stats {
+  int32_t n_flagged[2];  /* queries whose certificate failed (answered by the exact fallback) */
+  int32_t slices;        /* row slices per (database, query tile) used by the last search */
+  int32_t items;         /* work items of the scoring kernel */
+  int32_t grid;          /* CTAs launched by the scoring kernel */
+  int32_t exact_only;    /* 1 if the planner chose the fp32 scan for the whole batch */
+  int32_t launches;      /* kernels launched by the last search call */
+  uint32_t err_word;     /* device watchdog word, 0 = clean */
+} keds_search_stats;
+
+/* ---- index lifecycle ------------------------------------------------------------------------
+ * Replaces faiss.IndexFlatL2(768) / IndexFlatIP + faiss.index_cpu_to_gpu(res, gpu, index)
+ * (src/main.py:72-83, src/eval_retrieval.py:289-296). */
+int keds_index_create(int d, int metric, int device, keds_index_t** out);
+void keds_index_free(keds_index_t* idx);
+
+/* index.add(x) (src/main.py:78,83; src/eval_retrieval.py:293,296). x: [n][d] float32, host or
+ * device. Copies; the caller may free x on return. Builds the fp32 master, the bf16 operand copy
+ * and the per-row norms on the index's device. */
+int keds_index_add(keds_index_t* idx, const float* x, int64_t n);
+int keds_index_reset(keds_index_t* idx);                 /* index.reset() */
+int64_t keds_index_ntotal(const keds_index_t* idx);      /* index.ntotal */
+int keds_index_dim(const keds_index_t* idx);             /* index.d */
+int keds_index_metric(const keds_index_t* idx);
+int keds_index_device(const keds_index_t* idx);
+/* device pointer to the resident fp32 rows [ntotal][d] (for keds_gather_pool); owned by idx */
+const float* keds_index_rows(const keds_index_t* idx);
+/* added to every returned label (row-sharded indices report global ids) */
+int keds_index_set_id_offset(keds_index_t* idx, int64_t offset);
+
+/* ---- search ---------------------------------------------------------------------------------
+ * D, I = index.search(q, k) (src/trainer.py:213,221,271; src/eval_utils.py:169,177).
+ * q: [nq][d] float32. D: [nq][k] float32 (inner products, or squared L2 distances). I: [nq][k]
+ * int64 labels, best first; ties by lower label; rows past ntotal are padded with label -1 and
+ * D = -FLT_MAX (IP) / +FLT_MAX (L2). Results equal an exact fp32 flat search. */
+int keds_index_search(keds_index_t* idx, const float* q, int64_t nq, int k, float* D, int64_t* I,
+                      void* cuda_stream);
+int keds_index_search_ex(keds_index_t* idx, const float* q, int64_t nq, int k, float* D, int64_t* I,
+                         uint32_t flags, void* cuda_stream);
+/* Two indices, one query batch: the image-DB and text-DB searches of src/trainer.py:213 and :221
+ * fused into one pass over the queries. Both indices share d, metric and device. */
+int keds_index_search2(keds_index_t* a, keds_index_t* b, const float* q, int64_t nq, int k,
+                       float* Da, int64_t* Ia, float* Db, int64_t* Ib, uint32_t flags,
+                       void* cuda_stream);
+/* Wait for the last asynchronous search on idx and report its device status. */
+int keds_index_sync(keds_index_t* idx, void* cuda_stream);
+int keds_index_last_stats(const keds_index_t* idx, keds_search_stats* out);
+
+/* ---- neighbour gather / weighted pool ---------------------------------------------------------
+ * W == NULL:  out[b][j][:] = base[I[b][perm ? perm[j] : j]][:]   (out: [B][k][d])
+ *             replaces base[I.reshape(-1)].reshape(B,k,-1), the shared randperm(k) shuffle and the
+ *             .to(device) of src/trainer.py:214-230, src/eval_utils.py:170-183.
+ * W != NULL:  out[b][h][:] = sum_j W[b][h][j] * base[I[b][j]][:]  (W: [B][H][k], out: [B][H][d])
+ *             the attn@v-shaped pool of src/model/model.py:69-73.
+ * base, out, W: device float32. I: device int64. perm: device int32[k] or NULL. id < 0 -> zeros. */
+int keds_gather_pool(const float* base, int64_t n_base, const int64_t* I, const float* W,
+                     const int32_t* perm, int64_t B, int k, int H, int d, float* out,
+                     void* cuda_stream);
+
+/* ---- row-sharded merge ------------------------------------------------------------------------
+ * D_parts/I_parts: [parts][nq][k] per-shard results with global labels (device); writes the global
+ * top-k with the same ordering rule. New relative to the reference (replicas only). */
+int keds_topk_merge(const float* D_parts, const int64_t* I_parts, int parts, int64_t nq, int k,
+                    int metric, float* D, int64_t* I, void* cuda_stream);
+
+/* ---- gallery ranking --------------------------------------------------------------------------
+ * rank_out[q] = #{ g != target[q], g != exclude[q] : (s(q,g), -g) > (s(q,target), -target) } with
+ * s = fp32 inner product. Replaces the similarity matrix + full argsort + name matching of
+ * get_metrics_coco / _fashion / _cirr (src/eval_utils.py:1008-1067). All pointers device memory;
+ * exclude may be NULL. */
+int keds_gallery_rank(const float* Q, int64_t nq, const float* G, int64_t ng, int d,
+                      const int64_t* target, const int64_t* exclude, int64_t* rank_out,
+                      void* cuda_stream);
+/* hits[q][i] = #{ j < ks[i] : labels[I[q][j]] == qlabel[q] } for ascending ks (device pointers).
+ * The counting core of get_metrics_imgnet (src/eval_utils.py:1107-1118). */
+int keds_label_hits(const int64_t* I, int64_t nq, int kmax, const int64_t* labels,
+                    const int64_t* qlabel, const int32_t* ks, int nks, int32_t* hits,
+                    void* cuda_stream);
+
+/* ---- diagnostics ------------------------------------------------------------------------------
+ * Approximate (bf16 tensor-core) scores of q against every row: out [nq][ntotal] device float32.
+ * Test hook for the GEMM alone; not a product path. */
+int keds_debug_scores(keds_index_t* idx, const float* q, int64_t nq, float* out, void* cuda_stream);
+/* Scale the certificate's error bound (1.0 = rigorous bound). Test hook for the fallback. */
+int keds_index_set_eps_scale(keds_index_t* idx, float scale);
+
+const char* keds_last_error(void);
+int keds_device_count(void);          /* faiss.get_num_gpus() (src/eval_retrieval.py:289) */
+const char* keds_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KEDS_KNN_H */

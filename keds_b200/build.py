@@ -1,0 +1,62 @@
+"""Build libkeds_knn.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "csrc", "api.cu")
+DEPS = [
+    SRC,
+    os.path.join(HERE, "csrc", "ptx.cuh"),
+    os.path.join(HERE, "csrc", "score_topk_sm100.cuh"),
+    os.path.join(HERE, "csrc", "aux_kernels.cuh"),
+    os.path.join(os.path.dirname(HERE), "include", "keds_knn.h"),
+]
+LIB = os.path.join(HERE, "libkeds_knn.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+
+def find_nvcc() -> str | None:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    return None
+
+
+def is_stale() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(p) > t for p in DEPS)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile the library if it is missing or older than its sources; return its path."""
+    if not force and not is_stale():
+        return LIB
+    nvcc = find_nvcc()
+    if nvcc is None:
+        if os.path.exists(LIB):
+            return LIB  # GPU box without a toolkit on PATH: use the prebuilt library as shipped
+        raise RuntimeError("nvcc not found and libkeds_knn.so is not built")
+    cmd = [nvcc, *NVCC_FLAGS, "-o", LIB, SRC]
+    if verbose:
+        cmd += ["-Xptxas", "-v"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        sys.stderr.write(res.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

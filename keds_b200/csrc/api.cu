@@ -1,0 +1,719 @@
+// C ABI of libkeds_knn.so (see include/keds_knn.h). Host orchestration only: planning, buffers,
+// TMA descriptors, launches. All arithmetic is in the kernels of score_topk_sm100.cuh and
+// aux_kernels.cuh. There is no CPU path: without a CUDA device every compute call fails.
+#include "../../include/keds_knn.h"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "aux_kernels.cuh"
+
+using namespace keds;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CK(call)                                                                         \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess)                                                               \
+      return fail(e_ == cudaErrorMemoryAllocation ? KEDS_ERR_OOM : KEDS_ERR_CUDA,        \
+                  "%s failed: %s (%d) at %s:%d", #call, cudaGetErrorString(e_), (int)e_, \
+                  __FILE__, __LINE__);                                                   \
+  } while (0)
+
+#define CKS(call)          \
+  do {                     \
+    int s_ = (call);       \
+    if (s_ != 0) return s_; \
+  } while (0)
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  // grow without keeping contents
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    CK(cudaMalloc(&p, bytes));
+    cap = bytes;
+    return 0;
+  }
+  // grow keeping the first `keep` bytes
+  int grow_keep(size_t bytes, size_t keep) {
+    if (bytes <= cap) return 0;
+    void* np = nullptr;
+    CK(cudaMalloc(&np, bytes));
+    if (p && keep) CK(cudaMemcpy(np, p, keep, cudaMemcpyDeviceToDevice));
+    if (p) cudaFree(p);
+    p = np;
+    cap = bytes;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T* as() const { return static_cast<T*>(p); }
+};
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(dev) == cudaSuccess) ok = true;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* sym = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) !=
+          cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(sym);
+  return fn;
+}
+
+// bf16 [rows][d_pad] row-major -> boxes of {BK columns x box_rows rows}, 128-byte swizzle,
+// out-of-range rows read as zeros.
+int encode_rows_map(CUtensorMap* tm, const void* base, int64_t rows, int d_pad, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(KEDS_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(d_pad), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstr[1] = {static_cast<cuuint64_t>(d_pad) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(KEDS_ERR_CUDA, "cuTensorMapEncodeTiled failed: CUresult %d", (int)r);
+  return 0;
+}
+
+bool is_device_ptr(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+constexpr int CTRL_WORDS = 8;  // [0],[1] n_flagged per db, [2] err word, [3],[4] grid barriers
+constexpr int S_MAX = 192;
+constexpr size_t CAND_BUDGET = size_t(1) << 30;
+constexpr int64_t Q_PASS_MAX = 16384;
+
+struct Plan {
+  int exact_only = 0;
+  int S = 1, n_qt = 1, n_items = 0, grid = 0;
+};
+
+}  // namespace
+
+struct keds_index {
+  int d = 0, d_pad = 0, metric = 0, device = 0, num_sms = 0;
+  int64_t n = 0;
+  int64_t id_offset = 0;
+  float eps_scale = 1.f;
+  DevBuf x_f32, x_bf16, bias, dbstat;
+  CUtensorMap tm_x;
+  bool tm_x_ok = false;
+  // per-call scratch (one search in flight per handle)
+  DevBuf q_f32, q_bf16, qstat, cand, cand_cnt, cand_theta, flagged[2], ctrl, exact_scratch;
+  DevBuf D_stage[2], I_stage[2];
+  CUtensorMap tm_q;
+  const void* tm_q_base = nullptr;
+  int64_t tm_q_rows = 0;
+  keds_search_stats stats;
+  bool attrs_set = false;
+};
+
+namespace {
+
+int set_kernel_attrs(keds_index* ix) {
+  if (ix->attrs_set) return 0;
+  CK(cudaFuncSetAttribute(k_score_topk, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)SCORE_SMEM_BYTES));
+  CK(cudaFuncSetAttribute(k_select_rerank, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(k_exact_fallback, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  ix->attrs_set = true;
+  return 0;
+}
+
+// Pick the number of row slices: enough that no slice is expected to hold more than a third of
+// LKEEP of the top-k, enough work items to fill the SMs, then whatever minimises the longest CTA.
+Plan make_plan(const keds_index* ix, int n_db, int64_t nq, int k, int64_t n_min, int64_t n_max,
+               uint32_t flags) {
+  Plan pl;
+  pl.n_qt = static_cast<int>((nq + BM - 1) / BM);
+  const int T_min = static_cast<int>((n_min + BN - 1) / BN);
+  const int T_max = static_cast<int>((n_max + BN - 1) / BN);
+  const int S_sel = std::max(1, (3 * k + LKEEP - 1) / LKEEP);
+  const int groups = n_db * pl.n_qt;
+  int S_hi = std::min(T_min, S_MAX);
+  const long long by_mem = static_cast<long long>(CAND_BUDGET / (size_t(CAP) * BM * 8)) / groups;
+  S_hi = static_cast<int>(std::min<long long>(S_hi, by_mem));
+  if ((flags & KEDS_SEARCH_EXACT_ONLY) || S_hi < S_sel || k > R_MAX / 2) {
+    pl.exact_only = 1;
+    return pl;
+  }
+  double best = 1e300;
+  for (int S = S_sel; S <= S_hi; ++S) {
+    const long long items = static_cast<long long>(groups) * S;
+    const long long G = std::min<long long>(items, ix->num_sms);
+    const long long per_cta = (items + G - 1) / G;
+    const double cost = static_cast<double>(per_cta) * ((T_max + S - 1) / S) + 0.35 * per_cta;
+    if (cost < best - 1e-9) {
+      best = cost;
+      pl.S = S;
+    }
+  }
+  pl.n_items = groups * pl.S;
+  pl.grid = std::min(pl.n_items, ix->num_sms);
+  return pl;
+}
+
+int ensure_q_map(keds_index* ix, int64_t rows_needed) {
+  const size_t bytes = static_cast<size_t>(rows_needed) * ix->d_pad * 2;
+  if (bytes > ix->q_bf16.cap) {
+    // round up so repeated slightly larger batches do not re-encode every call
+    const int64_t rows = (rows_needed + 1023) / 1024 * 1024;
+    CKS(ix->q_bf16.ensure(static_cast<size_t>(rows) * ix->d_pad * 2));
+    CK(cudaMemset(ix->q_bf16.p, 0, ix->q_bf16.cap));
+    ix->tm_q_base = nullptr;
+  }
+  if (ix->tm_q_base != ix->q_bf16.p) {
+    const int64_t rows = static_cast<int64_t>(ix->q_bf16.cap / (static_cast<size_t>(ix->d_pad) * 2));
+    CKS(encode_rows_map(&ix->tm_q, ix->q_bf16.p, rows, ix->d_pad, BM));
+    ix->tm_q_base = ix->q_bf16.p;
+    ix->tm_q_rows = rows;
+  }
+  return 0;
+}
+
+int launch_exact(keds_index* ix, keds_index* dbix, int dbi, const float* q_dev, int64_t nq, int k,
+                 float* D, long long* I, cudaStream_t st) {
+  ExactParams ep;
+  ep.x_f32 = dbix->x_f32.as<float>();
+  ep.n_rows = dbix->n;
+  ep.d = ix->d;
+  ep.metric = ix->metric;
+  ep.k = k;
+  ep.nq = static_cast<int>(nq);
+  ep.q_f32 = q_dev;
+  ep.flagged = ix->flagged[dbi].as<int>();
+  ep.n_flagged = ix->ctrl.as<int>() + dbi;
+  long long fc = (256ll << 20) / (4 * std::max<int64_t>(dbix->n, 1));
+  fc = std::max(1ll, std::min(64ll, fc));
+  fc = std::min<long long>(fc, nq);
+  ep.f_cap = static_cast<int>(fc);
+  CKS(ix->exact_scratch.ensure(static_cast<size_t>(fc) * dbix->n * 4));
+  ep.scratch = ix->exact_scratch.as<float>();
+  ep.D = D;
+  ep.I = I;
+  ep.id_offset = dbix->id_offset;
+  ep.barrier = ix->ctrl.as<unsigned int>() + 3 + dbi;
+  const int dq = (ix->d + 3) & ~3;
+  const size_t smem = static_cast<size_t>(EXACT_QG) * dq * 4 + K_MAX * 8 + 256 * 4 + 16 + 16 + 32;
+  if (smem > 160 * 1024) return fail(KEDS_ERR_ARG, "d=%d too large for the exact fallback", ix->d);
+  int per_sm = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_exact_fallback, EXACT_THREADS, smem));
+  if (per_sm < 1) return fail(KEDS_ERR_CUDA, "exact fallback kernel does not fit on an SM");
+  const int grid = ix->num_sms * std::min(per_sm, 4);
+  void* args[] = {&ep};
+  CK(cudaLaunchCooperativeKernel((const void*)k_exact_fallback, dim3(grid), dim3(EXACT_THREADS), args,
+                                 smem, st));
+  ix->stats.launches++;
+  return 0;
+}
+
+// One pass (<= Q_PASS_MAX queries). q_dev: device fp32 [nq][d]. D/I: device outputs.
+int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int k, float* D[2],
+                long long* I[2], uint32_t flags, cudaStream_t st, float* dump, int64_t ld_dump) {
+  keds_index* a = ix[0];
+  CKS(set_kernel_attrs(a));
+  CKS(a->ctrl.ensure(CTRL_WORDS * 4));
+  CK(cudaMemsetAsync(a->ctrl.p, 0, CTRL_WORDS * 4, st));
+  for (int i = 0; i < n_db; ++i) CKS(a->flagged[i].ensure(static_cast<size_t>(nq) * 4));
+
+  int64_t n_min = ix[0]->n, n_max = ix[0]->n;
+  if (n_db > 1) {
+    n_min = std::min(n_min, ix[1]->n);
+    n_max = std::max(n_max, ix[1]->n);
+  }
+  Plan pl = make_plan(a, n_db, nq, k, n_min, n_max, flags);
+  if (dump && pl.exact_only) return fail(KEDS_ERR_ARG, "debug_scores needs at least one 256-row tile");
+  a->stats.exact_only = pl.exact_only;
+  a->stats.slices = pl.S;
+  a->stats.items = pl.n_items;
+  a->stats.grid = pl.grid;
+
+  if (pl.exact_only) {
+    for (int i = 0; i < n_db; ++i) {
+      k_flag_all<<<static_cast<unsigned>((nq + 255) / 256), 256, 0, st>>>(
+          a->flagged[i].as<int>(), a->ctrl.as<int>() + i, static_cast<int>(nq));
+      a->stats.launches++;
+    }
+  } else {
+    // operands: bf16 queries + per-query residual norms
+    const int64_t q_rows = static_cast<int64_t>(pl.n_qt) * BM;
+    CKS(ensure_q_map(a, q_rows));
+    CKS(a->qstat.ensure(static_cast<size_t>(nq) * sizeof(float4)));
+    {
+      const int threads = 256;
+      const long long warps_needed = nq;
+      const unsigned blocks =
+          static_cast<unsigned>(std::min<long long>((warps_needed * 32 + threads - 1) / threads, 4096));
+      k_prep_rows<<<blocks, threads, 0, st>>>(q_dev, nq, a->d, a->d_pad,
+                                              a->q_bf16.as<__nv_bfloat16>(), a->qstat.as<float4>(),
+                                              nullptr, nullptr);
+      a->stats.launches++;
+    }
+    const size_t items = static_cast<size_t>(pl.n_items);
+    CKS(a->cand.ensure(items * CAP * BM * 8));
+    CKS(a->cand_cnt.ensure(items * BM * 4));
+    CKS(a->cand_theta.ensure(items * BM * 4));
+
+    ScoreParams sp;
+    memset(&sp, 0, sizeof sp);
+    sp.n_db = n_db;
+    sp.n_qt = pl.n_qt;
+    sp.S = pl.S;
+    sp.n_items = pl.n_items;
+    sp.kblocks = a->d_pad / BK;
+    sp.nq = static_cast<int>(nq);
+    for (int i = 0; i < n_db; ++i) {
+      sp.n_rows[i] = static_cast<int>(ix[i]->n);
+      sp.n_tiles[i] = static_cast<int>((ix[i]->n + BN - 1) / BN);
+      sp.bias[i] = a->metric == METRIC_L2 ? ix[i]->bias.as<float>() : nullptr;
+    }
+    sp.cand = a->cand.as<uint2>();
+    sp.cand_cnt = a->cand_cnt.as<int>();
+    sp.cand_theta = a->cand_theta.as<float>();
+    sp.err = a->ctrl.as<uint32_t>() + 2;
+    sp.dump = dump;
+    sp.ld_dump = ld_dump;
+    k_score_topk<<<pl.grid, SCORE_THREADS, SCORE_SMEM_BYTES, st>>>(
+        a->tm_q, ix[0]->tm_x, n_db > 1 ? ix[1]->tm_x : ix[0]->tm_x, sp);
+    a->stats.launches++;
+    CK(cudaGetLastError());
+    if (dump) return 0;
+
+    RerankParams rp;
+    memset(&rp, 0, sizeof rp);
+    rp.n_db = n_db;
+    rp.n_qt = pl.n_qt;
+    rp.S = pl.S;
+    rp.nq = static_cast<int>(nq);
+    rp.k = k;
+    rp.d = a->d;
+    rp.metric = a->metric;
+    rp.cand = sp.cand;
+    rp.cand_cnt = sp.cand_cnt;
+    rp.cand_theta = sp.cand_theta;
+    rp.q_f32 = q_dev;
+    rp.qstat = a->qstat.as<float4>();
+    for (int i = 0; i < n_db; ++i) {
+      rp.x_f32[i] = ix[i]->x_f32.as<float>();
+      rp.dbstat[i] = ix[i]->dbstat.as<unsigned int>();
+      rp.D[i] = D[i];
+      rp.I[i] = I[i];
+      rp.id_offset[i] = ix[i]->id_offset;
+      rp.flagged[i] = a->flagged[i].as<int>();
+      rp.n_flagged[i] = a->ctrl.as<int>() + i;
+    }
+    rp.eps_scale = a->eps_scale;
+    const size_t slots = static_cast<size_t>(pl.S) * CAP;
+    const size_t smem = static_cast<size_t>((a->d + 3) & ~3) * 4 + slots * 8 + pl.S * 4 + R_MAX * 8 +
+                        256 * 4 + 32 * 4 + 16 + 16;
+    if (smem > 200 * 1024) return fail(KEDS_ERR_ARG, "re-rank shared memory %zu too large", smem);
+    k_select_rerank<<<dim3(static_cast<unsigned>(nq), n_db), RERANK_THREADS, smem, st>>>(rp);
+    a->stats.launches++;
+    CK(cudaGetLastError());
+  }
+  if (!(flags & KEDS_SEARCH_NO_FALLBACK) || pl.exact_only) {
+    for (int i = 0; i < n_db; ++i) CKS(launch_exact(a, ix[i], i, q_dev, nq, k, D[i], I[i], st));
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+__global__ void k_fill_pad(float* D, long long* I, long long n, float dv) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) {
+    D[i] = dv;
+    I[i] = -1;
+  }
+}
+
+int finish_sync(keds_index* a, cudaStream_t st) {
+  CK(cudaStreamSynchronize(st));
+  uint32_t h[CTRL_WORDS] = {0};
+  if (a->ctrl.p) CK(cudaMemcpy(h, a->ctrl.p, sizeof h, cudaMemcpyDeviceToHost));
+  a->stats.n_flagged[0] = static_cast<int32_t>(h[0]);
+  a->stats.n_flagged[1] = static_cast<int32_t>(h[1]);
+  a->stats.err_word = h[2];
+  if (h[2] != 0)
+    return fail(KEDS_ERR_KERNEL, "scoring kernel watchdog fired: error word 0x%x", h[2]);
+  return 0;
+}
+
+int search_impl(keds_index* ix[2], int n_db, const float* q, int64_t nq, int k, float* D[2],
+                int64_t* I[2], uint32_t flags, void* stream) {
+  keds_index* a = ix[0];
+  if (!a || !q || nq < 0 || k <= 0) return fail(KEDS_ERR_ARG, "search: null handle/query or bad nq/k");
+  if (k > K_MAX) return fail(KEDS_ERR_ARG, "search: k=%d exceeds the maximum %d", k, K_MAX);
+  for (int i = 0; i < n_db; ++i) {
+    if (!ix[i] || !D[i] || !I[i]) return fail(KEDS_ERR_ARG, "search: null index or output pointer");
+    if (ix[i]->d != a->d || ix[i]->metric != a->metric || ix[i]->device != a->device)
+      return fail(KEDS_ERR_ARG, "search2: indices differ in d, metric or device");
+    if (ix[i]->n > 0x7fffffffll - BN) return fail(KEDS_ERR_ARG, "index too large for 32-bit row ids");
+  }
+  DeviceGuard g(a->device);
+  if (!g.ok) return fail(KEDS_ERR_NO_GPU, "cannot select CUDA device %d", a->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  memset(&a->stats, 0, sizeof a->stats);
+  if (nq == 0) return 0;
+
+  const bool q_dev = is_device_ptr(q);
+  bool out_dev = true;
+  for (int i = 0; i < n_db; ++i) {
+    const bool dd = is_device_ptr(D[i]), di = is_device_ptr(I[i]);
+    if (dd != di) return fail(KEDS_ERR_ARG, "search: D and I must both be host or both be device memory");
+    out_dev = out_dev && dd;
+    if (i > 0 && dd != is_device_ptr(D[0]))
+      return fail(KEDS_ERR_ARG, "search2: outputs must all be host or all be device memory");
+  }
+  const float* qd = q;
+  if (!q_dev) {
+    CKS(a->q_f32.ensure(static_cast<size_t>(nq) * a->d * 4));
+    CK(cudaMemcpyAsync(a->q_f32.p, q, static_cast<size_t>(nq) * a->d * 4, cudaMemcpyHostToDevice, st));
+    qd = a->q_f32.as<float>();
+  }
+  float* Dd[2] = {nullptr, nullptr};
+  long long* Id[2] = {nullptr, nullptr};
+  for (int i = 0; i < n_db; ++i) {
+    if (out_dev) {
+      Dd[i] = D[i];
+      Id[i] = reinterpret_cast<long long*>(I[i]);
+    } else {
+      CKS(a->D_stage[i].ensure(static_cast<size_t>(nq) * k * 4));
+      CKS(a->I_stage[i].ensure(static_cast<size_t>(nq) * k * 8));
+      Dd[i] = a->D_stage[i].as<float>();
+      Id[i] = a->I_stage[i].as<long long>();
+    }
+  }
+  // empty databases answer with padding only
+  bool any_empty = false;
+  for (int i = 0; i < n_db; ++i) any_empty = any_empty || ix[i]->n == 0;
+  if (any_empty) {
+    for (int i = 0; i < n_db; ++i) {
+      if (ix[i]->n != 0) {
+        keds_index* one[2] = {ix[i], nullptr};
+        float* D1[2] = {Dd[i], nullptr};
+        long long* I1[2] = {Id[i], nullptr};
+        for (int64_t q0 = 0; q0 < nq; q0 += Q_PASS_MAX) {
+          const int64_t nb = std::min<int64_t>(Q_PASS_MAX, nq - q0);
+          float* Dp[2] = {D1[0] + q0 * k, nullptr};
+          long long* Ip[2] = {I1[0] + q0 * k, nullptr};
+          CKS(search_pass(one, 1, qd + q0 * a->d, nb, k, Dp, Ip, flags, st, nullptr, 0));
+          if (q0 + nb < nq) CKS(finish_sync(one[0], st));
+        }
+      } else {
+        const long long tot = static_cast<long long>(nq) * k;
+        k_fill_pad<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, st>>>(
+            Dd[i], Id[i], tot, a->metric == METRIC_L2 ? FLT_MAX : -FLT_MAX);
+      }
+    }
+  } else {
+    for (int64_t q0 = 0; q0 < nq; q0 += Q_PASS_MAX) {
+      const int64_t nb = std::min<int64_t>(Q_PASS_MAX, nq - q0);
+      float* Dp[2] = {Dd[0] + q0 * k, n_db > 1 ? Dd[1] + q0 * k : nullptr};
+      long long* Ip[2] = {Id[0] + q0 * k, n_db > 1 ? Id[1] + q0 * k : nullptr};
+      CKS(search_pass(ix, n_db, qd + q0 * a->d, nb, k, Dp, Ip, flags, st, nullptr, 0));
+      // scratch is reused by the next pass: drain this one first
+      if (q0 + nb < nq) CKS(finish_sync(a, st));
+    }
+  }
+  if (!out_dev) {
+    for (int i = 0; i < n_db; ++i) {
+      CK(cudaMemcpyAsync(D[i], Dd[i], static_cast<size_t>(nq) * k * 4, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(I[i], Id[i], static_cast<size_t>(nq) * k * 8, cudaMemcpyDeviceToHost, st));
+    }
+    return finish_sync(a, st);
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* keds_last_error(void) { return g_err.c_str(); }
+const char* keds_version(void) { return "keds-knn-b200 0.1 (sm_100a)"; }
+
+int keds_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int keds_index_create(int d, int metric, int device, keds_index_t** out) {
+  if (!out) return fail(KEDS_ERR_ARG, "create: out is null");
+  *out = nullptr;
+  if (d <= 0 || d > 16384) return fail(KEDS_ERR_ARG, "create: bad dimension %d", d);
+  if (metric != KEDS_METRIC_IP && metric != KEDS_METRIC_L2)
+    return fail(KEDS_ERR_ARG, "create: metric must be 0 (IP) or 1 (L2)");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(KEDS_ERR_NO_GPU, "no CUDA device: libkeds_knn has no CPU fallback");
+  }
+  if (device < 0 || device >= ndev) return fail(KEDS_ERR_ARG, "create: device %d of %d", device, ndev);
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(KEDS_ERR_NO_GPU, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                prop.major, prop.minor);
+  DeviceGuard g(device);
+  if (!g.ok) return fail(KEDS_ERR_NO_GPU, "cannot select CUDA device %d", device);
+  keds_index* ix = new keds_index();
+  ix->d = d;
+  ix->d_pad = (d + BK - 1) / BK * BK;
+  ix->metric = metric;
+  ix->device = device;
+  ix->num_sms = prop.multiProcessorCount;
+  memset(&ix->stats, 0, sizeof ix->stats);
+  int s = ix->dbstat.ensure(8);
+  if (s == 0 && cudaMemset(ix->dbstat.p, 0, 8) != cudaSuccess) s = fail(KEDS_ERR_CUDA, "memset failed");
+  if (s != 0) {
+    delete ix;
+    return s;
+  }
+  *out = ix;
+  return 0;
+}
+
+void keds_index_free(keds_index_t* ix) {
+  if (!ix) return;
+  DeviceGuard g(ix->device);
+  DevBuf* bufs[] = {&ix->x_f32, &ix->x_bf16, &ix->bias, &ix->dbstat, &ix->q_f32, &ix->q_bf16,
+                    &ix->qstat, &ix->cand, &ix->cand_cnt, &ix->cand_theta, &ix->flagged[0],
+                    &ix->flagged[1], &ix->ctrl, &ix->exact_scratch, &ix->D_stage[0], &ix->D_stage[1],
+                    &ix->I_stage[0], &ix->I_stage[1]};
+  for (DevBuf* b : bufs) b->release();
+  delete ix;
+}
+
+int keds_index_add(keds_index_t* ix, const float* x, int64_t n) {
+  if (!ix || (n > 0 && !x) || n < 0) return fail(KEDS_ERR_ARG, "add: null handle/data or negative n");
+  if (n == 0) return 0;
+  DeviceGuard g(ix->device);
+  if (!g.ok) return fail(KEDS_ERR_NO_GPU, "cannot select CUDA device %d", ix->device);
+  const int64_t n0 = ix->n, n1 = n0 + n;
+  if (n1 > 0x7fffffffll - BN) return fail(KEDS_ERR_ARG, "add: more than 2^31 rows");
+  const size_t d = ix->d, dp = ix->d_pad;
+  const int64_t cap_rows = n0 == 0 ? n1 : std::max<int64_t>(n1, n0 + n0 / 2);
+  const int64_t tiles_cap = (cap_rows + BN - 1) / BN;
+  if (static_cast<size_t>(n1) * d * 4 > ix->x_f32.cap) {
+    CKS(ix->x_f32.grow_keep(static_cast<size_t>(cap_rows) * d * 4, static_cast<size_t>(n0) * d * 4));
+    CKS(ix->x_bf16.grow_keep(static_cast<size_t>(cap_rows) * dp * 2, static_cast<size_t>(n0) * dp * 2));
+    CKS(ix->bias.grow_keep(static_cast<size_t>(tiles_cap) * BN * 4, static_cast<size_t>(n0) * 4));
+  }
+  CK(cudaMemcpy(ix->x_f32.as<float>() + n0 * d, x, static_cast<size_t>(n) * d * 4, cudaMemcpyDefault));
+  const unsigned blocks = static_cast<unsigned>(std::min<int64_t>((n * 32 + 255) / 256, 148 * 16));
+  k_prep_rows<<<blocks, 256>>>(ix->x_f32.as<float>() + n0 * d, n, ix->d, ix->d_pad,
+                               ix->x_bf16.as<__nv_bfloat16>() + n0 * dp, nullptr,
+                               ix->bias.as<float>() + n0, ix->dbstat.as<unsigned int>());
+  const int64_t padded = (n1 + BN - 1) / BN * BN;
+  if (padded > n1)
+    k_fill_f32<<<static_cast<unsigned>((padded - n1 + 255) / 256), 256>>>(ix->bias.as<float>() + n1,
+                                                                          padded - n1, -INFINITY);
+  CK(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  ix->n = n1;
+  CKS(encode_rows_map(&ix->tm_x, ix->x_bf16.p, n1, ix->d_pad, BN));
+  ix->tm_x_ok = true;
+  return 0;
+}
+
+int keds_index_reset(keds_index_t* ix) {
+  if (!ix) return fail(KEDS_ERR_ARG, "reset: null handle");
+  DeviceGuard g(ix->device);
+  CK(cudaDeviceSynchronize());
+  ix->x_f32.release();
+  ix->x_bf16.release();
+  ix->bias.release();
+  ix->n = 0;
+  ix->tm_x_ok = false;
+  CK(cudaMemset(ix->dbstat.p, 0, 8));
+  return 0;
+}
+
+int64_t keds_index_ntotal(const keds_index_t* ix) { return ix ? ix->n : -1; }
+int keds_index_dim(const keds_index_t* ix) { return ix ? ix->d : -1; }
+int keds_index_metric(const keds_index_t* ix) { return ix ? ix->metric : -1; }
+int keds_index_device(const keds_index_t* ix) { return ix ? ix->device : -1; }
+const float* keds_index_rows(const keds_index_t* ix) { return ix ? ix->x_f32.as<float>() : nullptr; }
+
+int keds_index_set_id_offset(keds_index_t* ix, int64_t offset) {
+  if (!ix) return fail(KEDS_ERR_ARG, "set_id_offset: null handle");
+  ix->id_offset = offset;
+  return 0;
+}
+
+int keds_index_set_eps_scale(keds_index_t* ix, float scale) {
+  if (!ix || !(scale >= 0.f)) return fail(KEDS_ERR_ARG, "set_eps_scale: bad argument");
+  ix->eps_scale = scale;
+  return 0;
+}
+
+int keds_index_search(keds_index_t* ix, const float* q, int64_t nq, int k, float* D, int64_t* I,
+                      void* stream) {
+  return keds_index_search_ex(ix, q, nq, k, D, I, 0u, stream);
+}
+
+int keds_index_search_ex(keds_index_t* ix, const float* q, int64_t nq, int k, float* D, int64_t* I,
+                         uint32_t flags, void* stream) {
+  keds_index* v[2] = {ix, nullptr};
+  float* Dv[2] = {D, nullptr};
+  int64_t* Iv[2] = {I, nullptr};
+  return search_impl(v, 1, q, nq, k, Dv, Iv, flags, stream);
+}
+
+int keds_index_search2(keds_index_t* a, keds_index_t* b, const float* q, int64_t nq, int k, float* Da,
+                       int64_t* Ia, float* Db, int64_t* Ib, uint32_t flags, void* stream) {
+  keds_index* v[2] = {a, b};
+  float* Dv[2] = {Da, Db};
+  int64_t* Iv[2] = {Ia, Ib};
+  return search_impl(v, 2, q, nq, k, Dv, Iv, flags, stream);
+}
+
+int keds_index_sync(keds_index_t* ix, void* stream) {
+  if (!ix) return fail(KEDS_ERR_ARG, "sync: null handle");
+  DeviceGuard g(ix->device);
+  return finish_sync(ix, static_cast<cudaStream_t>(stream));
+}
+
+int keds_index_last_stats(const keds_index_t* ix, keds_search_stats* out) {
+  if (!ix || !out) return fail(KEDS_ERR_ARG, "last_stats: null argument");
+  *out = ix->stats;
+  return 0;
+}
+
+int keds_debug_scores(keds_index_t* ix, const float* q, int64_t nq, float* out, void* stream) {
+  if (!ix || !q || !out || nq <= 0 || nq > Q_PASS_MAX) return fail(KEDS_ERR_ARG, "debug_scores: bad argument");
+  if (!is_device_ptr(q) || !is_device_ptr(out)) return fail(KEDS_ERR_ARG, "debug_scores: device pointers only");
+  if (ix->n == 0) return fail(KEDS_ERR_ARG, "debug_scores: empty index");
+  DeviceGuard g(ix->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  memset(&ix->stats, 0, sizeof ix->stats);
+  keds_index* v[2] = {ix, nullptr};
+  float* Dv[2] = {nullptr, nullptr};
+  long long* Iv[2] = {nullptr, nullptr};
+  CKS(search_pass(v, 1, q, nq, 1, Dv, Iv, 0u, st, out, ix->n));
+  return finish_sync(ix, st);
+}
+
+int keds_gather_pool(const float* base, int64_t n_base, const int64_t* I, const float* W,
+                     const int32_t* perm, int64_t B, int k, int H, int d, float* out, void* stream) {
+  if (!base || !I || !out || B < 0 || k <= 0 || d <= 0 || n_base < 0)
+    return fail(KEDS_ERR_ARG, "gather_pool: bad argument");
+  if (B == 0) return 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!W) {
+    const long long warps = static_cast<long long>(B) * k;
+    k_gather_rows<<<static_cast<unsigned>((warps * 32 + 255) / 256), 256, 0, st>>>(
+        base, reinterpret_cast<const long long*>(I), perm, B, k, d, out);
+  } else {
+    if (H <= 0) return fail(KEDS_ERR_ARG, "gather_pool: H must be positive with weights");
+    const size_t smem = static_cast<size_t>(k) * 8 + static_cast<size_t>(H) * k * 4;
+    if (smem > 48 * 1024) return fail(KEDS_ERR_ARG, "gather_pool: H*k too large");
+    k_weighted_pool<<<static_cast<unsigned>(B), 256, smem, st>>>(
+        base, reinterpret_cast<const long long*>(I), W, B, k, H, d, out);
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int keds_topk_merge(const float* Dp, const int64_t* Ip, int parts, int64_t nq, int k, int metric,
+                    float* D, int64_t* I, void* stream) {
+  if (!Dp || !Ip || !D || !I || parts <= 0 || nq < 0 || k <= 0)
+    return fail(KEDS_ERR_ARG, "topk_merge: bad argument");
+  if (nq == 0) return 0;
+  const size_t tot = static_cast<size_t>(parts) * k;
+  const size_t smem = tot * 8 + ((tot + 1) & ~size_t(1)) * 4 + tot * 8;
+  if (smem > 200 * 1024) return fail(KEDS_ERR_ARG, "topk_merge: parts*k too large");
+  static bool attr = false;
+  if (!attr) {
+    CK(cudaFuncSetAttribute(k_topk_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  k_topk_merge<<<static_cast<unsigned>(nq), 128, smem, static_cast<cudaStream_t>(stream)>>>(
+      Dp, reinterpret_cast<const long long*>(Ip), parts, nq, k, metric, D, reinterpret_cast<long long*>(I));
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int keds_gallery_rank(const float* Q, int64_t nq, const float* G, int64_t ng, int d,
+                      const int64_t* target, const int64_t* exclude, int64_t* rank_out, void* stream) {
+  if (!Q || !G || !target || !rank_out || nq < 0 || ng <= 0 || d <= 0)
+    return fail(KEDS_ERR_ARG, "gallery_rank: bad argument");
+  if (nq == 0) return 0;
+  const size_t smem = static_cast<size_t>((d + 3) & ~3) * 4;
+  if (smem > 48 * 1024) return fail(KEDS_ERR_ARG, "gallery_rank: d too large");
+  k_gallery_rank<<<static_cast<unsigned>(nq), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+      Q, nq, G, ng, d, reinterpret_cast<const long long*>(target),
+      reinterpret_cast<const long long*>(exclude), reinterpret_cast<long long*>(rank_out));
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int keds_label_hits(const int64_t* I, int64_t nq, int kmax, const int64_t* labels, const int64_t* qlabel,
+                    const int32_t* ks, int nks, int32_t* hits, void* stream) {
+  if (!I || !labels || !qlabel || !ks || !hits || nq < 0 || kmax <= 0 || nks <= 0)
+    return fail(KEDS_ERR_ARG, "label_hits: bad argument");
+  if (nq == 0) return 0;
+  k_label_hits<<<static_cast<unsigned>((nq + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const long long*>(I), nq, kmax, reinterpret_cast<const long long*>(labels),
+      reinterpret_cast<const long long*>(qlabel), ks, nks, hits);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

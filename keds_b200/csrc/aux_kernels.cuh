@@ -1,0 +1,641 @@
+// Plain CUDA-core kernels around the tcgen05 scoring kernel: operand preparation, candidate
+// selection + exact fp32 re-rank with an exactness certificate, the exact fp32 fallback, shard
+// merge, neighbour gather / weighted pool, gallery rank counting and label-hit counting.
+#pragma once
+#include <cuda_bf16.h>
+#include <float.h>
+#include "score_topk_sm100.cuh"
+
+namespace keds {
+
+constexpr int METRIC_IP = 0;
+constexpr int METRIC_L2 = 1;
+constexpr int RERANK_THREADS = 256;
+constexpr int R_MAX = 512;      // most candidates one query may send to the fp32 re-rank
+constexpr int K_MAX = 2048;     // largest k (Faiss' GPU flat index has the same limit)
+constexpr int EXACT_THREADS = 256;
+constexpr int EXACT_QG = 8;     // queries scored together against one pass over the rows
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// The one fp32 scoring routine of the library (re-rank, fallback and gallery ranking all call it,
+// so a (query,row) pair gets the same bits on every path). Warp-cooperative; q may be shared or
+// global memory. IP: sum q*x. L2: sum (q-x)^2. Every lane returns the full sum.
+__device__ __forceinline__ float warp_exact_score(const float* __restrict__ q,
+                                                  const float* __restrict__ x, int d, int metric,
+                                                  int lane) {
+  float acc = 0.f;
+  if ((d & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(q)) & 15) == 0) {
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    const float4* q4 = reinterpret_cast<const float4*>(q);
+    const int d4 = d >> 2;
+    if (metric == METRIC_IP) {
+      for (int c = lane; c < d4; c += 32) {
+        const float4 a = __ldg(x4 + c);
+        const float4 b = q4[c];
+        acc = fmaf(a.x, b.x, acc);
+        acc = fmaf(a.y, b.y, acc);
+        acc = fmaf(a.z, b.z, acc);
+        acc = fmaf(a.w, b.w, acc);
+      }
+    } else {
+      for (int c = lane; c < d4; c += 32) {
+        const float4 a = __ldg(x4 + c);
+        const float4 b = q4[c];
+        float t;
+        t = b.x - a.x; acc = fmaf(t, t, acc);
+        t = b.y - a.y; acc = fmaf(t, t, acc);
+        t = b.z - a.z; acc = fmaf(t, t, acc);
+        t = b.w - a.w; acc = fmaf(t, t, acc);
+      }
+    }
+  } else {
+    if (metric == METRIC_IP) {
+      for (int c = lane; c < d; c += 32) acc = fmaf(__ldg(x + c), q[c], acc);
+    } else {
+      for (int c = lane; c < d; c += 32) {
+        const float t = q[c] - __ldg(x + c);
+        acc = fmaf(t, t, acc);
+      }
+    }
+  }
+  return warp_sum(acc);
+}
+
+// Total order used everywhere: better score first, then lower row id.
+// `rank_score` is the IP value, or minus the squared distance under L2.
+__device__ __forceinline__ unsigned long long order_key(float rank_score, uint32_t id) {
+  if (rank_score == 0.f) rank_score = 0.f;  // -0 -> +0
+  return (static_cast<unsigned long long>(f32_to_key(rank_score)) << 32) |
+         static_cast<unsigned long long>(0xFFFFFFFFu - id);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Operand preparation: fp32 rows -> bf16 rows padded to d_pad, plus the per-row statistics the
+// exactness certificate needs. One warp per row.
+//   stat[r] = { |x|^2, |bf16(x)|, |x - bf16(x)|, 0 }        (optional)
+//   bias[r] = -0.5 |x|^2                                    (optional; L2 ranking bias)
+//   gmax[0] = max_r |bf16(x_r)| , gmax[1] = max_r |x_r - bf16(x_r)|   as float bit patterns
+__global__ void k_prep_rows(const float* __restrict__ x, long long n, int d, int d_pad,
+                            __nv_bfloat16* __restrict__ out, float4* __restrict__ stat,
+                            float* __restrict__ bias, unsigned int* __restrict__ gmax) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  float mx_b = 0.f, mx_d = 0.f;
+  for (long long r = warp0; r < n; r += nwarps) {
+    const float* xr = x + r * d;
+    __nv_bfloat16* orow = out + r * d_pad;
+    float n2 = 0.f, b2 = 0.f, e2 = 0.f;
+    for (int c = lane; c < d_pad; c += 32) {
+      const float v = c < d ? xr[c] : 0.f;
+      const __nv_bfloat16 b = __float2bfloat16_rn(v);
+      const float bf = __bfloat162float(b);
+      orow[c] = b;
+      n2 = fmaf(v, v, n2);
+      b2 = fmaf(bf, bf, b2);
+      const float e = v - bf;
+      e2 = fmaf(e, e, e2);
+    }
+    n2 = warp_sum(n2);
+    b2 = warp_sum(b2);
+    e2 = warp_sum(e2);
+    const float bn = sqrtf(b2), dn = sqrtf(e2);
+    if (lane == 0) {
+      if (stat != nullptr) stat[r] = make_float4(n2, bn, dn, 0.f);
+      if (bias != nullptr) bias[r] = -0.5f * n2;
+    }
+    mx_b = fmaxf(mx_b, bn);
+    mx_d = fmaxf(mx_d, dn);
+  }
+  if (gmax != nullptr && lane == 0) {
+    // round the maxima up by an ulp-ish factor so they stay upper bounds
+    atomicMax(gmax + 0, __float_as_uint(mx_b * 1.000001f));
+    atomicMax(gmax + 1, __float_as_uint(mx_d * 1.000001f));
+  }
+}
+
+__global__ void k_fill_f32(float* p, long long n, float v) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Candidate selection + fp32 re-rank + certificate. One block per (query, db).
+//
+// Let a(n) be the bf16-GEMM score, s(n) the exact one, |a - s| <= eps for every row (eps from
+// Cauchy-Schwarz on the two rounding residuals + an fp32 accumulation allowance). With a_(k) the
+// k-th largest approximate score, every true top-k row has a(n) >= a_(k) - 2 eps. So the set
+// C = { n : a(n) >= tau }, tau = a_(k) - 2 eps, contains the exact answer provided no slice
+// dropped a row scoring >= tau, i.e. every slice threshold theta < tau. If that (or |C| <= R_MAX)
+// fails the query is queued for the exact fallback instead of being answered from C.
+struct RerankParams {
+  int n_db, n_qt, S, nq, k, d, metric;
+  const uint2* cand;
+  const int* cand_cnt;
+  const float* cand_theta;
+  const float* q_f32;      // [nq][d]
+  const float4* qstat;     // [nq] {|q|^2, |bf16 q|, |q - bf16 q|}
+  const float* x_f32[2];
+  const unsigned int* dbstat[2];
+  float* D[2];
+  long long* I[2];
+  long long id_offset[2];
+  int* flagged[2];
+  int* n_flagged[2];
+  float eps_scale;         // 1.0 normally; tests shrink/grow it to exercise the fallback
+};
+
+__device__ __forceinline__ float block_max_f(float v, float* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float r = red[0];
+  for (int w = 1; w < (blockDim.x >> 5); ++w) r = fmaxf(r, red[w]);
+  __syncthreads();
+  return r;
+}
+
+// k-th largest of keys[0..n) (1 <= k <= n), 4 x 8-bit radix passes with a shared histogram.
+__device__ unsigned int block_kth_largest(const unsigned int* keys, int n, int k,
+                                          unsigned int* hist /*256*/, unsigned int* bcast /*2*/) {
+  unsigned int prefix = 0, mask = 0;
+  int need = k;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const unsigned int key = keys[i];
+      if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int acc = 0, b = 255;
+      for (; b > 0; --b) {
+        const int h = static_cast<int>(hist[b]);
+        if (acc + h >= need) break;
+        acc += h;
+      }
+      bcast[0] = static_cast<unsigned int>(b);
+      bcast[1] = static_cast<unsigned int>(need - acc);
+    }
+    __syncthreads();
+    prefix |= bcast[0] << shift;
+    mask |= 255u << shift;
+    need = static_cast<int>(bcast[1]);
+    __syncthreads();
+  }
+  return prefix;
+}
+
+__global__ void __launch_bounds__(RERANK_THREADS)
+k_select_rerank(const RerankParams p) {
+  extern __shared__ uint8_t rr_smem[];
+  const int q = blockIdx.x, db = blockIdx.y;
+  const int qt = q / BM, ql = q % BM;
+  const int slots = p.S * CAP;
+  // shared layout
+  float* qvec = reinterpret_cast<float*>(rr_smem);                      // d (16-B aligned)
+  unsigned int* keys = reinterpret_cast<unsigned int*>(qvec + ((p.d + 3) & ~3));
+  unsigned int* ids = keys + slots;
+  int* s_cnt = reinterpret_cast<int*>(ids + slots);                     // S
+  unsigned int* sel_id = reinterpret_cast<unsigned int*>(s_cnt + p.S);  // R_MAX
+  float* sel_sc = reinterpret_cast<float*>(sel_id + R_MAX);             // R_MAX
+  unsigned int* hist = reinterpret_cast<unsigned int*>(sel_sc + R_MAX); // 256
+  float* red = reinterpret_cast<float*>(hist + 256);                    // 32
+  unsigned int* bcast = reinterpret_cast<unsigned int*>(red + 32);      // 4
+  int* counters = reinterpret_cast<int*>(bcast + 4);                    // 4
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < 4) counters[tid] = 0;
+  for (int c = tid; c < p.d; c += blockDim.x) qvec[c] = p.q_f32[static_cast<long long>(q) * p.d + c];
+  float th_max = -INFINITY;
+  for (int s = tid; s < p.S; s += blockDim.x) {
+    const long long item = (static_cast<long long>(db) * p.S + s) * p.n_qt + qt;
+    s_cnt[s] = p.cand_cnt[item * BM + ql];
+    th_max = fmaxf(th_max, p.cand_theta[item * BM + ql]);
+  }
+  th_max = block_max_f(th_max, red);  // (syncs)
+  for (int sl = tid; sl < slots; sl += blockDim.x) {
+    const int s = sl / CAP, e = sl % CAP;
+    if (e < s_cnt[s]) {
+      const long long item = (static_cast<long long>(db) * p.S + s) * p.n_qt + qt;
+      const uint2 en = p.cand[(item * CAP + e) * BM + ql];
+      const int pos = atomicAdd(&counters[0], 1);
+      float sc = __uint_as_float(en.x);
+      if (sc == 0.f) sc = 0.f;
+      keys[pos] = f32_to_key(sc);
+      ids[pos] = en.y;
+    }
+  }
+  __syncthreads();
+  const int n = counters[0];
+
+  // eps: |a - s| <= |dq| |bf(x)| + |q| |dx| + accumulation allowance
+  const float4 qs = p.qstat[q];
+  const float xb = __uint_as_float(p.dbstat[db][0]);
+  const float xd = __uint_as_float(p.dbstat[db][1]);
+  const float qn = sqrtf(qs.x);
+  const int d_pad = (p.d + BK - 1) / BK * BK;
+  float eps = qs.z * xb + qn * xd + (static_cast<float>(d_pad) * 2.4e-7f) * qs.y * xb;
+  eps *= 1.0001f * p.eps_scale;
+
+  float tau = -INFINITY;
+  if (n >= p.k) {
+    const unsigned int kth = block_kth_largest(keys, n, p.k, hist, bcast);
+    tau = key_to_f32(kth) - 2.f * eps;
+  }
+  for (int i = tid; i < n; i += blockDim.x) {
+    if (key_to_f32(keys[i]) >= tau) {
+      const int pos = atomicAdd(&counters[1], 1);
+      if (pos < R_MAX) sel_id[pos] = ids[i];
+    }
+  }
+  __syncthreads();
+  int m = counters[1];
+  const bool ok = (m <= R_MAX) && (th_max == -INFINITY || th_max < tau);
+  if (!ok && tid == 0) {
+    const int pos = atomicAdd(p.n_flagged[db], 1);
+    p.flagged[db][pos] = q;
+  }
+  m = min(m, R_MAX);
+
+  const float* xbase = p.x_f32[db];
+  for (int c = warp; c < m; c += (blockDim.x >> 5)) {
+    const float sc = warp_exact_score(qvec, xbase + static_cast<long long>(sel_id[c]) * p.d, p.d,
+                                      p.metric, lane);
+    if (lane == 0) sel_sc[c] = sc;
+  }
+  __syncthreads();
+  float* Dq = p.D[db] + static_cast<long long>(q) * p.k;
+  long long* Iq = p.I[db] + static_cast<long long>(q) * p.k;
+  for (int c = tid; c < m; c += blockDim.x) {
+    const float sc = sel_sc[c];
+    const unsigned long long mine = order_key(p.metric == METRIC_L2 ? -sc : sc, sel_id[c]);
+    int rank = 0;
+    for (int j = 0; j < m; ++j) {
+      const float sj = sel_sc[j];
+      rank += order_key(p.metric == METRIC_L2 ? -sj : sj, sel_id[j]) > mine;
+    }
+    if (rank < p.k) {
+      Dq[rank] = sc;
+      Iq[rank] = static_cast<long long>(sel_id[c]) + p.id_offset[db];
+    }
+  }
+  for (int r = m + tid; r < p.k; r += blockDim.x) {
+    Dq[r] = p.metric == METRIC_L2 ? FLT_MAX : -FLT_MAX;
+    Iq[r] = -1;
+  }
+}
+
+__global__ void k_flag_all(int* flagged, int* n_flagged, int nq) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nq) flagged[i] = i;
+  if (i == 0) *n_flagged = nq;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Exact fp32 fallback: one persistent cooperative launch answers every flagged query, however
+// many there are, and returns at once when there are none.
+struct ExactParams {
+  const float* x_f32;
+  long long n_rows;
+  int d, metric, k, nq;
+  const float* q_f32;
+  const int* flagged;
+  const int* n_flagged;
+  float* scratch;          // [f_cap][n_rows] rank scores (IP, or -dist)
+  int f_cap;
+  float* D;
+  long long* I;
+  long long id_offset;
+  unsigned int* barrier;   // zeroed before launch
+};
+
+__device__ __forceinline__ void grid_barrier(unsigned int* ctr, unsigned int& target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(ctr, 1u);
+    while (*reinterpret_cast<volatile unsigned int*>(ctr) < target) { __nanosleep(64); }
+    __threadfence();
+  }
+  __syncthreads();
+  target += gridDim.x;
+}
+
+__global__ void __launch_bounds__(EXACT_THREADS)
+k_exact_fallback(const ExactParams p) {
+  const int nfl = *reinterpret_cast<const volatile int*>(p.n_flagged);
+  if (nfl <= 0) return;
+  extern __shared__ uint8_t ex_smem[];
+  float* qs = reinterpret_cast<float*>(ex_smem);                       // EXACT_QG * dq
+  const int dq = (p.d + 3) & ~3;
+  unsigned int* sel_key = reinterpret_cast<unsigned int*>(qs + EXACT_QG * dq);  // K_MAX
+  unsigned int* sel_id = sel_key + K_MAX;                              // K_MAX
+  unsigned int* hist = sel_id + K_MAX;                                 // 256
+  unsigned int* bcast = hist + 256;                                    // 4
+  int* counters = reinterpret_cast<int*>(bcast + 4);                   // 4
+  int* wsum = counters + 4;                                            // 8 (per-warp tie counts)
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wpb = blockDim.x >> 5;
+  const long long groups = (p.n_rows + 31) / 32;
+  unsigned int bar_target = gridDim.x;
+
+  for (int r0 = 0; r0 < nfl; r0 += p.f_cap) {
+    const int F = min(p.f_cap, nfl - r0);
+    // ---- phase 1: rank scores of F flagged queries against every row
+    for (int g0 = 0; g0 < F; g0 += EXACT_QG) {
+      const int G = min(EXACT_QG, F - g0);
+      __syncthreads();
+      for (int i = tid; i < G * dq; i += blockDim.x) {
+        const int qi = i / dq, c = i % dq;
+        const int q = p.flagged[r0 + g0 + qi];
+        qs[i] = c < p.d ? p.q_f32[static_cast<long long>(q) * p.d + c] : 0.f;
+      }
+      __syncthreads();
+      for (long long g = static_cast<long long>(blockIdx.x) * wpb + warp; g < groups;
+           g += static_cast<long long>(gridDim.x) * wpb) {
+        float keep[EXACT_QG];
+#pragma unroll
+        for (int i = 0; i < EXACT_QG; ++i) keep[i] = 0.f;
+        for (int rr = 0; rr < 32; ++rr) {
+          const long long row = g * 32 + rr;
+          if (row >= p.n_rows) break;
+          const float* xr = p.x_f32 + row * p.d;
+#pragma unroll
+          for (int i = 0; i < EXACT_QG; ++i) {
+            if (i < G) {
+              const float sc = warp_exact_score(qs + i * dq, xr, p.d, p.metric, lane);
+              if (lane == rr) keep[i] = p.metric == METRIC_L2 ? -sc : sc;
+            }
+          }
+        }
+        const long long row = g * 32 + lane;
+        if (row < p.n_rows) {
+#pragma unroll
+          for (int i = 0; i < EXACT_QG; ++i)
+            if (i < G) p.scratch[static_cast<long long>(g0 + i) * p.n_rows + row] = keep[i];
+        }
+      }
+    }
+    grid_barrier(p.barrier, bar_target);
+    // ---- phase 2: one block per flagged query selects and orders its top-k
+    for (int f = blockIdx.x; f < F; f += gridDim.x) {
+      const int q = p.flagged[r0 + f];
+      const float* sc = p.scratch + static_cast<long long>(f) * p.n_rows;
+      const long long n = p.n_rows;
+      const int keff = static_cast<int>(min(static_cast<long long>(p.k), n));
+      // k-th largest rank score (radix select over global memory)
+      unsigned int prefix = 0, mask = 0;
+      int need = keff;
+      for (int shift = 24; shift >= 0; shift -= 8) {
+        for (int i = tid; i < 256; i += blockDim.x) hist[i] = 0;
+        __syncthreads();
+        for (long long i = tid; i < n; i += blockDim.x) {
+          float v = sc[i];
+          if (v == 0.f) v = 0.f;
+          const unsigned int key = f32_to_key(v);
+          if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (tid == 0) {
+          int acc = 0, b = 255;
+          for (; b > 0; --b) {
+            const int h = static_cast<int>(hist[b]);
+            if (acc + h >= need) break;
+            acc += h;
+          }
+          bcast[0] = static_cast<unsigned int>(b);
+          bcast[1] = static_cast<unsigned int>(need - acc);
+        }
+        __syncthreads();
+        prefix |= bcast[0] << shift;
+        mask |= 255u << shift;
+        need = static_cast<int>(bcast[1]);
+        __syncthreads();
+      }
+      const unsigned int kth = prefix;  // `need` rows equal to kth are wanted, lowest ids first
+      if (tid < 4) counters[tid] = 0;
+      __syncthreads();
+      // rows strictly better than kth: any order; rows equal to kth: in id order until `need`
+      for (long long base = 0; base < n; base += blockDim.x) {
+        const long long i = base + tid;
+        unsigned int key = 0;
+        bool gt = false, eq = false;
+        if (i < n) {
+          float v = sc[i];
+          if (v == 0.f) v = 0.f;
+          key = f32_to_key(v);
+          gt = key > kth;
+          eq = key == kth;
+        }
+        if (gt) {
+          const int pos = atomicAdd(&counters[0], 1);
+          sel_key[pos] = key;
+          sel_id[pos] = static_cast<unsigned int>(i);
+        }
+        const int taken = counters[1];  // ties taken so far (stable: updated after the sync below)
+        if (taken < need) {
+          const unsigned int bal = __ballot_sync(0xffffffffu, eq);
+          if (lane == 0) wsum[warp] = __popc(bal);
+          __syncthreads();
+          int before = 0;
+          for (int w = 0; w < warp; ++w) before += wsum[w];
+          const int my = taken + before + __popc(bal & ((1u << lane) - 1u));
+          if (eq && my < need) {
+            const int pos = (keff - need) + my;  // ties fill the tail slots
+            sel_key[pos] = key;
+            sel_id[pos] = static_cast<unsigned int>(i);
+          }
+          __syncthreads();
+          if (tid == 0) {
+            int tot = 0;
+            for (int w = 0; w < wpb; ++w) tot += wsum[w];
+            counters[1] = taken + tot;
+          }
+          __syncthreads();
+        }
+      }
+      __syncthreads();
+      float* Dq = p.D + static_cast<long long>(q) * p.k;
+      long long* Iq = p.I + static_cast<long long>(q) * p.k;
+      for (int c = tid; c < keff; c += blockDim.x) {
+        const unsigned long long mine =
+            (static_cast<unsigned long long>(sel_key[c]) << 32) | (0xFFFFFFFFu - sel_id[c]);
+        int rank = 0;
+        for (int j = 0; j < keff; ++j) {
+          const unsigned long long other =
+              (static_cast<unsigned long long>(sel_key[j]) << 32) | (0xFFFFFFFFu - sel_id[j]);
+          rank += other > mine;
+        }
+        const float v = key_to_f32(sel_key[c]);
+        Dq[rank] = p.metric == METRIC_L2 ? -v : v;
+        Iq[rank] = static_cast<long long>(sel_id[c]) + p.id_offset;
+      }
+      for (int r = keff + tid; r < p.k; r += blockDim.x) {
+        Dq[r] = p.metric == METRIC_L2 ? FLT_MAX : -FLT_MAX;
+        Iq[r] = -1;
+      }
+      __syncthreads();
+    }
+    grid_barrier(p.barrier, bar_target);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Merge `parts` per-shard results [parts][nq][k] into the global top-k (same total order; ids are
+// already global). One block per query. Used after the all-gather of a row-sharded search.
+__global__ void k_topk_merge(const float* __restrict__ Dp, const long long* __restrict__ Ip,
+                             int parts, long long nq, int k, int metric, float* __restrict__ D,
+                             long long* __restrict__ I) {
+  extern __shared__ uint8_t mg_smem[];
+  unsigned long long* key = reinterpret_cast<unsigned long long*>(mg_smem);   // parts*k
+  float* val = reinterpret_cast<float*>(key + parts * k);                     // parts*k
+  long long* idv = reinterpret_cast<long long*>(val + ((parts * k + 1) & ~1)); // parts*k
+  const long long q = blockIdx.x;
+  const int tot = parts * k;
+  for (int i = threadIdx.x; i < tot; i += blockDim.x) {
+    const int pt = i / k, j = i % k;
+    const long long src = (static_cast<long long>(pt) * nq + q) * k + j;
+    const float v = Dp[src];
+    const long long id = Ip[src];
+    val[i] = v;
+    idv[i] = id;
+    // 64-bit ids do not fit the 32-bit tie-break field in general: compare (score, id) directly
+    key[i] = id < 0 ? 0ull : 1ull;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < tot; i += blockDim.x) {
+    if (key[i] == 0ull) continue;
+    const float vi = metric == METRIC_L2 ? -val[i] : val[i];
+    const long long idi = idv[i];
+    int rank = 0;
+    for (int j = 0; j < tot; ++j) {
+      if (key[j] == 0ull) continue;
+      const float vj = metric == METRIC_L2 ? -val[j] : val[j];
+      rank += (vj > vi) || (vj == vi && idv[j] < idi);
+    }
+    if (rank < k) {
+      D[q * k + rank] = val[i];
+      I[q * k + rank] = idi;
+    }
+  }
+  // padding when fewer than k valid entries exist
+  __shared__ int nvalid;
+  if (threadIdx.x == 0) nvalid = 0;
+  __syncthreads();
+  int mine = 0;
+  for (int i = threadIdx.x; i < tot; i += blockDim.x) mine += key[i] != 0ull;
+  atomicAdd(&nvalid, mine);
+  __syncthreads();
+  for (int r = nvalid + threadIdx.x; r < k; r += blockDim.x) {
+    D[q * k + r] = metric == METRIC_L2 ? FLT_MAX : -FLT_MAX;
+    I[q * k + r] = -1;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Neighbour gather (+ optional column permutation) and weighted pool.
+//   gather: out[b][j][:] = base[I[b][perm ? perm[j] : j]][:]              (W == nullptr)
+//   pool:   out[b][h][:] = sum_j W[b][h][j] * base[I[b][j]][:]
+// Replaces the CPU index_select + randperm copy + H2D of src/trainer.py:214-230 and the attn@v
+// shaped reduction of src/model/model.py:69-73. Rows with id < 0 read as zeros.
+__global__ void k_gather_rows(const float* __restrict__ base, const long long* __restrict__ I,
+                              const int* __restrict__ perm, long long B, int k, int d,
+                              float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long w = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (w >= B * k) return;
+  const long long b = w / k;
+  const int j = static_cast<int>(w % k);
+  const long long id = I[b * k + (perm ? perm[j] : j)];
+  float* o = out + w * d;
+  if ((d & 3) == 0 && ((reinterpret_cast<uintptr_t>(base) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
+    const float4* s4 = reinterpret_cast<const float4*>(base + (id < 0 ? 0 : id) * d);
+    float4* o4 = reinterpret_cast<float4*>(o);
+    for (int c = lane; c < (d >> 2); c += 32)
+      o4[c] = id < 0 ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(s4 + c);
+  } else {
+    for (int c = lane; c < d; c += 32) o[c] = id < 0 ? 0.f : base[id * d + c];
+  }
+}
+
+__global__ void k_weighted_pool(const float* __restrict__ base, const long long* __restrict__ I,
+                                const float* __restrict__ W, long long B, int k, int H, int d,
+                                float* __restrict__ out) {
+  extern __shared__ uint8_t pl_smem[];
+  long long* ids = reinterpret_cast<long long*>(pl_smem);  // k
+  float* w = reinterpret_cast<float*>(ids + k);            // H*k
+  const long long b = blockIdx.x;
+  for (int j = threadIdx.x; j < k; j += blockDim.x) ids[j] = I[b * k + j];
+  for (int i = threadIdx.x; i < H * k; i += blockDim.x) w[i] = W[b * H * k + i];
+  __syncthreads();
+  for (int h = 0; h < H; ++h) {
+    for (int c = threadIdx.x; c < d; c += blockDim.x) {
+      float acc = 0.f;
+      for (int j = 0; j < k; ++j) {
+        const long long id = ids[j];
+        if (id >= 0) acc = fmaf(w[h * k + j], __ldg(base + id * d + c), acc);
+      }
+      out[(b * H + h) * d + c] = acc;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Gallery ranking by counting (no sort): rank[q] = number of gallery rows, other than the target
+// and the optional excluded row, that beat the target under (score desc, id asc).
+// Covers the argsort-then-find of src/eval_utils.py:1008-1067 (COCO / FashionIQ / CIRR).
+__global__ void __launch_bounds__(256)
+k_gallery_rank(const float* __restrict__ Q, long long nq, const float* __restrict__ G, long long ng,
+               int d, const long long* __restrict__ target, const long long* __restrict__ exclude,
+               long long* __restrict__ rank_out) {
+  extern __shared__ uint8_t gr_smem[];
+  float* qv = reinterpret_cast<float*>(gr_smem);
+  __shared__ int total;
+  const long long q = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) qv[c] = Q[q * d + c];
+  if (threadIdx.x == 0) total = 0;
+  __syncthreads();
+  const long long t = target[q];
+  const long long ex = exclude ? exclude[q] : -1;
+  const float st = warp_exact_score(qv, G + t * d, d, METRIC_IP, lane);
+  int cnt = 0;
+  for (long long g = warp; g < ng; g += nw) {
+    if (g == t || g == ex) continue;
+    const float s = warp_exact_score(qv, G + g * d, d, METRIC_IP, lane);
+    cnt += (s > st) || (s == st && g < t);
+  }
+  if (lane == 0) atomicAdd(&total, cnt);
+  __syncthreads();
+  if (threadIdx.x == 0) rank_out[q] = total;
+}
+
+// hits[q][i] = #{ j < ks[i] : labels[I[q][j]] == qlabel[q] }   (ImageNet-domain R@k / P@k,
+// src/eval_utils.py:1107-1118 without the [100 x G] scatter masks)
+__global__ void k_label_hits(const long long* __restrict__ I, long long nq, int kmax,
+                             const long long* __restrict__ labels, const long long* __restrict__ qlabel,
+                             const int* __restrict__ ks, int nks, int* __restrict__ hits) {
+  const long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  const long long ql = qlabel[q];
+  int acc = 0, ki = 0;
+  for (int j = 0; j < kmax && ki < nks; ++j) {
+    const long long id = I[q * kmax + j];
+    acc += (id >= 0 && labels[id] == ql);
+    while (ki < nks && j + 1 == ks[ki]) hits[q * nks + ki++] = acc;
+  }
+  while (ki < nks) hits[q * nks + ki++] = acc;
+}
+
+}  // namespace keds

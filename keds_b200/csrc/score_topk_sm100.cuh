@@ -1,0 +1,339 @@
+// Fused bf16 scoring GEMM + per-query candidate selection for sm_100a.
+//
+// Replaces the "SGEMM tile -> HBM -> k-select" pair inside the Faiss GPU flat index that KEDs
+// calls at src/trainer.py:213,221,271 and src/eval_utils.py:169,177. The [queries x rows] score
+// matrix lives only in TMEM; what reaches HBM is, per (row slice, query), a short list of
+// candidate (approx score, row id) pairs plus the slice's drop threshold.
+//
+//   warp 0        TMA producer: per k-block one {64 x 128} query box + one {64 x 256} row box
+//   warp 1        tcgen05.mma issuer (one lane), owns the TMEM allocation
+//   warps 2..5    epilogue: TMEM lane == query, so one thread owns one query's scores
+//
+// Tile: M = 128 queries (TMEM lanes) x N = 256 DB rows (TMEM columns), K streamed in 64-wide
+// k-blocks (one 128-byte swizzle row). Two 256-column accumulators double-buffer MMA vs epilogue.
+#pragma once
+#include "ptx.cuh"
+
+namespace keds {
+
+constexpr int BM = 128;
+constexpr int BN = 256;
+constexpr int BK = 64;
+constexpr int UK = 16;
+constexpr int NSTAGE = 3;
+constexpr int LKEEP = 16;   // a compaction keeps scores above the LKEEP-th best seen
+constexpr int CAP = 64;     // candidate slots per (item, query)
+constexpr int CHUNK = 32;   // TMEM columns per tcgen05.ld
+constexpr int SCORE_THREADS = 192;
+constexpr uint32_t Q_STAGE_BYTES = BM * BK * 2;
+constexpr uint32_t X_STAGE_BYTES = BN * BK * 2;
+constexpr uint32_t STAGE_BYTES = Q_STAGE_BYTES + X_STAGE_BYTES;
+constexpr uint32_t CAND_WARP_BYTES = CAP * 32 * 8;
+constexpr uint32_t TMEM_COLS = 512;
+
+// dynamic shared memory map (offsets from a 1024-aligned base)
+constexpr uint32_t SM_STAGES = 0;
+constexpr uint32_t SM_CAND = SM_STAGES + NSTAGE * STAGE_BYTES;
+constexpr uint32_t SM_BIAS = SM_CAND + 4 * CAND_WARP_BYTES;
+constexpr uint32_t SM_BARS = SM_BIAS + 2 * BN * 4;
+constexpr uint32_t SM_END = SM_BARS + 128;
+constexpr uint32_t SCORE_SMEM_BYTES = SM_END + 1024;  // + alignment slack
+
+struct ScoreParams {
+  int n_db;          // 1 or 2 databases scored against the same queries
+  int n_qt;          // query tiles of BM
+  int S;             // row slices per (db, query tile)
+  int n_items;       // n_db * S * n_qt ; item = ((db * S) + s) * n_qt + qt
+  int kblocks;       // d_pad / BK
+  int nq;            // live queries
+  int n_rows[2];     // rows per database
+  int n_tiles[2];    // ceil(n_rows / BN)
+  const float* bias[2];  // nullable; additive per-row bias padded with -inf to n_tiles * BN
+  uint2* cand;       // [n_items][CAP][BM] {approx score bits, row id}
+  int* cand_cnt;     // [n_items][BM]
+  float* cand_theta; // [n_items][BM]  everything the slice dropped scored <= theta
+  uint32_t* err;     // device error word (0 = ok)
+  float* dump;       // debug: full approx scores [n_db][nq][ld_dump], or nullptr
+  long long ld_dump;
+};
+
+struct ItemCoord {
+  int db, s, qt, t0, t1;
+};
+
+__device__ __forceinline__ ItemCoord decode_item(const ScoreParams& p, int item) {
+  ItemCoord c;
+  c.qt = item % p.n_qt;
+  const int t = item / p.n_qt;
+  c.s = t % p.S;
+  c.db = t / p.S;
+  const long long T = p.n_tiles[c.db];
+  c.t0 = static_cast<int>((T * c.s) / p.S);
+  c.t1 = static_cast<int>((T * (c.s + 1)) / p.S);
+  return c;
+}
+
+__device__ __forceinline__ void sts64(uint32_t addr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+  uint2 r;
+  asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(addr) : "memory");
+  return r;
+}
+__device__ __forceinline__ float lds32f(uint32_t addr) {
+  float r;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(addr) : "memory");
+  return r;
+}
+
+struct CandState {
+  int cnt;
+  float theta;
+};
+
+// Per-thread compaction of one query's candidate slots (all 32 lanes of a warp run it in lock
+// step on their own columns of the warp's interleaved buffer): find the LKEEP-th best score with
+// a register sorting network, raise theta to it, keep only strictly better entries.
+__device__ __noinline__ CandState compact_candidates(uint32_t slot0, int cnt, float theta) {
+  float s[CAP];
+#pragma unroll
+  for (int e = 0; e < CAP; ++e) s[e] = (e < cnt) ? lds32f(slot0 + e * 256) : -INFINITY;
+#pragma unroll
+  for (int k = 2; k <= CAP; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+      for (int i = 0; i < CAP; ++i) {
+        const int l = i ^ j;
+        if (l > i) {
+          const float a = s[i], b = s[l];
+          const float mx = fmaxf(a, b), mn = fminf(a, b);
+          const bool desc = (i & k) == 0;  // descending overall
+          s[i] = desc ? mx : mn;
+          s[l] = desc ? mn : mx;
+        }
+      }
+    }
+  }
+  theta = fmaxf(theta, s[LKEEP - 1]);
+  int w = 0;
+  for (int e = 0; e < cnt; ++e) {
+    const uint2 en = lds64(slot0 + e * 256);
+    if (__uint_as_float(en.x) > theta) {
+      sts64(slot0 + w * 256, en.x, en.y);
+      ++w;
+    }
+  }
+  CandState r;
+  r.cnt = w;
+  r.theta = theta;
+  return r;
+}
+
+__global__ void __launch_bounds__(SCORE_THREADS, 1)
+k_score_topk(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_x0,
+             const __grid_constant__ CUtensorMap tm_x1, const ScoreParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (sbase - smem_u32(smem_raw));
+
+  const uint32_t bars = sbase + SM_BARS;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (NSTAGE + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * NSTAGE + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * NSTAGE + 2 + a); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + SM_BARS + 96);
+  volatile uint32_t* dead = reinterpret_cast<volatile uint32_t*>(gbase + SM_BARS + 100);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&tm_q);
+    prefetch_tensormap(&tm_x0);
+    if (p.n_db > 1) prefetch_tensormap(&tm_x1);
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);
+    }
+    *dead = 0;
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const ItemCoord c = decode_item(p, item);
+        const CUtensorMap* tmx = c.db == 0 ? &tm_x0 : &tm_x1;
+        for (int tile = c.t0; tile < c.t1; ++tile) {
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1u, dead, p.err, 0x100u + stage);
+            const uint32_t sq = sbase + SM_STAGES + stage * STAGE_BYTES;
+            const uint32_t sx = sq + Q_STAGE_BYTES;
+            mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
+            tma_load_2d(sq, &tm_q, full_bar(stage), kb * BK, c.qt * BM, kEvictLast);
+            tma_load_2d(sx, tmx, full_bar(stage), kb * BK, tile * BN,
+                        p.n_qt > 1 ? kEvictNormal : kEvictFirst);
+            if (++stage == NSTAGE) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = idesc_bf16_f32(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const ItemCoord c = decode_item(p, item);
+        for (int tile = c.t0; tile < c.t1; ++tile) {
+          mbar_wait(tempty_bar(acc), acc_phase ^ 1u, dead, p.err, 0x200u + acc);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            mbar_wait(full_bar(stage), phase, dead, p.err, 0x300u + stage);
+            tc_fence_after();
+            const uint32_t sq = sbase + SM_STAGES + stage * STAGE_BYTES;
+            const uint64_t adesc = smem_desc_sw128(sq);
+            const uint64_t bdesc = smem_desc_sw128(sq + Q_STAGE_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / UK; ++k) {
+              // +32 bytes per K=16 step inside the 128-byte swizzle row: +2 in 16-byte units
+              umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(empty_bar(stage));
+            if (++stage == NSTAGE) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+          umma_commit(tfull_bar(acc));
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1u;
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (lane == query)
+    const int quad = warp & 3;                // TMEM lane quadrant this warp may read
+    const int q_local = quad * 32 + lane;
+    const uint32_t wbuf = sbase + SM_CAND + static_cast<uint32_t>(warp - 2) * CAND_WARP_BYTES;
+    const uint32_t slot0 = wbuf + lane * 8;   // entry e of this lane lives at slot0 + e * 256
+    float* sbias = reinterpret_cast<float*>(gbase + SM_BIAS);
+    const int et = threadIdx.x - 64;          // 0..127 among epilogue threads
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      const ItemCoord c = decode_item(p, item);
+      const int q_glob = c.qt * BM + q_local;
+      const bool active = q_glob < p.nq;
+      float theta = active ? -INFINITY : INFINITY;
+      int cnt = 0;
+      const float* bias = p.bias[c.db];
+      const int n_rows = p.n_rows[c.db];
+      for (int tile = c.t0; tile < c.t1; ++tile) {
+        if (bias != nullptr) {
+          sbias[acc * BN + et] = bias[static_cast<long long>(tile) * BN + et];
+          sbias[acc * BN + 128 + et] = bias[static_cast<long long>(tile) * BN + 128 + et];
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        mbar_wait(tfull_bar(acc), acc_phase, dead, p.err, 0x400u + acc);
+        tc_fence_after();
+        const uint32_t taddr =
+            tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN);
+        const int nvalid = n_rows - tile * BN;  // >= BN for full tiles
+#pragma unroll 1
+        for (int ch = 0; ch < BN / CHUNK; ++ch) {
+          uint32_t v[CHUNK];
+          tmem_ld32(taddr + ch * CHUNK, v);
+          tmem_ld_wait(v);
+          if (bias != nullptr) {
+            const float4* b4 = reinterpret_cast<const float4*>(sbias + acc * BN + ch * CHUNK);
+#pragma unroll
+            for (int j4 = 0; j4 < CHUNK / 4; ++j4) {
+              const float4 b = b4[j4];
+              v[4 * j4 + 0] = __float_as_uint(__uint_as_float(v[4 * j4 + 0]) + b.x);
+              v[4 * j4 + 1] = __float_as_uint(__uint_as_float(v[4 * j4 + 1]) + b.y);
+              v[4 * j4 + 2] = __float_as_uint(__uint_as_float(v[4 * j4 + 2]) + b.z);
+              v[4 * j4 + 3] = __float_as_uint(__uint_as_float(v[4 * j4 + 3]) + b.w);
+            }
+          } else if (nvalid < BN) {
+            // zero-filled out-of-range rows score 0 under IP: take them out of the race
+#pragma unroll
+            for (int j = 0; j < CHUNK; ++j)
+              if (ch * CHUNK + j >= nvalid) v[j] = 0xff800000u;  // -inf
+          }
+          const uint32_t idx0 = static_cast<uint32_t>(tile * BN + ch * CHUNK);
+          if (p.dump != nullptr && active) {
+            float* drow = p.dump + (static_cast<long long>(c.db) * p.nq + q_glob) * p.ld_dump;
+#pragma unroll
+            for (int j = 0; j < CHUNK; ++j)
+              if (static_cast<int>(idx0) + j < n_rows) drow[idx0 + j] = __uint_as_float(v[j]);
+          }
+          uint32_t wptr = slot0 + static_cast<uint32_t>(cnt) * 256u;
+#pragma unroll
+          for (int j = 0; j < CHUNK; ++j) {
+            if (__uint_as_float(v[j]) > theta) {
+              sts64(wptr, v[j], idx0 + j);
+              wptr += 256u;
+            }
+          }
+          cnt = static_cast<int>((wptr - slot0) >> 8);
+          if (__any_sync(0xffffffffu, cnt > CAP - CHUNK)) {
+            const CandState st = compact_candidates(slot0, cnt, theta);
+            cnt = st.cnt;
+            theta = st.theta;
+          }
+        }
+        // accumulator drained: hand the TMEM buffer back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+      // flush this item's candidates: [item][e][query] so each store instruction is one 256-B row
+      int maxc = cnt;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) maxc = max(maxc, __shfl_xor_sync(0xffffffffu, maxc, o));
+      uint2* cbase = p.cand + static_cast<long long>(item) * CAP * BM + q_local;
+      for (int e = 0; e < maxc; ++e) {
+        if (e < cnt) cbase[static_cast<long long>(e) * BM] = lds64(slot0 + e * 256);
+      }
+      p.cand_cnt[static_cast<long long>(item) * BM + q_local] = cnt;
+      p.cand_theta[static_cast<long long>(item) * BM + q_local] = theta;
+      __syncwarp();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace keds

@@ -1,0 +1,391 @@
+"""Faiss-shaped index objects over libkeds_knn.so.
+
+Mirrors exactly the slice of the Faiss Python API that KEDs touches:
+
+    faiss.IndexFlatL2(768) / IndexFlatIP          src/main.py:74,80  src/eval_retrieval.py:291,294
+    faiss.StandardGpuResources()                   src/main.py:73
+    faiss.index_cpu_to_gpu(res, gpu, index)        src/main.py:76,82
+    faiss.index_cpu_to_all_gpus(index)             src/eval_retrieval.py:292,295
+    faiss.get_num_gpus()                           src/eval_retrieval.py:289
+    index.add(x) / index.search(x, k) / .ntotal    src/main.py:78,83  src/trainer.py:213,221,271
+
+so that `import keds_b200.faiss_compat as faiss` leaves the reference's call sites unchanged.
+numpy in -> numpy out (float32 D, int64 I) like Faiss; as an extension a CUDA torch.Tensor in gives
+CUDA tensors out with no host hop, ordered on torch's current stream.
+
+There is no CPU search: a flat index that has not been moved to a GPU can only collect rows.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _capi
+
+try:  # torch is plumbing (device tensors, streams); numpy-only use works without it
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+METRIC_INNER_PRODUCT = _capi.METRIC_IP
+METRIC_L2 = _capi.METRIC_L2
+
+
+def _is_tensor(x) -> bool:
+    return torch is not None and isinstance(x, torch.Tensor)
+
+
+def _as_f32_matrix(x, d: int, what: str) -> np.ndarray:
+    """Faiss' SWIG layer semantics: 2-D, second dim == d, coerced to C-contiguous float32."""
+    a = np.asarray(x)
+    if a.ndim != 2:
+        raise ValueError(f"{what}: expected a 2-D array, got shape {a.shape}")
+    if a.shape[1] != d:
+        raise AssertionError(f"{what}: second dimension {a.shape[1]} != index dimension {d}")
+    if a.dtype != np.float32:
+        raise TypeError(f"{what}: expected float32, got {a.dtype}")
+    return np.ascontiguousarray(a)
+
+
+def _stream_ptr(device: int) -> int:
+    if torch is not None and torch.cuda.is_available():
+        return int(torch.cuda.current_stream(device).cuda_stream)
+    return 0
+
+
+class StandardGpuResources:
+    """Placeholder with Faiss' name: the native handle owns its own device memory."""
+
+    def __init__(self) -> None:
+        self.temp_memory = None
+
+    def setTempMemory(self, nbytes: int) -> None:  # noqa: N802 (Faiss spelling)
+        self.temp_memory = int(nbytes)
+
+    def noTempMemory(self) -> None:  # noqa: N802
+        self.temp_memory = 0
+
+
+class GpuClonerOptions:
+    def __init__(self) -> None:
+        self.useFloat16 = False
+
+
+class GpuMultipleClonerOptions(GpuClonerOptions):
+    def __init__(self) -> None:
+        super().__init__()
+        self.shard = False
+
+
+class IndexFlat:
+    """Host-side flat index: collects rows until it is cloned to a GPU (no CPU search)."""
+
+    def __init__(self, d: int, metric: int = METRIC_L2) -> None:
+        if int(d) <= 0:
+            raise ValueError("dimension must be positive")
+        self.d = int(d)
+        self.metric_type = int(metric)
+        self.is_trained = True
+        self._blocks: List[np.ndarray] = []
+
+    @property
+    def ntotal(self) -> int:
+        return int(sum(b.shape[0] for b in self._blocks))
+
+    def add(self, x) -> None:
+        self._blocks.append(_as_f32_matrix(x, self.d, "add").copy())
+
+    def reset(self) -> None:
+        self._blocks = []
+
+    def search(self, x, k):
+        raise RuntimeError(
+            "keds_b200 has no CPU search path: move the index to a GPU with "
+            "index_cpu_to_gpu / index_cpu_to_all_gpus first"
+        )
+
+
+class IndexFlatIP(IndexFlat):
+    def __init__(self, d: int) -> None:
+        super().__init__(d, METRIC_INNER_PRODUCT)
+
+
+class IndexFlatL2(IndexFlat):
+    def __init__(self, d: int) -> None:
+        super().__init__(d, METRIC_L2)
+
+
+class GpuIndexFlat:
+    """One native index on one B200. `search` == Faiss' contract (best first, -1 padding)."""
+
+    def __init__(self, d: int, metric: int = METRIC_L2, device: int = 0) -> None:
+        self._lib = _capi.load()
+        self.d = int(d)
+        self.metric_type = int(metric)
+        self.device = int(device)
+        self.is_trained = True
+        h = C.c_void_p()
+        _capi.check(self._lib.keds_index_create(self.d, self.metric_type, self.device, C.byref(h)))
+        self._h = h
+
+    # -- lifecycle
+    def __del__(self) -> None:
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            try:
+                self._lib.keds_index_free(h)
+            except Exception:
+                pass
+            self._h = None
+
+    @property
+    def ntotal(self) -> int:
+        return int(self._lib.keds_index_ntotal(self._h))
+
+    def reset(self) -> None:
+        _capi.check(self._lib.keds_index_reset(self._h))
+
+    def set_id_offset(self, offset: int) -> None:
+        _capi.check(self._lib.keds_index_set_id_offset(self._h, int(offset)))
+
+    def set_eps_scale(self, scale: float) -> None:
+        _capi.check(self._lib.keds_index_set_eps_scale(self._h, float(scale)))
+
+    # -- add
+    def add(self, x) -> None:
+        if _is_tensor(x):
+            if x.dim() != 2 or x.shape[1] != self.d:
+                raise AssertionError(f"add: shape {tuple(x.shape)} does not match d={self.d}")
+            if x.dtype != torch.float32:
+                raise TypeError(f"add: expected float32, got {x.dtype}")
+            x = x.contiguous()
+            if x.is_cuda:
+                torch.cuda.current_stream(x.device).synchronize()
+            _capi.check(self._lib.keds_index_add(self._h, x.data_ptr(), x.shape[0]))
+            return
+        a = _as_f32_matrix(x, self.d, "add")
+        _capi.check(self._lib.keds_index_add(self._h, a.ctypes.data, a.shape[0]))
+
+    # -- search
+    def search(self, x, k: int, flags: int = 0):
+        k = int(k)
+        if k <= 0:
+            raise ValueError("k must be positive")
+        if _is_tensor(x) and x.is_cuda:
+            q = self._check_q_tensor(x)
+            D = torch.empty((q.shape[0], k), dtype=torch.float32, device=q.device)
+            I = torch.empty((q.shape[0], k), dtype=torch.int64, device=q.device)
+            _capi.check(
+                self._lib.keds_index_search_ex(
+                    self._h, q.data_ptr(), q.shape[0], k, D.data_ptr(), I.data_ptr(), flags,
+                    _stream_ptr(self.device),
+                )
+            )
+            return D, I
+        a = _as_f32_matrix(x.numpy() if _is_tensor(x) else x, self.d, "search")
+        D = np.empty((a.shape[0], k), dtype=np.float32)
+        I = np.empty((a.shape[0], k), dtype=np.int64)
+        _capi.check(
+            self._lib.keds_index_search_ex(
+                self._h, a.ctypes.data, a.shape[0], k, D.ctypes.data, I.ctypes.data, flags,
+                _stream_ptr(self.device),
+            )
+        )
+        return D, I
+
+    def _check_q_tensor(self, x):
+        if x.dim() != 2 or x.shape[1] != self.d:
+            raise AssertionError(f"search: shape {tuple(x.shape)} does not match d={self.d}")
+        if x.dtype != torch.float32:
+            raise TypeError(f"search: expected float32, got {x.dtype}")
+        if x.device.index != self.device:
+            raise ValueError(f"search: query on cuda:{x.device.index}, index on cuda:{self.device}")
+        return x.contiguous()
+
+    def sync(self) -> None:
+        """Wait for the last asynchronous search and raise if the device reported an error."""
+        _capi.check(self._lib.keds_index_sync(self._h, _stream_ptr(self.device)))
+
+    def last_stats(self) -> dict:
+        st = _capi.SearchStats()
+        _capi.check(self._lib.keds_index_last_stats(self._h, C.byref(st)))
+        return {
+            "n_flagged": [int(st.n_flagged[0]), int(st.n_flagged[1])],
+            "slices": int(st.slices),
+            "items": int(st.items),
+            "grid": int(st.grid),
+            "exact_only": int(st.exact_only),
+            "launches": int(st.launches),
+            "err_word": int(st.err_word),
+        }
+
+    def rows_ptr(self) -> int:
+        """Device address of the resident fp32 rows [ntotal, d]."""
+        return int(self._lib.keds_index_rows(self._h) or 0)
+
+    def debug_scores(self, q):
+        """bf16 tensor-core scores of q against every row (test hook)."""
+        q = self._check_q_tensor(q)
+        out = torch.empty((q.shape[0], self.ntotal), dtype=torch.float32, device=q.device)
+        _capi.check(
+            self._lib.keds_debug_scores(self._h, q.data_ptr(), q.shape[0], out.data_ptr(),
+                                        _stream_ptr(self.device))
+        )
+        return out
+
+
+def search2(a: GpuIndexFlat, b: GpuIndexFlat, x, k: int, flags: int = 0):
+    """Both databases against one query batch in one pass (src/trainer.py:213 + :221)."""
+    lib = _capi.load()
+    k = int(k)
+    if _is_tensor(x) and x.is_cuda:
+        q = a._check_q_tensor(x)
+        outs = []
+        for _ in range(2):
+            outs.append(torch.empty((q.shape[0], k), dtype=torch.float32, device=q.device))
+            outs.append(torch.empty((q.shape[0], k), dtype=torch.int64, device=q.device))
+        _capi.check(
+            lib.keds_index_search2(a._h, b._h, q.data_ptr(), q.shape[0], k, outs[0].data_ptr(),
+                                   outs[1].data_ptr(), outs[2].data_ptr(), outs[3].data_ptr(),
+                                   flags, _stream_ptr(a.device))
+        )
+        return (outs[0], outs[1]), (outs[2], outs[3])
+    arr = _as_f32_matrix(x.numpy() if _is_tensor(x) else x, a.d, "search2")
+    Da = np.empty((arr.shape[0], k), np.float32)
+    Ia = np.empty((arr.shape[0], k), np.int64)
+    Db = np.empty_like(Da)
+    Ib = np.empty_like(Ia)
+    _capi.check(
+        lib.keds_index_search2(a._h, b._h, arr.ctypes.data, arr.shape[0], k, Da.ctypes.data,
+                               Ia.ctypes.data, Db.ctypes.data, Ib.ctypes.data, flags,
+                               _stream_ptr(a.device))
+    )
+    return (Da, Ia), (Db, Ib)
+
+
+class IndexReplicas:
+    """Faiss' default for index_cpu_to_all_gpus: a full copy per GPU, queries split across them.
+    Results are identical to a single-GPU search (src/eval_retrieval.py:292,295)."""
+
+    def __init__(self, d: int, metric: int, devices: Sequence[int]) -> None:
+        self.d, self.metric_type = int(d), int(metric)
+        self.subs = [GpuIndexFlat(d, metric, dev) for dev in devices]
+        self.is_trained = True
+
+    @property
+    def ntotal(self) -> int:
+        return self.subs[0].ntotal
+
+    def add(self, x) -> None:
+        for s in self.subs:
+            s.add(x)
+
+    def reset(self) -> None:
+        for s in self.subs:
+            s.reset()
+
+    def search(self, x, k: int):
+        a = _as_f32_matrix(x.cpu().numpy() if _is_tensor(x) else x, self.d, "search")
+        n = a.shape[0]
+        bounds = np.linspace(0, n, len(self.subs) + 1).astype(np.int64)
+        Ds, Is = [], []
+        for s, lo, hi in zip(self.subs, bounds[:-1], bounds[1:]):
+            if hi > lo:
+                D, I = s.search(a[lo:hi], k)
+                Ds.append(D)
+                Is.append(I)
+        if not Ds:
+            return np.empty((0, k), np.float32), np.empty((0, k), np.int64)
+        return np.concatenate(Ds), np.concatenate(Is)
+
+
+class IndexShards:
+    """Row shards across the GPUs of one process (GpuMultipleClonerOptions.shard=True): every GPU
+    searches its rows for all queries, labels are global, a merge kernel picks the global top-k.
+    The multi-process (one rank per GPU, NCCL all-gather) form is keds_b200.sharded.ShardedIndex."""
+
+    def __init__(self, d: int, metric: int, devices: Sequence[int]) -> None:
+        self.d, self.metric_type = int(d), int(metric)
+        self.devices = list(devices)
+        self.subs = [GpuIndexFlat(d, metric, dev) for dev in devices]
+        self._ntotal = 0
+        self.is_trained = True
+
+    @property
+    def ntotal(self) -> int:
+        return self._ntotal
+
+    def add(self, x) -> None:
+        a = _as_f32_matrix(x.cpu().numpy() if _is_tensor(x) else x, self.d, "add")
+        if self._ntotal != 0:
+            raise RuntimeError("IndexShards.add: add all rows in one call (contiguous row ranges)")
+        n, R = a.shape[0], len(self.subs)
+        per = -(-n // R)
+        for r, s in enumerate(self.subs):
+            lo, hi = min(n, r * per), min(n, (r + 1) * per)
+            s.set_id_offset(lo)
+            if hi > lo:
+                s.add(a[lo:hi])
+        self._ntotal = n
+
+    def reset(self) -> None:
+        for s in self.subs:
+            s.reset()
+        self._ntotal = 0
+
+    def search(self, x, k: int):
+        if torch is None:
+            raise RuntimeError("IndexShards needs torch for cross-device staging")
+        a = _as_f32_matrix(x.cpu().numpy() if _is_tensor(x) else x, self.d, "search")
+        lib = _capi.load()
+        nq, R = a.shape[0], len(self.subs)
+        dev0 = torch.device("cuda", self.devices[0])
+        Dp = torch.empty((R, nq, k), dtype=torch.float32, device=dev0)
+        Ip = torch.empty((R, nq, k), dtype=torch.int64, device=dev0)
+        for r, s in enumerate(self.subs):
+            q = torch.from_numpy(a).to(torch.device("cuda", s.device))
+            with torch.cuda.device(s.device):
+                D, I = s.search(q, k)
+                s.sync()
+            Dp[r].copy_(D)
+            Ip[r].copy_(I)
+        D = torch.empty((nq, k), dtype=torch.float32, device=dev0)
+        I = torch.empty((nq, k), dtype=torch.int64, device=dev0)
+        with torch.cuda.device(dev0):
+            _capi.check(
+                lib.keds_topk_merge(Dp.data_ptr(), Ip.data_ptr(), R, nq, k, self.metric_type,
+                                    D.data_ptr(), I.data_ptr(), _stream_ptr(self.devices[0]))
+            )
+            torch.cuda.synchronize(dev0)
+        return D.cpu().numpy(), I.cpu().numpy()
+
+
+def get_num_gpus() -> int:
+    return int(_capi.load().keds_device_count())
+
+
+def index_cpu_to_gpu(res, device: int, index: IndexFlat, options=None) -> GpuIndexFlat:
+    g = GpuIndexFlat(index.d, index.metric_type, int(device))
+    for blk in index._blocks:
+        g.add(blk)
+    return g
+
+
+def index_cpu_to_all_gpus(index: IndexFlat, co: Optional[GpuMultipleClonerOptions] = None, ngpu: int = -1):
+    n = get_num_gpus() if ngpu is None or ngpu < 0 else int(ngpu)
+    if n <= 0:
+        raise RuntimeError("no CUDA device: keds_b200 has no CPU fallback")
+    devices = list(range(n))
+    if n == 1:
+        return index_cpu_to_gpu(None, 0, index)
+    cls = IndexShards if (co is not None and getattr(co, "shard", False)) else IndexReplicas
+    multi = cls(index.d, index.metric_type, devices)
+    if index._blocks:
+        multi.add(np.concatenate(index._blocks))
+    return multi
+
+
+def index_gpu_to_cpu(index) -> IndexFlat:
+    raise RuntimeError("keds_b200 keeps no CPU search path; rebuild the index from the .pt database")
