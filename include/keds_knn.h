@@ -36,6 +36,8 @@ enum keds_status {
 /* search flags */
 #define KEDS_SEARCH_EXACT_ONLY 1u  /* skip the bf16 tensor-core pass, answer with the fp32 scan */
 #define KEDS_SEARCH_NO_FALLBACK 2u /* debugging: do not run the exact fallback for flagged queries */
+#define KEDS_SEARCH_FORCE_IP 4u    /* rank by inner product whatever the index metric (the reference's
+                                      use_faiss=False branch, src/trainer.py:246-257) */
 
 typedef struct keds_search_stats {
   int32_t n_flagged[2];  /* queries whose certificate failed (answered by the exact fallback) */
@@ -84,6 +86,11 @@ int keds_index_search2(keds_index_t* a, keds_index_t* b, const float* q, int64_t
 /* Wait for the last asynchronous search on idx and report its device status. */
 int keds_index_sync(keds_index_t* idx, void* cuda_stream);
 int keds_index_last_stats(const keds_index_t* idx, keds_search_stats* out);
+/* Per-launch CUDA-event timing of the scoring kernel on the caller's stream (bench.py's roofline
+ * leg). set_profiling(1) starts recording; profile() waits for the recorded launches and returns
+ * their summed duration in ms and their count, then clears the record. */
+int keds_index_set_profiling(keds_index_t* idx, int enable);
+int keds_index_profile(keds_index_t* idx, double* score_ms_total, int64_t* score_launches);
 
 /* ---- neighbour gather / weighted pool ---------------------------------------------------------
  * W == NULL:  out[b][j][:] = base[I[b][perm ? perm[j] : j]][:]   (out: [B][k][d])
@@ -101,6 +108,11 @@ int keds_gather_pool(const float* base, int64_t n_base, const int64_t* I, const 
  * top-k with the same ordering rule. New relative to the reference (replicas only). */
 int keds_topk_merge(const float* D_parts, const int64_t* I_parts, int parts, int64_t nq, int k,
                     int metric, float* D, int64_t* I, void* cuda_stream);
+/* Same, with part p at D_parts + p*stride_d (floats) and I_parts + p*stride_i (int64s): lets one
+ * packed all-gather buffer ([rank][D block | I block]) be merged in place. */
+int keds_topk_merge_strided(const float* D_parts, const int64_t* I_parts, int64_t stride_d,
+                            int64_t stride_i, int parts, int64_t nq, int k, int metric, float* D,
+                            int64_t* I, void* cuda_stream);
 
 /* ---- gallery ranking --------------------------------------------------------------------------
  * rank_out[q] = #{ g != target[q], g != exclude[q] : (s(q,g), -g) > (s(q,target), -target) } with

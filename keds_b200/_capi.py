@@ -13,6 +13,7 @@ METRIC_IP = 0
 METRIC_L2 = 1
 SEARCH_EXACT_ONLY = 1
 SEARCH_NO_FALLBACK = 2
+SEARCH_FORCE_IP = 4
 
 
 class SearchStats(C.Structure):
@@ -52,11 +53,17 @@ SIGNATURES = {
     ),
     "keds_index_sync": (C.c_int, [_vp, _vp]),
     "keds_index_last_stats": (C.c_int, [_vp, C.POINTER(SearchStats)]),
+    "keds_index_set_profiling": (C.c_int, [_vp, C.c_int]),
+    "keds_index_profile": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "keds_gather_pool": (
         C.c_int,
         [_vp, C.c_int64, _vp, _vp, _vp, C.c_int64, C.c_int, C.c_int, C.c_int, _vp, _vp],
     ),
     "keds_topk_merge": (C.c_int, [_vp, _vp, C.c_int, C.c_int64, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "keds_topk_merge_strided": (
+        C.c_int,
+        [_vp, _vp, C.c_int64, C.c_int64, C.c_int, C.c_int64, C.c_int, C.c_int, _vp, _vp, _vp],
+    ),
     "keds_gallery_rank": (C.c_int, [_vp, C.c_int64, _vp, C.c_int64, C.c_int, _vp, _vp, _vp, _vp]),
     "keds_label_hits": (C.c_int, [_vp, C.c_int64, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp]),
     "keds_debug_scores": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp]),

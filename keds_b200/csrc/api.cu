@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "aux_kernels.cuh"
 
@@ -158,6 +159,10 @@ struct keds_index {
   int64_t tm_q_rows = 0;
   keds_search_stats stats;
   bool attrs_set = false;
+  // optional per-launch timing of the scoring kernel (bench.py's roofline leg)
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_ev;  // pairs: [2i] before, [2i+1] after
+  size_t prof_used = 0;
 };
 
 namespace {
@@ -224,12 +229,12 @@ int ensure_q_map(keds_index* ix, int64_t rows_needed) {
 }
 
 int launch_exact(keds_index* ix, keds_index* dbix, int dbi, const float* q_dev, int64_t nq, int k,
-                 float* D, long long* I, cudaStream_t st) {
+                 float* D, long long* I, int metric, cudaStream_t st) {
   ExactParams ep;
   ep.x_f32 = dbix->x_f32.as<float>();
   ep.n_rows = dbix->n;
   ep.d = ix->d;
-  ep.metric = ix->metric;
+  ep.metric = metric;
   ep.k = k;
   ep.nq = static_cast<int>(nq);
   ep.q_f32 = q_dev;
@@ -263,6 +268,7 @@ int launch_exact(keds_index* ix, keds_index* dbix, int dbi, const float* q_dev, 
 int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int k, float* D[2],
                 long long* I[2], uint32_t flags, cudaStream_t st, float* dump, int64_t ld_dump) {
   keds_index* a = ix[0];
+  const int metric = (flags & KEDS_SEARCH_FORCE_IP) ? METRIC_IP : a->metric;
   CKS(set_kernel_attrs(a));
   CKS(a->ctrl.ensure(CTRL_WORDS * 4));
   CK(cudaMemsetAsync(a->ctrl.p, 0, CTRL_WORDS * 4, st));
@@ -317,7 +323,7 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
     for (int i = 0; i < n_db; ++i) {
       sp.n_rows[i] = static_cast<int>(ix[i]->n);
       sp.n_tiles[i] = static_cast<int>((ix[i]->n + BN - 1) / BN);
-      sp.bias[i] = a->metric == METRIC_L2 ? ix[i]->bias.as<float>() : nullptr;
+      sp.bias[i] = metric == METRIC_L2 ? ix[i]->bias.as<float>() : nullptr;
     }
     sp.cand = a->cand.as<uint2>();
     sp.cand_cnt = a->cand_cnt.as<int>();
@@ -325,8 +331,22 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
     sp.err = a->ctrl.as<uint32_t>() + 2;
     sp.dump = dump;
     sp.ld_dump = ld_dump;
+    cudaEvent_t ev_after = nullptr;
+    if (a->profiling) {
+      if (a->prof_used + 2 > a->prof_ev.size()) {
+        cudaEvent_t e0, e1;
+        CK(cudaEventCreate(&e0));
+        CK(cudaEventCreate(&e1));
+        a->prof_ev.push_back(e0);
+        a->prof_ev.push_back(e1);
+      }
+      CK(cudaEventRecord(a->prof_ev[a->prof_used], st));
+      ev_after = a->prof_ev[a->prof_used + 1];
+      a->prof_used += 2;
+    }
     k_score_topk<<<pl.grid, SCORE_THREADS, SCORE_SMEM_BYTES, st>>>(
         a->tm_q, ix[0]->tm_x, n_db > 1 ? ix[1]->tm_x : ix[0]->tm_x, sp);
+    if (ev_after) CK(cudaEventRecord(ev_after, st));
     a->stats.launches++;
     CK(cudaGetLastError());
     if (dump) return 0;
@@ -339,7 +359,7 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
     rp.nq = static_cast<int>(nq);
     rp.k = k;
     rp.d = a->d;
-    rp.metric = a->metric;
+    rp.metric = metric;
     rp.cand = sp.cand;
     rp.cand_cnt = sp.cand_cnt;
     rp.cand_theta = sp.cand_theta;
@@ -364,7 +384,7 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
     CK(cudaGetLastError());
   }
   if (!(flags & KEDS_SEARCH_NO_FALLBACK) || pl.exact_only) {
-    for (int i = 0; i < n_db; ++i) CKS(launch_exact(a, ix[i], i, q_dev, nq, k, D[i], I[i], st));
+    for (int i = 0; i < n_db; ++i) CKS(launch_exact(a, ix[i], i, q_dev, nq, k, D[i], I[i], metric, st));
   }
   CK(cudaGetLastError());
   return 0;
@@ -454,7 +474,8 @@ int search_impl(keds_index* ix[2], int n_db, const float* q, int64_t nq, int k, 
       } else {
         const long long tot = static_cast<long long>(nq) * k;
         k_fill_pad<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, st>>>(
-            Dd[i], Id[i], tot, a->metric == METRIC_L2 ? FLT_MAX : -FLT_MAX);
+            Dd[i], Id[i], tot,
+            (a->metric == METRIC_L2 && !(flags & KEDS_SEARCH_FORCE_IP)) ? FLT_MAX : -FLT_MAX);
       }
     }
   } else {
@@ -537,6 +558,7 @@ void keds_index_free(keds_index_t* ix) {
                     &ix->flagged[1], &ix->ctrl, &ix->exact_scratch, &ix->D_stage[0], &ix->D_stage[1],
                     &ix->I_stage[0], &ix->I_stage[1]};
   for (DevBuf* b : bufs) b->release();
+  for (cudaEvent_t e : ix->prof_ev) cudaEventDestroy(e);
   delete ix;
 }
 
@@ -630,6 +652,29 @@ int keds_index_sync(keds_index_t* ix, void* stream) {
   return finish_sync(ix, static_cast<cudaStream_t>(stream));
 }
 
+int keds_index_set_profiling(keds_index_t* ix, int enable) {
+  if (!ix) return fail(KEDS_ERR_ARG, "set_profiling: null handle");
+  ix->profiling = enable != 0;
+  ix->prof_used = 0;
+  return 0;
+}
+
+int keds_index_profile(keds_index_t* ix, double* score_ms_total, int64_t* score_launches) {
+  if (!ix || !score_ms_total || !score_launches) return fail(KEDS_ERR_ARG, "profile: null argument");
+  DeviceGuard g(ix->device);
+  double tot = 0.0;
+  for (size_t i = 0; i + 1 < ix->prof_used; i += 2) {
+    CK(cudaEventSynchronize(ix->prof_ev[i + 1]));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, ix->prof_ev[i], ix->prof_ev[i + 1]));
+    tot += ms;
+  }
+  *score_ms_total = tot;
+  *score_launches = static_cast<int64_t>(ix->prof_used / 2);
+  ix->prof_used = 0;
+  return 0;
+}
+
 int keds_index_last_stats(const keds_index_t* ix, keds_search_stats* out) {
   if (!ix || !out) return fail(KEDS_ERR_ARG, "last_stats: null argument");
   *out = ix->stats;
@@ -673,6 +718,12 @@ int keds_gather_pool(const float* base, int64_t n_base, const int64_t* I, const 
 
 int keds_topk_merge(const float* Dp, const int64_t* Ip, int parts, int64_t nq, int k, int metric,
                     float* D, int64_t* I, void* stream) {
+  return keds_topk_merge_strided(Dp, Ip, nq * k, nq * k, parts, nq, k, metric, D, I, stream);
+}
+
+int keds_topk_merge_strided(const float* Dp, const int64_t* Ip, int64_t stride_d, int64_t stride_i,
+                            int parts, int64_t nq, int k, int metric, float* D, int64_t* I,
+                            void* stream) {
   if (!Dp || !Ip || !D || !I || parts <= 0 || nq < 0 || k <= 0)
     return fail(KEDS_ERR_ARG, "topk_merge: bad argument");
   if (nq == 0) return 0;
@@ -685,7 +736,8 @@ int keds_topk_merge(const float* Dp, const int64_t* Ip, int parts, int64_t nq, i
     attr = true;
   }
   k_topk_merge<<<static_cast<unsigned>(nq), 128, smem, static_cast<cudaStream_t>(stream)>>>(
-      Dp, reinterpret_cast<const long long*>(Ip), parts, nq, k, metric, D, reinterpret_cast<long long*>(I));
+      Dp, reinterpret_cast<const long long*>(Ip), stride_d, stride_i, parts, nq, k, metric, D,
+      reinterpret_cast<long long*>(I));
   CK(cudaGetLastError());
   return 0;
 }

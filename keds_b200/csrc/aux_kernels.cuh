@@ -492,11 +492,11 @@ k_exact_fallback(const ExactParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Merge `parts` per-shard results [parts][nq][k] into the global top-k (same total order; ids are
+// Merge `parts` per-shard results (part p at Dp + p*stride_d, Ip + p*stride_i, each [nq][k]) into the global top-k (same total order; ids are
 // already global). One block per query. Used after the all-gather of a row-sharded search.
 __global__ void k_topk_merge(const float* __restrict__ Dp, const long long* __restrict__ Ip,
-                             int parts, long long nq, int k, int metric, float* __restrict__ D,
-                             long long* __restrict__ I) {
+                             long long stride_d, long long stride_i, int parts, long long nq, int k,
+                             int metric, float* __restrict__ D, long long* __restrict__ I) {
   extern __shared__ uint8_t mg_smem[];
   unsigned long long* key = reinterpret_cast<unsigned long long*>(mg_smem);   // parts*k
   float* val = reinterpret_cast<float*>(key + parts * k);                     // parts*k
@@ -505,9 +505,9 @@ __global__ void k_topk_merge(const float* __restrict__ Dp, const long long* __re
   const int tot = parts * k;
   for (int i = threadIdx.x; i < tot; i += blockDim.x) {
     const int pt = i / k, j = i % k;
-    const long long src = (static_cast<long long>(pt) * nq + q) * k + j;
-    const float v = Dp[src];
-    const long long id = Ip[src];
+    const long long src = q * k + j;
+    const float v = Dp[pt * stride_d + src];
+    const long long id = Ip[pt * stride_i + src];
     val[i] = v;
     idv[i] = id;
     // 64-bit ids do not fit the 32-bit tie-break field in general: compare (score, id) directly

@@ -221,6 +221,15 @@ class GpuIndexFlat:
             "err_word": int(st.err_word),
         }
 
+    def set_profiling(self, enable: bool) -> None:
+        _capi.check(self._lib.keds_index_set_profiling(self._h, int(bool(enable))))
+
+    def profile(self):
+        """(summed ms, launches) of the scoring kernel since set_profiling(True); waits for them."""
+        ms, n = C.c_double(0.0), C.c_int64(0)
+        _capi.check(self._lib.keds_index_profile(self._h, C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)
+
     def rows_ptr(self) -> int:
         """Device address of the resident fp32 rows [ntotal, d]."""
         return int(self._lib.keds_index_rows(self._h) or 0)

@@ -1,0 +1,167 @@
+"""Gallery ranking and Recall@K on the native path.
+
+Same names, arguments and returned dict keys as the reference's metric functions
+(src/eval_utils.py:1008-1134).  The reference builds the full [Q, G] similarity matrix, argsorts
+every row, moves it to the CPU and matches *name strings* per element (a Q*G Python
+os.path.basename loop at :1046-1048).  Here names become integer ids once, and the GPU counts, per
+query, how many gallery rows beat the target (keds_gallery_rank) or how many of the exact top-200
+share the query's label (index search + keds_label_hits).  No sort, no Q x G matrix in HBM.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _capi
+from .index import GpuIndexFlat, METRIC_INNER_PRODUCT, _stream_ptr
+
+
+def _dev_f32(x, device: torch.device) -> torch.Tensor:
+    t = x if isinstance(x, torch.Tensor) else torch.as_tensor(np.asarray(x))
+    return t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+def _cuda_device(*tensors) -> torch.device:
+    for t in tensors:
+        if isinstance(t, torch.Tensor) and t.is_cuda:
+            return t.device
+    if not torch.cuda.is_available():
+        raise RuntimeError("keds_b200.metrics needs a CUDA device (no CPU path)")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def gallery_rank(query: torch.Tensor, gallery: torch.Tensor, target, exclude=None) -> torch.Tensor:
+    """rank[q] = number of gallery rows (target and `exclude` left out) that beat the target under
+    (inner product descending, row id ascending). int64 [Q] on the device."""
+    lib = _capi.load()
+    dev = _cuda_device(query, gallery)
+    Q = _dev_f32(query, dev)
+    G = _dev_f32(gallery, dev)
+    if Q.dim() != 2 or G.dim() != 2 or Q.shape[1] != G.shape[1]:
+        raise ValueError("query and gallery must be [*, d] with the same d")
+    t = torch.as_tensor(np.asarray(target) if not isinstance(target, torch.Tensor) else target)
+    t = t.to(device=dev, dtype=torch.int64).contiguous()
+    if t.numel() != Q.shape[0]:
+        raise ValueError("one target per query")
+    if t.numel() and (int(t.min()) < 0 or int(t.max()) >= G.shape[0]):
+        raise IndexError("target id outside the gallery")
+    e_ptr = 0
+    if exclude is not None:
+        e = torch.as_tensor(np.asarray(exclude) if not isinstance(exclude, torch.Tensor) else exclude)
+        e = e.to(device=dev, dtype=torch.int64).contiguous()
+        e_ptr = e.data_ptr()
+    out = torch.empty(Q.shape[0], dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        _capi.check(
+            lib.keds_gallery_rank(Q.data_ptr(), Q.shape[0], G.data_ptr(), G.shape[0], Q.shape[1],
+                                  t.data_ptr(), e_ptr, out.data_ptr(), _stream_ptr(dev.index))
+        )
+    return out
+
+
+def recall_at_k(ranks: torch.Tensor, ks: Sequence[int]) -> Dict[int, float]:
+    """fraction of queries whose target rank is < k."""
+    r = ranks.cpu().numpy()
+    return {int(k): float(np.mean(r < k)) if len(r) else 0.0 for k in ks}
+
+
+def get_metrics_coco(image_features, ref_features, logit_scale=None) -> Dict[str, float]:
+    """src/eval_utils.py:1008-1022. logit_scale > 0 does not change ranks and is accepted only for
+    signature compatibility."""
+    metrics: Dict[str, float] = {}
+    n = len(ref_features)
+    diag = torch.arange(n, dtype=torch.int64)
+    for name, (A, B) in {"image_to_ref": (image_features, ref_features),
+                         "ref_to_image": (ref_features, image_features)}.items():
+        preds = gallery_rank(A, B, diag).cpu().numpy()
+        metrics[f"{name}_mean_rank"] = preds.mean() + 1
+        metrics[f"{name}_median_rank"] = np.floor(np.median(preds)) + 1
+        for k in [1, 5, 10, 50, 100]:
+            metrics[f"{name}_R@{k}"] = np.mean(preds < k)
+    return metrics
+
+
+def get_metrics_fashion(image_features, ref_features, target_names, answer_names) -> Dict[str, float]:
+    """src/eval_utils.py:1025-1037."""
+    pos = {n: i for i, n in enumerate(target_names)}
+    if len(pos) != len(target_names):
+        raise AssertionError("gallery names must be unique (the reference asserts one hit per query)")
+    tgt = np.array([pos[n] for n in answer_names], np.int64)
+    r = gallery_rank(ref_features, image_features, tgt).cpu().numpy()
+    return {f"R@{k}": float(np.sum(r < k)) / len(r) * 100 for k in [1, 5, 10, 50, 100]}
+
+
+def get_metrics_cirr(image_features, ref_features, reference_names, index_names, target_names) -> Dict[str, float]:
+    """src/eval_utils.py:1040-1067: the query's own reference image is removed from its ranking."""
+    names = [os.path.basename(n) for n in index_names]  # G calls instead of Q*G (:1046-1048)
+    pos = {n: i for i, n in enumerate(names)}
+    if len(pos) != len(names):
+        raise AssertionError("gallery names must be unique (the reference asserts one hit per query)")
+    tgt = np.array([pos[n] for n in target_names], np.int64)
+    ref = np.array([pos[n] for n in reference_names], np.int64)
+    r = gallery_rank(ref_features, image_features, tgt, ref).cpu().numpy()
+    return {f"recall_R@{k}": float(np.sum(r < k)) / len(r) * 100 for k in [1, 5, 10, 50, 100]}
+
+
+def get_cirr_testoutput(image_features, ref_features, reference_names, index_names, id_names) -> Dict:
+    """src/eval_utils.py:1070-1087: top-50 gallery names per pair id, reference image removed."""
+    dev = _cuda_device(image_features, ref_features)
+    G = _dev_f32(image_features, dev)
+    Q = _dev_f32(ref_features, dev)
+    pos = {n: i for i, n in enumerate(index_names)}
+    ref = np.array([pos[n] for n in reference_names], np.int64)
+    ix = GpuIndexFlat(G.shape[1], METRIC_INNER_PRODUCT, dev.index)
+    ix.add(G)
+    kk = min(51, G.shape[0])
+    _, I = ix.search(Q, kk)
+    I = I.cpu().numpy()
+    result = {"version": "rc2", "metric": "recall"}
+    for ind in range(len(id_names)):
+        pairid = str(id_names[ind].item() if hasattr(id_names[ind], "item") else id_names[ind])
+        row = [j for j in I[ind] if j != ref[ind] and j >= 0][:50]
+        result[pairid] = [index_names[j].replace(".png", "") for j in row]
+    return result
+
+
+def label_hits(I: torch.Tensor, labels: torch.Tensor, qlabel: torch.Tensor, ks: Sequence[int]) -> torch.Tensor:
+    """hits[q, i] = #{ j < ks[i] : labels[I[q, j]] == qlabel[q] } (device int32 [Q, len(ks)])."""
+    lib = _capi.load()
+    dev = I.device
+    ks_t = torch.tensor(list(ks), dtype=torch.int32, device=dev)
+    labels = labels.to(device=dev, dtype=torch.int64).contiguous()
+    qlabel = qlabel.to(device=dev, dtype=torch.int64).contiguous()
+    I = I.contiguous()
+    hits = torch.empty((I.shape[0], len(ks)), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _capi.check(
+            lib.keds_label_hits(I.data_ptr(), I.shape[0], I.shape[1], labels.data_ptr(), qlabel.data_ptr(),
+                                ks_t.data_ptr(), len(ks), hits.data_ptr(), _stream_ptr(dev.index))
+        )
+    return hits
+
+
+def get_metrics_imgnet(query_features, image_features, query_labels, target_labels) -> Dict[str, float]:
+    """src/eval_utils.py:1090-1134: R@k = hits_in_top_k / (num_relevant + 1e-5) (:1115),
+    P@k = hits_in_top_k / k (:1116), averaged over the queries; k in {1,5,10,50,100,200}."""
+    ks = [1, 5, 10, 50, 100, 200]
+    dev = _cuda_device(query_features, image_features)
+    G = _dev_f32(image_features, dev)
+    Q = _dev_f32(query_features, dev)
+    ql = torch.as_tensor(query_labels).to(device=dev, dtype=torch.int64)
+    tl = torch.as_tensor(target_labels).to(device=dev, dtype=torch.int64)
+    ix = GpuIndexFlat(G.shape[1], METRIC_INNER_PRODUCT, dev.index)
+    ix.add(G)
+    kmax = max(ks)
+    _, I = ix.search(Q, kmax)
+    hits = label_hits(I, tl, ql, ks).to(torch.float32)
+    n_cls = int(max(int(tl.max()), int(ql.max()))) + 1
+    num_total = torch.bincount(tl, minlength=n_cls)[ql].to(torch.float32)
+    metrics: Dict[str, float] = {}
+    for i, k in enumerate(ks):
+        metrics[f"Real2Sketch_R@{k}"] = float((hits[:, i] / (num_total + 1e-5)).mean())
+        metrics[f"Real2Sketch_P@{k}"] = float((hits[:, i] / float(min(k, G.shape[0]))).mean())
+    return metrics

@@ -1,0 +1,161 @@
+"""The retrieval operator of KEDs on the native path.
+
+`get_retrieved_features` / `get_extra_cap_features` keep the reference's names, arguments and
+return values (src/trainer.py:198-283, src/eval_utils.py:153-186) so the training and eval loops
+call them unchanged.  What changes underneath:
+
+  reference (per call)                                   here
+  -----------------------------------------------------  -----------------------------------------
+  feature.clone().cpu().numpy()  x2  (D2H + sync)        queries stay on the GPU
+  image_index.search + text_index.search (2 passes)      one fused pass over both databases
+  base[I.reshape(-1)] on a 1.5 GB CPU tensor             gather kernel on the resident fp32 rows
+  feats[:, randperm(k), :] CPU copy                      permutation folded into the gather
+  .clone().to(device)  x2 (12.6 MB pageable H2D)         output is produced on the device
+
+`KnowledgeBase` replaces the index construction block of src/main.py:72-96 /
+src/eval_retrieval.py:280-298: it loads the .pt databases (layout unchanged: float32 [N, 768] CPU
+tensors + database_names.txt) and builds one native index per database on the local GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _capi
+from .index import GpuIndexFlat, METRIC_INNER_PRODUCT, METRIC_L2, search2, _stream_ptr
+
+
+def gather_rows(index: GpuIndexFlat, I: torch.Tensor, perm: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[b, j, :] = rows[I[b, perm[j]], :] from the index's resident fp32 rows (device tensors)."""
+    lib = _capi.load()
+    assert I.is_cuda and I.dtype == torch.int64 and I.dim() == 2
+    I = I.contiguous()
+    B, k = I.shape
+    out = torch.empty((B, k, index.d), dtype=torch.float32, device=I.device)
+    p = 0
+    if perm is not None:
+        perm = perm.to(device=I.device, dtype=torch.int32).contiguous()
+        assert perm.numel() == k
+        p = perm.data_ptr()
+    _capi.check(
+        lib.keds_gather_pool(index.rows_ptr(), index.ntotal, I.data_ptr(), 0, p, B, k, 1, index.d,
+                             out.data_ptr(), _stream_ptr(index.device))
+    )
+    return out
+
+
+def weighted_pool(index: GpuIndexFlat, I: torch.Tensor, W: torch.Tensor) -> torch.Tensor:
+    """out[b, h, :] = sum_j W[b, h, j] * rows[I[b, j], :]   (W: [B, H, k] float32, device)."""
+    lib = _capi.load()
+    assert I.is_cuda and I.dtype == torch.int64 and W.is_cuda and W.dtype == torch.float32
+    I = I.contiguous()
+    W = W.contiguous()
+    B, k = I.shape
+    assert W.dim() == 3 and W.shape[0] == B and W.shape[2] == k
+    H = W.shape[1]
+    out = torch.empty((B, H, index.d), dtype=torch.float32, device=I.device)
+    _capi.check(
+        lib.keds_gather_pool(index.rows_ptr(), index.ntotal, I.data_ptr(), W.data_ptr(), 0, B, k, H,
+                             index.d, out.data_ptr(), _stream_ptr(index.device))
+    )
+    return out
+
+
+class KnowledgeBase:
+    """The `database` object of the reference as a sequence:
+    [image_bases, text_bases, basenames, image_gpu_index, text_gpu_index]  (src/main.py:95-96).
+    image_bases / text_bases stay plain CPU float32 tensors (the .pt layout); the indices are
+    native and hold their own device copies."""
+
+    def __init__(self, image_bases: torch.Tensor, text_bases: torch.Tensor, basenames: Sequence[str],
+                 device: int = 0, metric: int = METRIC_L2) -> None:
+        for t in (image_bases, text_bases):
+            if not (isinstance(t, torch.Tensor) and t.dtype == torch.float32 and t.dim() == 2):
+                raise TypeError("knowledge bases must be 2-D float32 torch tensors (the .pt layout)")
+        if image_bases.shape != text_bases.shape:
+            raise ValueError("image and text bases must be aligned row for row")
+        self.image_bases = image_bases
+        self.text_bases = text_bases
+        self.basenames = list(basenames)
+        d = image_bases.shape[1]
+        self.image_index = GpuIndexFlat(d, metric, device)
+        self.text_index = GpuIndexFlat(d, metric, device)
+        self.image_index.add(image_bases)
+        self.text_index.add(text_bases)
+
+    @classmethod
+    def load(cls, image_pt: str, text_pt: str, names_txt: str, device: int = 0, metric: int = METRIC_L2):
+        """torch.load the two .pt files and read database_names.txt (src/main.py:470-477)."""
+        image_bases = torch.load(image_pt, map_location="cpu")
+        text_bases = torch.load(text_pt, map_location="cpu")
+        with open(names_txt) as f:
+            basenames = [line.rstrip("\n") for line in f]
+        return cls(image_bases, text_bases, basenames, device, metric)
+
+    # sequence protocol: database[0..4]
+    def _seq(self):
+        return [self.image_bases, self.text_bases, self.basenames, self.image_index, self.text_index]
+
+    def __getitem__(self, i):
+        return self._seq()[i]
+
+    def __len__(self) -> int:
+        return 5
+
+
+def _native(ix) -> bool:
+    return isinstance(ix, GpuIndexFlat)
+
+
+def get_retrieved_features(feature, database, args=None, topk: int = 16, use_faiss: bool = True):
+    """Same contract as src/trainer.py:198-259: returns (topk_image_features, topk_text_features),
+    each [B, topk, d] on feature.device; image neighbours permuted along k by one
+    torch.randperm(topk) shared by the batch (:218-219), text neighbours in rank order.
+
+    use_faiss=False in the reference is a dense torch matmul over the whole database; both
+    settings run the native search here (same answer: exact top-k by inner product / L2)."""
+    image_base, text_base, basenames, image_index, text_index = (database[i] for i in range(5))
+    if not (_native(image_index) and _native(text_index)):
+        raise TypeError("database[3] and database[4] must be keds_b200 GPU indices (no CPU path)")
+    if use_faiss:
+        feature = feature / feature.norm(dim=1, keepdim=True)  # src/trainer.py:206
+    dev = torch.device("cuda", image_index.device)
+    q = feature.detach().to(device=dev, dtype=torch.float32).contiguous()
+    flags = 0 if use_faiss else _capi.SEARCH_FORCE_IP  # the torch branch ranks by raw inner product
+    (_, Ii), (_, It) = search2(image_index, text_index, q, topk, flags)
+    perm = torch.randperm(topk) if use_faiss else None  # CPU generator, like the reference (:218)
+    topk_image_features = gather_rows(image_index, Ii, perm)
+    topk_text_features = gather_rows(text_index, It, None)
+    return topk_image_features.to(feature.device), topk_text_features.to(feature.device)
+
+
+def get_extra_cap_features(feature, database, args=None, topk: int = 2):
+    """src/trainer.py:262-283: top-`topk` text neighbours + their basenames (row-major order)."""
+    image_base, text_base, basenames, image_index, text_index = (database[i] for i in range(5))
+    if not _native(text_index):
+        raise TypeError("database[4] must be a keds_b200 GPU index (no CPU path)")
+    feature = feature / feature.norm(dim=1, keepdim=True)
+    dev = torch.device("cuda", text_index.device)
+    q = feature.detach().to(device=dev, dtype=torch.float32).contiguous()
+    _, It = text_index.search(q, topk)
+    feats = gather_rows(text_index, It, None)
+    ids = It.cpu().numpy()
+    names = [basenames[int(j)] for row in ids for j in row]
+    return feats.to(feature.device), names
+
+
+def retrieve_and_pool(feature: torch.Tensor, database, topk: int = 16, tau: float = 100.0):
+    """Fused consumer primitive: search both databases, then softmax(tau * D)-weighted pool of the
+    neighbours of each stream -> ([B, 1, d], [B, 1, d]).  The attn@v shape of
+    src/model/model.py:69-73 with the weights supplied by the caller's scores."""
+    image_index, text_index = database[3], database[4]
+    dev = torch.device("cuda", image_index.device)
+    q = feature.detach().to(device=dev, dtype=torch.float32).contiguous()
+    (Di, Ii), (Dt, It) = search2(image_index, text_index, q, topk)
+    sign = -1.0 if image_index.metric_type == METRIC_L2 else 1.0
+    Wi = torch.softmax(sign * tau * Di, dim=1).unsqueeze(1)
+    Wt = torch.softmax(sign * tau * Dt, dim=1).unsqueeze(1)
+    return weighted_pool(image_index, Ii, Wi), weighted_pool(text_index, It, Wt)

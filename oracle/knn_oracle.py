@@ -210,7 +210,7 @@ def metrics_imgnet(query_features, image_features, query_labels, target_labels) 
     for k in ks:
         c = hit[:, :k].sum(1).astype(np.float32)
         out[f"Real2Sketch_R@{k}"] = float(np.mean(c / (num_rel + np.float32(1e-5))))
-        out[f"Real2Sketch_P@{k}"] = float(np.mean(c / np.float32(min(k, I.shape[1]))))
+        out[f"Real2Sketch_P@{k}"] = float(np.mean(c / np.float32(min(k, len(tl)))))
     return out
 
 

@@ -107,7 +107,9 @@ def main() -> None:
     tgt = rng.integers(0, G, Q)
     ref = (tgt + rng.integers(1, G, Q)) % G
     gq = torch.Generator().manual_seed(1007)
-    qf = gal[tgt] + 0.9 * torch.randn(Q, d, generator=gq) / np.sqrt(d)
+    # composed query = target + its reference image + heavy noise: the reference image ranks high
+    # (so removing it matters, :1052-1056) and recall lands strictly between 0 and 100
+    qf = gal[tgt] + gal[ref] + 3.2 * torch.randn(Q, d, generator=gq) / np.sqrt(d)
     qf = qf / qf.norm(dim=1, keepdim=True)
     index_names = [f"./images/dev/dev-{i}.png" for i in range(G)]
     reference_names = [f"dev-{i}.png" for i in ref]
@@ -120,7 +122,7 @@ def main() -> None:
     P = 200
     img = unit(P, d, 1010)
     gc = torch.Generator().manual_seed(1011)
-    rf = img + 1.2 * torch.randn(P, d, generator=gc) / np.sqrt(d)
+    rf = img + 3.0 * torch.randn(P, d, generator=gc) / np.sqrt(d)
     rf = rf / rf.norm(dim=1, keepdim=True)
     m = ev["get_metrics_coco"](img, rf, torch.tensor(100.0))
     metrics["coco"] = {kk: float(v) for kk, v in m.items()}

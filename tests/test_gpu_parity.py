@@ -1,0 +1,437 @@
+"""GPU (-m gpu): the native path, called through the C ABI, against the CPU oracle on the same
+seeded inputs. Parity rule (BASELINE.json north_star): identical top-k label sets except
+near-ties (exact score gap < 1e-5), distances within 1e-4 absolute."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from keds_b200 import _capi  # noqa: E402
+from keds_b200 import faiss_compat as faiss  # noqa: E402
+from keds_b200 import metrics as km  # noqa: E402
+from keds_b200 import retrieval as kr  # noqa: E402
+from keds_b200.index import GpuIndexFlat, search2  # noqa: E402
+from oracle import knn_oracle as orc  # noqa: E402
+
+TIE_GAP = 1e-5   # north_star: index sets may differ only inside near-ties
+D_TOL = 1e-4     # north_star: distances within 1e-4 absolute
+
+
+def unit(n, d, seed):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(n, d, generator=g)
+    return (x / x.norm(dim=1, keepdim=True)).numpy()
+
+
+def build(db, metric):
+    ix = GpuIndexFlat(db.shape[1], faiss.METRIC_L2 if metric == "l2" else faiss.METRIC_INNER_PRODUCT, 0)
+    ix.add(db)
+    return ix
+
+
+def check(ix, db, q, k, metric, flags=0):
+    D, I = ix.search(q, k, flags)
+    assert D.dtype == np.float32 and I.dtype == np.int64 and D.shape == (q.shape[0], k)
+    Dr, Ir = orc.search(db, q, k, metric)
+    c = orc.compare_topk(Dr, Ir, D, I, db, q, metric, TIE_GAP, D_TOL)
+    assert c["ok"], (c, ix.last_stats())
+    assert ix.last_stats()["err_word"] == 0
+    return c
+
+
+# ------------------------------------------------------------------ the GEMM alone
+@pytest.mark.parametrize("n,b,d", [(5000, 200, 768), (300, 7, 64), (1000, 128, 200), (257, 129, 768)])
+def test_tensor_core_scores_match_bf16_reference(n, b, d):
+    db, q = unit(n, d, 1), unit(b, d, 2)
+    ix = build(db, "ip")
+    got = ix.debug_scores(torch.from_numpy(q).cuda()).cpu().double()
+    tb = lambda a: torch.from_numpy(a).bfloat16().double()
+    ref = tb(q) @ tb(db).t()
+    assert (got - ref).abs().max().item() < 2e-6      # fp32 accumulation order only
+    exact = torch.from_numpy(q).double() @ torch.from_numpy(db).double().t()
+    assert (got - exact).abs().max().item() < 4e-3    # bf16 operand rounding, unit-norm rows
+
+
+# ------------------------------------------------------------------ search vs oracle
+SHAPES = [
+    (5000, 200, 768, 16),    # several tiles, two query tiles
+    (70000, 130, 768, 16),   # N not a multiple of the 256-row tile, B not a multiple of 128
+    (999, 5, 768, 16),       # tiny batch
+    (3000, 64, 96, 4),       # d not a multiple of 64 (zero padded k-block)
+    (2297, 300, 768, 16),    # CIRR-gallery sized
+    (4096, 128, 768, 1),     # k = 1
+    (20000, 128, 768, 64),   # k = 64 (config 5's k)
+    (300, 40, 100, 16),      # d % 4 == 0 only; two tiles
+]
+
+
+@pytest.mark.parametrize("metric", ["ip", "l2"])
+@pytest.mark.parametrize("n,b,d,k", SHAPES)
+def test_search_matches_oracle(n, b, d, k, metric):
+    db, q = unit(n, d, 11), unit(b, d, 12)
+    if metric == "l2":  # non-unit rows so that L2 and IP really rank differently
+        db = db * np.linspace(0.8, 1.25, n, dtype=np.float32)[:, None]
+    ix = build(db, metric)
+    check(ix, db, q, k, metric)
+    check(ix, db, q, k, metric, _capi.SEARCH_EXACT_ONLY)
+
+
+def test_config1_4096_queries_vs_50k_rows():
+    """BASELINE.json configs[0]: 4,096 unit-norm queries vs 50k x 768, k = 16."""
+    db, q = unit(50000, 768, 1000), unit(4096, 768, 1001)
+    ix = build(db, "ip")
+    c = check(ix, db, q, 16, "ip")
+    assert c["rows_identical"] >= 4090
+    st = ix.last_stats()
+    assert st["exact_only"] == 0 and st["n_flagged"][0] < 64   # the tensor-core path answered
+
+
+def test_odd_dimension_and_unaligned_rows():
+    db, q = unit(700, 50, 3), unit(33, 50, 4)   # d = 50: scalar fp32 path, padded k-block
+    check(build(db, "ip"), db, q, 10, "ip")
+    check(build(db, "l2"), db, q, 10, "l2")
+
+
+def test_k_larger_than_ntotal_pads_with_minus_one():
+    db, q = unit(10, 64, 5), unit(4, 64, 6)
+    for metric, pad in (("ip", -orc.FLT_MAX), ("l2", orc.FLT_MAX)):
+        ix = build(db, metric)
+        D, I = ix.search(q, 16)
+        assert (I[:, 10:] == -1).all() and (D[:, 10:] == pad).all()
+        check(ix, db, q, 16, metric)
+    db = unit(600, 64, 5)   # approx path with k > ntotal
+    check(build(db, "ip"), db, q, 700, "ip")
+
+
+def test_empty_index_and_empty_batch():
+    ix = GpuIndexFlat(32, faiss.METRIC_INNER_PRODUCT, 0)
+    D, I = ix.search(np.zeros((3, 32), np.float32), 4)
+    assert (I == -1).all() and (D == -orc.FLT_MAX).all()
+    ix.add(unit(50, 32, 1))
+    D, I = ix.search(np.zeros((0, 32), np.float32), 4)
+    assert D.shape == (0, 4) and I.shape == (0, 4)
+
+
+def test_incremental_add_and_reset():
+    db, q = unit(3000, 128, 7), unit(20, 128, 8)
+    ix = GpuIndexFlat(128, faiss.METRIC_INNER_PRODUCT, 0)
+    ix.add(db[:1000])
+    ix.add(db[1000:1001])
+    ix.add(db[1001:])
+    assert ix.ntotal == 3000
+    check(ix, db, q, 16, "ip")
+    ix.reset()
+    assert ix.ntotal == 0
+    ix.add(db[:500])
+    check(ix, db[:500], q, 16, "ip")
+
+
+def test_exact_duplicates_follow_the_tie_policy():
+    """score descending, then label ascending -- duplicates of a row are returned lowest id first."""
+    base = unit(400, 768, 9)
+    db = np.concatenate([base, base[:100], base[:50]])   # rows 400..499 and 500..549 are copies
+    q = base[:32] + 0.01 * unit(32, 768, 10)
+    for metric in ("ip", "l2"):
+        ix = build(db, metric)
+        D, I = ix.search(q, 8)
+        Dr, Ir = orc.search(db, q, 8, metric)
+        # float64 may split an fp32 tie either way: compare through the parity rule, then check
+        # the deterministic order among exact fp32 ties directly
+        assert orc.compare_topk(Dr, Ir, D, I, db, q, metric, TIE_GAP, D_TOL)["ok"]
+        for b in range(32):
+            for j in range(7):
+                if D[b, j] == D[b, j + 1]:
+                    assert I[b, j] < I[b, j + 1]
+        assert I[0, 0] == 0 and set(I[0, :3]) == {0, 400, 500}
+
+
+def test_all_equal_scores():
+    db = np.tile(unit(1, 64, 1), (1000, 1))
+    q = unit(3, 64, 2)
+    for flags in (0, _capi.SEARCH_EXACT_ONLY):
+        D, I = build(db, "ip").search(q, 5, flags)
+        assert (I == np.arange(5)).all()
+
+
+def test_clustered_database_certificate_and_fallback():
+    """Real CLIP embeddings cluster: 8 tight clusters put thousands of rows inside the bf16 error
+    band around the k-th score, so the certificate must hand queries to the exact path -- answers
+    stay exact."""
+    g = torch.Generator().manual_seed(21)
+    cent = unit(8, 768, 20)
+    assign = torch.randint(0, 8, (20000,), generator=g).numpy()
+    db = cent[assign] + 0.05 * unit(20000, 768, 22)
+    db = (db / np.linalg.norm(db, axis=1, keepdims=True)).astype(np.float32)
+    q = cent[np.arange(40) % 8] + 0.05 * unit(40, 768, 23)
+    q = (q / np.linalg.norm(q, axis=1, keepdims=True)).astype(np.float32)
+    ix = build(db, "ip")
+    check(ix, db, q, 16, "ip")
+    assert ix.last_stats()["n_flagged"][0] > 0
+
+
+def test_inflated_error_bound_routes_everything_through_the_fallback():
+    db, q = unit(6000, 768, 31), unit(150, 768, 32)
+    ix = build(db, "ip")
+    ix.set_eps_scale(1000.0)
+    check(ix, db, q, 16, "ip")
+    assert ix.last_stats()["n_flagged"][0] == 150
+    ix.set_eps_scale(1.0)
+    check(ix, db, q, 16, "ip")
+    assert ix.last_stats()["n_flagged"][0] == 0
+
+
+def test_bf16_alone_is_not_exact_but_the_certified_path_is():
+    """Evidence that the re-rank matters: ranking by raw tensor-core scores disagrees with fp32 on
+    some queries of config 1's shape; the library's answer does not."""
+    db, q = unit(50000, 768, 1000), unit(512, 768, 1001)
+    ix = build(db, "ip")
+    approx = ix.debug_scores(torch.from_numpy(q).cuda())
+    Ia = approx.topk(16, dim=1).indices.sort(dim=1).values.cpu().numpy()
+    _, Ir = orc.search(db, q, 16)
+    raw_same = int((np.sort(Ir, 1) == Ia).all(1).sum())
+    c = check(ix, db, q, 16, "ip")
+    assert raw_same < 512 and c["bad_rows"] == 0
+
+
+def test_device_tensors_in_device_tensors_out():
+    db, q = unit(9000, 768, 41), unit(100, 768, 42)
+    ix = build(db, "ip")
+    qd = torch.from_numpy(q).cuda()
+    D, I = ix.search(qd, 16)
+    assert D.is_cuda and I.is_cuda and I.dtype == torch.int64
+    ix.sync()
+    Dn, In = ix.search(q, 16)
+    assert np.array_equal(I.cpu().numpy(), In) and np.array_equal(D.cpu().numpy(), Dn)
+
+
+def test_fused_two_database_search_equals_two_searches():
+    a, b, q = unit(30000, 768, 51), unit(30000, 768, 52), unit(128, 768, 53)
+    ia, ib = build(a, "ip"), build(b, "ip")
+    (Da, Ia), (Db, Ib) = search2(ia, ib, q, 16)
+    D1, I1 = ia.search(q, 16)
+    D2, I2 = ib.search(q, 16)
+    assert np.array_equal(Ia, I1) and np.array_equal(Ib, I2)
+    assert np.array_equal(Da, D1) and np.array_equal(Db, D2)
+    a2 = unit(12345, 768, 54)   # databases of different sizes
+    ia2 = build(a2, "ip")
+    (Da, Ia), (Db, Ib) = search2(ia2, ib, q, 16)
+    assert orc.compare_topk(*orc.search(a2, q, 16), Da, Ia, a2, q)["ok"]
+    assert np.array_equal(Ib, I2)
+
+
+def test_argument_errors():
+    ix = build(unit(100, 32, 1), "ip")
+    with pytest.raises(AssertionError):
+        ix.search(np.zeros((2, 31), np.float32), 4)
+    with pytest.raises(TypeError):
+        ix.search(np.zeros((2, 32), np.float64), 4)
+    with pytest.raises(RuntimeError, match="exceeds"):
+        ix.search(np.zeros((2, 32), np.float32), 5000)
+    with pytest.raises(ValueError):
+        ix.search(np.zeros((2, 32), np.float32), 0)
+
+
+# ------------------------------------------------------------------ shards + merge kernel
+def test_row_shards_merge_to_the_unsharded_answer():
+    """size-independent property: 1, 2, 3 and 8 row shards give bit-identical (D, I)."""
+    db, q = unit(40000, 768, 61), unit(96, 768, 62)
+    lib = _capi.load()
+    D1, I1 = build(db, "ip").search(q, 64)
+    for R in (2, 3, 8):
+        per = -(-len(db) // R)
+        Dp = torch.empty((R, 96, 64), dtype=torch.float32, device="cuda")
+        Ip = torch.empty((R, 96, 64), dtype=torch.int64, device="cuda")
+        for r in range(R):
+            ix = build(db[r * per:(r + 1) * per], "ip")
+            ix.set_id_offset(r * per)
+            D, I = ix.search(torch.from_numpy(q).cuda(), 64)
+            ix.sync()
+            Dp[r], Ip[r] = D, I
+        D = torch.empty((96, 64), dtype=torch.float32, device="cuda")
+        I = torch.empty((96, 64), dtype=torch.int64, device="cuda")
+        _capi.check(lib.keds_topk_merge(Dp.data_ptr(), Ip.data_ptr(), R, 96, 64, 0, D.data_ptr(), I.data_ptr(), None))
+        torch.cuda.synchronize()
+        assert np.array_equal(I.cpu().numpy(), I1) and np.array_equal(D.cpu().numpy(), D1)
+
+
+def test_index_shards_and_replicas_in_one_process():
+    db, q = unit(5000, 64, 71), unit(50, 64, 72)
+    for cls in (faiss.IndexShards, faiss.IndexReplicas):
+        multi = cls(64, faiss.METRIC_L2, [0, 0])     # two handles on the one GPU of the test box
+        multi.add(db)
+        D, I = multi.search(q, 16)
+        assert multi.ntotal == 5000
+        assert orc.compare_topk(*orc.search(db, q, 16, "l2"), D, I, db, q, "l2")["ok"]
+
+
+# ------------------------------------------------------------------ gather / pool
+def test_gather_and_weighted_pool_match_oracle():
+    db, q = unit(8000, 768, 81), unit(64, 768, 82)
+    ix = build(db, "ip")
+    D, I = ix.search(torch.from_numpy(q).cuda(), 16)
+    perm = torch.randperm(16, generator=torch.Generator().manual_seed(3))
+    got = kr.gather_rows(ix, I, perm).cpu().numpy()
+    assert np.array_equal(got, orc.gather(db, I.cpu().numpy(), perm.numpy()))
+    assert np.array_equal(kr.gather_rows(ix, I).cpu().numpy(), orc.gather(db, I.cpu().numpy()))
+    W = torch.softmax(100.0 * D, dim=1).unsqueeze(1).repeat(1, 8, 1).contiguous()
+    W[:, 1:] = torch.rand(64, 7, 16, device="cuda")
+    pooled = kr.weighted_pool(ix, I, W).cpu().numpy()
+    ref = orc.weighted_pool(db, I.cpu().numpy(), W.cpu().numpy())
+    assert np.abs(pooled - ref).max() < 1e-5     # fp32 vs float64 accumulation of 16 terms
+    Ineg = I.clone()
+    Ineg[:, -1] = -1
+    assert (kr.gather_rows(ix, Ineg)[:, -1] == 0).all()
+
+
+# ------------------------------------------------------------------ reference-shaped operators vs golden
+def test_get_retrieved_features_matches_the_reference_outputs(golden_dir):
+    z = np.load(os.path.join(golden_dir, "retrieval.npz"))
+    ib, tb = torch.from_numpy(z["image_base"]), torch.from_numpy(z["text_base"])
+    names = [f"{i:07d}" for i in range(len(ib))]
+    feature = torch.from_numpy(z["feature"]).cuda()
+    for metric in (faiss.METRIC_L2, faiss.METRIC_INNER_PRODUCT):   # unit rows: same ranking
+        database = kr.KnowledgeBase(ib, tb, names, 0, metric)
+        torch.manual_seed(999)
+        fi, ft = kr.get_retrieved_features(feature, database, None, topk=16, use_faiss=True)
+        assert fi.is_cuda and fi.shape == (32, 16, 64)
+        assert np.array_equal(fi.cpu().numpy(), z["faiss_branch_image"])
+        assert np.array_equal(ft.cpu().numpy(), z["faiss_branch_text"])
+        ti, tt = kr.get_retrieved_features(feature, database, None, topk=16, use_faiss=False)
+        assert np.array_equal(ti.cpu().numpy(), z["torch_branch_image"])
+        assert np.array_equal(tt.cpu().numpy(), z["torch_branch_text"])
+        et, en = kr.get_extra_cap_features(feature, database, None, topk=2)
+        assert np.array_equal(et.cpu().numpy(), z["extra_text"]) and en == list(z["extra_names"])
+
+
+def test_reference_call_sequence_through_the_faiss_names(golden_dir):
+    """src/main.py:72-83 verbatim, with `faiss` bound to keds_b200.faiss_compat."""
+    z = np.load(os.path.join(golden_dir, "retrieval.npz"))
+    image_bases = torch.from_numpy(z["image_base"])
+    image_index = faiss.IndexFlatL2(64)
+    res = faiss.StandardGpuResources()
+    image_gpu_index = faiss.index_cpu_to_gpu(res, 0, image_index)
+    image_gpu_index.add(image_bases.numpy())
+    f = z["feature"] / np.linalg.norm(z["feature"], axis=1, keepdims=True)
+    _, topk = image_gpu_index.search(f, 16)
+    assert np.array_equal(image_bases[topk.reshape(-1)].reshape(32, 16, -1).numpy(),
+                          orc.gather(z["image_base"], orc.search(z["image_base"], f, 16, "l2")[1]))
+    assert faiss.get_num_gpus() >= 1
+    allg = faiss.index_cpu_to_all_gpus(image_index)
+    allg.add(image_bases.numpy())
+    assert np.array_equal(allg.search(f, 16)[1], topk)
+
+
+def _close(got, want, tol=1e-4):
+    assert set(got) == set(want)
+    for k in want:
+        assert float(got[k]) == pytest.approx(want[k], rel=tol, abs=tol), (k, got[k], want[k])
+
+
+def test_gallery_metrics_match_the_reference_outputs(golden_dir):
+    z = np.load(os.path.join(golden_dir, "metrics_inputs.npz"))
+    e = json.load(open(os.path.join(golden_dir, "metrics_expected.json")))
+    t = lambda a: torch.from_numpy(a).cuda()
+    _close(km.get_metrics_cirr(t(z["gal"]), t(z["qf"]), e["reference_names"], e["index_names"], e["target_names"]),
+           e["metrics"]["cirr"])
+    ans = [e["fashion_names"][i] for i in z["tgt"]]
+    _close(km.get_metrics_fashion(t(z["gal"]), t(z["qf"]), e["fashion_names"], ans), e["metrics"]["fashion"])
+    _close(km.get_metrics_coco(t(z["coco_img"]), t(z["coco_ref"]), torch.tensor(100.0)), e["metrics"]["coco"])
+    _close(km.get_metrics_imgnet(t(z["in_q"]), t(z["in_gal"]), torch.from_numpy(z["in_qlab"]),
+                                 torch.from_numpy(z["in_glab"])), e["metrics"]["imgnet"])
+
+
+def test_gallery_rank_matches_oracle_at_cirr_shape():
+    """configs[3]: 4,181 queries vs 2,297 gallery rows, one excluded reference image per query."""
+    gal = unit(2297, 768, 1006)
+    rng = np.random.default_rng(1007)
+    tgt = rng.integers(0, 2297, 4181)
+    ref = (tgt + rng.integers(1, 2297, 4181)) % 2297
+    q = gal[tgt] + gal[ref] + 2.0 * unit(4181, 768, 1007)
+    q = (q / np.linalg.norm(q, axis=1, keepdims=True)).astype(np.float32)
+    got = km.gallery_rank(torch.from_numpy(q).cuda(), torch.from_numpy(gal).cuda(), tgt, ref).cpu().numpy()
+    want = orc.target_ranks(q, gal, tgt, ref)
+    # fp32 vs float64 scores may flip a near-tie: ranks may differ by the number of near-ties only
+    assert np.mean(got == want) > 0.999 and np.abs(got - want).max() <= 1
+    for k in (1, 5, 10, 50, 100):
+        assert np.mean(got < k) == pytest.approx(np.mean(want < k), abs=5e-4)
+
+
+def test_imgnet_shaped_recall_50k_gallery():
+    """configs[3]: 50k-row gallery with labels < 7000, top-200 label hits."""
+    rng = np.random.default_rng(1008)
+    glab = rng.integers(0, 7000, 50000)
+    qlab = rng.integers(0, 7000, 1000)
+    cent = unit(7000, 256, 1008)
+    gal = cent[glab] + 1.0 * unit(50000, 256, 1009)
+    gal = (gal / np.linalg.norm(gal, axis=1, keepdims=True)).astype(np.float32)
+    q = cent[qlab] + 1.0 * unit(1000, 256, 1010)
+    q = (q / np.linalg.norm(q, axis=1, keepdims=True)).astype(np.float32)
+    got = km.get_metrics_imgnet(torch.from_numpy(q), torch.from_numpy(gal), torch.from_numpy(qlab), torch.from_numpy(glab))
+    want = orc.metrics_imgnet(q, gal, qlab, glab)
+    _close(got, want, 2e-3)
+
+
+# ------------------------------------------------------------------ full-size properties (configs[1])
+def test_training_step_shape_full_size_properties():
+    """128 queries vs two 0.5M x 768 databases, k = 16: too big for the float64 oracle in seconds,
+    so check (a) the fused two-DB search against torch float64 on the GPU, (b) shard invariance,
+    (c) invariance under a permutation of the rows, (d) L2 == IP ranking on unit rows."""
+    n, d, b, k = 500000, 768, 128, 16
+    dbs = []
+    for s in (1002, 1003):
+        g = torch.Generator(device="cuda").manual_seed(s)
+        x = torch.randn(n, d, generator=g, device="cuda")
+        dbs.append(x / x.norm(dim=1, keepdim=True))
+    q = torch.from_numpy(unit(b, d, 1004)).cuda()
+    ia = GpuIndexFlat(d, faiss.METRIC_INNER_PRODUCT, 0)
+    ib = GpuIndexFlat(d, faiss.METRIC_INNER_PRODUCT, 0)
+    ia.add(dbs[0])
+    ib.add(dbs[1])
+    (Da, Ia), (Db, Ib) = search2(ia, ib, q, k)
+    ia.sync()
+    assert ia.last_stats()["exact_only"] == 0 and ia.last_stats()["err_word"] == 0
+    for dbt, D, I in ((dbs[0], Da, Ia), (dbs[1], Db, Ib)):
+        s = q.double() @ dbt.double().t()
+        v, i = s.topk(k, dim=1)
+        assert (i == I).all(dim=1).float().mean().item() >= 0.99      # near-ties may swap
+        assert (torch.sort(i, 1).values == torch.sort(I, 1).values).all(dim=1).float().mean().item() >= 0.99
+        assert (v.float() - D).abs().max().item() < D_TOL
+    # (b) two row shards + merge == whole
+    lib = _capi.load()
+    half = n // 2
+    Dp = torch.empty((2, b, k), dtype=torch.float32, device="cuda")
+    Ip = torch.empty((2, b, k), dtype=torch.int64, device="cuda")
+    for r in range(2):
+        sh = GpuIndexFlat(d, faiss.METRIC_INNER_PRODUCT, 0)
+        sh.add(dbs[0][r * half:(r + 1) * half])
+        sh.set_id_offset(r * half)
+        Dp[r], Ip[r] = sh.search(q, k)
+        sh.sync()
+        del sh
+    Dm = torch.empty((b, k), dtype=torch.float32, device="cuda")
+    Im = torch.empty((b, k), dtype=torch.int64, device="cuda")
+    _capi.check(lib.keds_topk_merge(Dp.data_ptr(), Ip.data_ptr(), 2, b, k, 0, Dm.data_ptr(), Im.data_ptr(), None))
+    torch.cuda.synchronize()
+    assert torch.equal(Im, Ia) and torch.equal(Dm, Da)
+    # (c) permuting the rows permutes the labels and nothing else
+    perm = torch.randperm(n, device="cuda", generator=torch.Generator(device="cuda").manual_seed(7))
+    ip = GpuIndexFlat(d, faiss.METRIC_INNER_PRODUCT, 0)
+    ip.add(dbs[0][perm].contiguous())
+    Dq, Iq = ip.search(q, k)
+    ip.sync()
+    assert torch.equal(Dq, Da)
+    assert (perm[Iq] == Ia).all(dim=1).float().mean().item() >= 0.99
+    del ip
+    # (d) squared L2 on unit rows: same ranking, D = 2 - 2 ip
+    il2 = GpuIndexFlat(d, faiss.METRIC_L2, 0)
+    il2.add(dbs[0])
+    qn = q / q.norm(dim=1, keepdim=True)
+    Dl, Il = il2.search(qn, k)
+    Di, Ii = ia.search(qn, k)
+    il2.sync()
+    assert (Il == Ii).all(dim=1).float().mean().item() >= 0.98
+    assert (Dl - (2 - 2 * Di)).abs().max().item() < 1e-5
