@@ -1,0 +1,445 @@
+#!/usr/bin/env python
+"""bench.py -- kNN queries/sec of the KEDs knowledge-retrieval step on B200.
+
+Workload (BASELINE.json configs[1]): batch-128 unit-norm 768-d queries against a 0.5M x 768 image
+database and a 0.5M x 768 text database, k = 16, exact inner-product search, followed by the
+neighbour gather (image stream permuted) and the weighted pool into the two streams.  One "step"
+is one such batch.  Synthetic data, seeds from SURVEY.md section 8(d).
+
+    python bench.py --gpus N --steps K --warmup W          # ours (native sm_100a path)
+    python bench.py --impl reference ...                    # the reference's CPU formulation
+    torchrun --nproc-per-node N bench.py --gpus N ...       # one rank per GPU
+
+N > 1: one replica of both databases per rank and an independent 128-query batch per rank -- the
+reference's own training layout (one Faiss replica per DDP rank, src/main.py:76,82), no data-path
+collective, weak scaling.  The row-sharded exchange (all-gather + merge) is measured beside it as
+`sharded` (configs[4] shape: 1M rows per rank, k = 64).
+
+Timing: W >= 3 warm-ups; K steps bracketed by barrier + synchronize; CUDA events on the launching
+stream; max over ranks.  Inputs (2 x 768 MB of bf16 rows + fp32 re-rank rows) exceed the 126 MB L2,
+so every step streams from HBM.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_ROWS, DIM, BATCH, K = 500_000, 768, 128, 16
+SEED_IMG, SEED_TXT, SEED_Q = 1002, 1003, 1004
+METRIC_NAME = "kNN queries/sec (k=16, 0.5Mx768 DB)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=int, default=N_ROWS, help="rows per database (default: the baseline's 0.5M)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sharded", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            j = json.load(open(p))
+            return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def make_db_gpu(n, d, seed, device):
+    """unit-norm rows; the text DB is built from the image DB (aligned pairs) like SURVEY 8(d)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    x = torch.randn(n, d, generator=g, device=device)
+    return x / x.norm(dim=1, keepdim=True)
+
+
+def make_queries(b, d, seed):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(b, d, generator=g)
+    return x / x.norm(dim=1, keepdim=True)
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.proc = None
+        self.gpu = gpu_index
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            txt, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            txt = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in txt.strip().splitlines():
+            f = [c.strip() for c in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if sm:
+            # the busiest half of the samples = "under load"
+            top = sorted(sm)[len(sm) // 2:]
+            out.update(sm_mhz=float(np.median(top)), sm_max_mhz=float(max(mx)), samples=len(sm))
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def dist_setup(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if args.impl == "reference":
+            return rank, world, local  # rank 0 alone works; no process group needed
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, local
+
+
+# ---------------------------------------------------------------------------------------------
+def cpu_port_qps(db_img, db_txt, q, reps, threads=None):
+    """The reference's own CPU formulation of the path (src/trainer.py:246-257: q @ base.T, topk,
+    gather), fp32 MKL SGEMM on the host cores.  oracle/ is used here only as the thing timed for
+    the baseline legs, never by the product."""
+    from oracle import knn_oracle as orc
+    if threads:
+        torch.set_num_threads(threads)
+    t_best = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        _, Ii = orc.search_f32_blas(db_img, q, K)
+        _, It = orc.search_f32_blas(db_txt, q, K)
+        fi = orc.gather(db_img, Ii, np.random.permutation(K))
+        ft = orc.gather(db_txt, It)
+        _ = fi.mean(1), ft.mean(1)
+        t_best.append(time.perf_counter() - t0)
+    t = float(np.median(t_best))
+    return q.shape[0] / t, t
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    n = args.rows
+    torch.manual_seed(0)
+    g = torch.Generator().manual_seed(SEED_IMG)
+    # bounded sample: the full 128-query batch against `rows_cpu` rows of each database
+    rows_cpu = min(n, 500_000)
+    db_img = torch.randn(rows_cpu, DIM, generator=g)
+    db_img = (db_img / db_img.norm(dim=1, keepdim=True)).numpy()
+    g = torch.Generator().manual_seed(SEED_TXT)
+    db_txt = torch.randn(rows_cpu, DIM, generator=g)
+    db_txt = (db_txt / db_txt.norm(dim=1, keepdim=True)).numpy()
+    q = make_queries(BATCH, DIM, SEED_Q).numpy()
+    steps = max(1, min(args.steps, 20))
+    warm = max(1, min(args.warmup, 2))
+    cpu_port_qps(db_img, db_txt, q, warm)
+    qps, t = cpu_port_qps(db_img, db_txt, q, steps)
+    qps_full = qps * rows_cpu / n  # linear in rows if the sample is smaller than the workload
+    cores = torch.get_num_threads()
+    line = {
+        "impl": "reference", "metric": METRIC_NAME, "value": qps_full, "unit": "queries/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": t * 1e3 * n / rows_cpu, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: 128 queries vs 0.5Mx768 image DB + 0.5Mx768 text DB, k=16, gather+pool",
+                   "batch": BATCH, "rows_per_db": n, "k": K, "dim": DIM},
+        "cpu_baseline": {"value": qps_full, "unit": "queries/s", "cores": cores, "kind": "port",
+                         "sample": f"{BATCH} queries x 2 DBs x {rows_cpu} rows per step, {steps} steps, "
+                                   f"torch-CPU fp32 matmul+topk+gather (src/trainer.py:246-257); Faiss is not installable here"},
+        "e2e": {"value": qps_full, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local):
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the native path has no CPU fallback")
+    import torch.distributed as dist
+    from keds_b200 import _capi
+    from keds_b200 import retrieval as kr
+    from keds_b200.index import GpuIndexFlat, METRIC_INNER_PRODUCT, search2
+
+    _capi.load()
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    n = args.rows
+    img = make_db_gpu(n, DIM, SEED_IMG, dev)
+    noise = make_db_gpu(n, DIM, SEED_TXT, dev)
+    txt = img * 0.5 + noise * 0.5
+    txt = txt / txt.norm(dim=1, keepdim=True)
+    del noise
+    ia = GpuIndexFlat(DIM, METRIC_INNER_PRODUCT, local)
+    ib = GpuIndexFlat(DIM, METRIC_INNER_PRODUCT, local)
+    ia.add(img)
+    ib.add(txt)
+    db_img_host = img.cpu().numpy() if (rank == 0 and not args.no_cpu_baseline) else None
+    db_txt_host = txt.cpu().numpy() if (rank == 0 and not args.no_cpu_baseline) else None
+    del img, txt
+    torch.cuda.empty_cache()
+
+    # every rank gets its own query batch (data parallel), pinned on the host for the e2e leg
+    q_host = make_queries(BATCH, DIM, SEED_Q + rank).pin_memory()
+    q_dev = q_host.to(dev)
+    perm = torch.randperm(K, generator=torch.Generator().manual_seed(999)).to(dev, torch.int32)
+    W_uniform = torch.full((BATCH, 1, K), 1.0 / K, device=dev)
+
+    def step(q):
+        (Di, Ii), (Dt, It) = search2(ia, ib, q, K)
+        fi = kr.gather_rows(ia, Ii, perm)
+        ft = kr.gather_rows(ib, It, None)
+        pi = kr.weighted_pool(ia, Ii, W_uniform)
+        pt = kr.weighted_pool(ib, It, W_uniform)
+        return Ii, It, fi, ft, pi, pt
+
+    LAUNCHES_PER_STEP = 9  # prep_rows, score_topk, select_rerank, 2 x exact_fallback, 2 x gather, 2 x pool
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    W = max(3, args.warmup)
+    for _ in range(W):
+        step(q_dev)
+    ia.sync()
+
+    # ---- device-resident throughput (value) with the scoring kernel timed per launch
+    barrier()
+    ia.set_profiling(True)
+    sampler = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = step(q_dev)
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    ia.sync()
+    score_ms, score_n = ia.profile()
+    ia.set_profiling(False)
+    stats = ia.last_stats()
+
+    # ---- end to end: pinned host queries in, pooled streams + labels out, every step
+    h2d = q_host.numel() * 4
+    res_host = [torch.empty((BATCH, 1, DIM), dtype=torch.float32).pin_memory() for _ in range(2)]
+    lab_host = [torch.empty((BATCH, K), dtype=torch.int64).pin_memory() for _ in range(2)]
+    d2h = sum(t.numel() * t.element_size() for t in res_host + lab_host)
+    q_stage = torch.empty_like(q_dev)
+
+    def e2e_step():
+        q_stage.copy_(q_host, non_blocking=True)
+        Ii, It, fi, ft, pi, pt = step(q_stage)
+        res_host[0].copy_(pi, non_blocking=True)
+        res_host[1].copy_(pt, non_blocking=True)
+        lab_host[0].copy_(Ii, non_blocking=True)
+        lab_host[1].copy_(It, non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the caller reads the result every step
+
+    e2e_steps = max(10, min(args.steps, 1000))
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    f1.record()
+    barrier()
+    e2e_ms = f0.elapsed_time(f1)
+    clocks = sampler.stop() if sampler else None
+
+    # ---- the Faiss-shaped numpy call exactly as the reference issues it (two searches, numpy out)
+    q_np = q_host.numpy()
+    for _ in range(3):
+        ia.search(q_np, K), ib.search(q_np, K)
+    t0 = time.perf_counter()
+    reps = 50
+    for _ in range(reps):
+        ia.search(q_np, K)
+        ib.search(q_np, K)
+    dropin_ms = (time.perf_counter() - t0) / reps * 1e3
+
+    # ---- max over ranks
+    def rmax(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ms_total = rmax(ms_total)
+    e2e_ms = rmax(e2e_ms)
+    dropin_ms = rmax(dropin_ms)
+
+    sharded = None
+    if world > 1 and not args.no_sharded:
+        del ia, ib
+        torch.cuda.empty_cache()
+        sharded = run_sharded(args, rank, world, local, dev)
+
+    if rank != 0:
+        return
+    ms_per_step = ms_total / args.steps
+    value = world * BATCH / (ms_per_step * 1e-3)
+    e2e_val = world * BATCH / (e2e_ms / e2e_steps * 1e-3)
+
+    # roofline of the dominant kernel (k_score_topk): algorithmic bytes per launch =
+    # 2 DBs x N x 768 x 2 B (bf16 rows) + B x 768 x 2 (queries) + 2 x 12 x B x k (results)
+    alg_bytes = 2 * n * DIM * 2 + BATCH * DIM * 2 + 2 * 12 * BATCH * K
+    hbm_peak, peak_src = peaks()
+    score_avg_ms = score_ms / max(1, score_n)
+    achieved = alg_bytes / (score_avg_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "score_topk_dram_bytes.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    line = {
+        "metric": METRIC_NAME, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+        "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "configs[1]: 128 queries vs 0.5Mx768 image DB + 0.5Mx768 text DB, k=16, "
+                               "fused two-DB search + gather (image stream permuted) + weighted pool",
+                   "batch_per_gpu": BATCH, "rows_per_db": n, "k": K, "dim": DIM,
+                   "parallelism": f"replica x{world} (one full DB copy + own query batch per GPU, no collective)",
+                   "l2": "inputs larger than L2 (2 x 768 MB bf16 rows streamed per step vs 126 MB L2)",
+                   "slices": stats["slices"], "score_grid": stats["grid"], "flagged_last_step": stats["n_flagged"]},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                     "traffic": traffic, "kernel": "k_score_topk", "kernel_ms": score_avg_ms, "launches_timed": score_n,
+                     "kernel_share_of_step": score_avg_ms / ms_per_step, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg_bytes,
+                     "step_frac_of_roofline": (alg_bytes / hbm_peak / 1e9) / (ms_per_step * 1e-3)},
+        "e2e": {"value": e2e_val, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
+                "what": "pinned host queries -> search2 + gather + pool -> pooled streams and labels read back, sync every step"},
+        "dropin_numpy": {"value": world * BATCH / (dropin_ms * 1e-3), "unit": "queries/s", "ms_per_step": dropin_ms,
+                         "what": "image_index.search(q_np,16); text_index.search(q_np,16) as in src/trainer.py:213,221"},
+        "gpu_launches": LAUNCHES_PER_STEP * args.steps,
+        "clocks": clocks,
+    }
+    if sharded is not None:
+        line["sharded"] = sharded
+    if not args.no_cpu_baseline and db_img_host is not None:
+        q = make_queries(BATCH, DIM, SEED_Q).numpy()
+        cpu_port_qps(db_img_host[:50_000], db_txt_host[:50_000], q, 1)
+        t0 = time.perf_counter()
+        reps = 0
+        ts = []
+        while time.perf_counter() - t0 < 12.0 and reps < 20:
+            qps, t = cpu_port_qps(db_img_host, db_txt_host, q, 1)
+            ts.append(t)
+            reps += 1
+        tmed = float(np.median(ts))
+        line["cpu_baseline"] = {
+            "value": BATCH / tmed, "unit": "queries/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"full workload ({BATCH} queries x 2 x {n} rows), median of {reps} repetitions; torch-CPU fp32 "
+                      f"matmul+topk+gather (the reference's own non-Faiss formulation, src/trainer.py:246-257)"}
+    print(json.dumps(line), flush=True)
+
+
+def run_sharded(args, rank, world, local, dev):
+    """configs[4] shape: 8M x 768 rows over 8 ranks = 1M rows per rank (weak: rows per rank fixed),
+    128 replicated queries, k = 64, local search -> packed NCCL all-gather -> merge kernel."""
+    import torch.distributed as dist
+    from keds_b200.index import METRIC_INNER_PRODUCT
+    from keds_b200.sharded import ShardedIndex
+    rows = 1_000_000
+    k = 64
+    sh = ShardedIndex(DIM, METRIC_INNER_PRODUCT, local)
+    x = make_db_gpu(rows, DIM, 1010 + rank, dev)
+    sh.add_local(x, rank * rows, rows * world)
+    del x
+    torch.cuda.empty_cache()
+    q = make_queries(BATCH, DIM, 1020).to(dev)
+    for _ in range(5):
+        sh.search(q, k)
+    dist.barrier()
+    torch.cuda.synchronize()
+    steps = max(10, min(args.steps, 500))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        sh.search(q, k)
+    e1.record()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    hbm_peak, _ = peaks()
+    roof_ms = (rows * DIM * 2) / (hbm_peak * 1e9) * 1e3
+    return {"workload": f"configs[4]: {rows * world} x 768 rows row-sharded over {world} GPUs ({rows} per GPU), "
+                        f"{BATCH} queries, k={k}, NCCL all-gather + merge kernel",
+            "ms_per_step": ms, "value": BATCH / (ms * 1e-3), "unit": "queries/s", "steps": steps,
+            "frac_of_hbm_roofline": roof_ms / ms}
+
+
+def main():
+    args = parse()
+    rank, world, local = dist_setup(args)
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under torch.distributed.run
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    try:
+        run_ours(args, rank, world, local)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            if dist.is_initialized():
+                dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
