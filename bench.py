@@ -226,17 +226,16 @@ def run_ours(args, rank, world, local):
     q_host = make_queries(BATCH, DIM, SEED_Q + rank).pin_memory()
     q_dev = q_host.to(dev)
     perm = torch.randperm(K, generator=torch.Generator().manual_seed(999)).to(dev, torch.int32)
-    W_uniform = torch.full((BATCH, 1, K), 1.0 / K, device=dev)
+
+    bufs = {}
 
     def step(q):
-        (Di, Ii), (Dt, It) = search2(ia, ib, q, K)
-        fi = kr.gather_rows(ia, Ii, perm)
-        ft = kr.gather_rows(ib, It, None)
-        pi = kr.weighted_pool(ia, Ii, W_uniform)
-        pt = kr.weighted_pool(ib, It, W_uniform)
-        return Ii, It, fi, ft, pi, pt
+        # one native call: fused two-DB search, gather of both streams (image permuted), softmax pool
+        o = kr.retrieve2(ia, ib, q, K, perm_img=perm, want_feats=True, pool_mode=kr.POOL_SOFTMAX, tau=100.0,
+                         out=bufs)
+        return o["I_img"], o["I_txt"], o["feat_img"], o["feat_txt"], o["pool_img"], o["pool_txt"]
 
-    LAUNCHES_PER_STEP = 9  # prep_rows, score_topk, select_rerank, 2 x exact_fallback, 2 x gather, 2 x pool
+    LAUNCHES_PER_STEP = 5  # k_prep_rows, k_score_topk, k_select_rerank, k_exact_fallback, k_consume2
 
     def barrier():
         if world > 1:
@@ -266,7 +265,7 @@ def run_ours(args, rank, world, local):
 
     # ---- end to end: pinned host queries in, pooled streams + labels out, every step
     h2d = q_host.numel() * 4
-    res_host = [torch.empty((BATCH, 1, DIM), dtype=torch.float32).pin_memory() for _ in range(2)]
+    res_host = [torch.empty((BATCH, DIM), dtype=torch.float32).pin_memory() for _ in range(2)]
     lab_host = [torch.empty((BATCH, K), dtype=torch.int64).pin_memory() for _ in range(2)]
     d2h = sum(t.numel() * t.element_size() for t in res_host + lab_host)
     q_stage = torch.empty_like(q_dev)

@@ -83,6 +83,17 @@ int keds_index_search_ex(keds_index_t* idx, const float* q, int64_t nq, int k, f
 int keds_index_search2(keds_index_t* a, keds_index_t* b, const float* q, int64_t nq, int k,
                        float* Da, int64_t* Ia, float* Db, int64_t* Ib, uint32_t flags,
                        void* cuda_stream);
+/* The whole retrieval operator of src/trainer.py:198-230 in one call (device pointers only):
+ * search both databases, then per stream s in {img, txt}
+ *   feat_s[b][j][:] = rows_s[I_s[b][perm_s ? perm_s[j] : j]][:]      (nullable; [nq][k][d])
+ *   pool_s[b][:]    = sum_j w_j rows_s[I_s[b][j]][:]                 (nullable; [nq][d])
+ * pool_mode 0: no pool; 1: w = 1/k; 2: w = softmax_j(+-tau * D_s[b][j]) (minus under L2).
+ * Each neighbour row is read once for both outputs. perm_*: device int32[k] or NULL. */
+int keds_retrieve2(keds_index_t* img, keds_index_t* txt, const float* q, int64_t nq, int k,
+                   const int32_t* perm_img, const int32_t* perm_txt, int pool_mode, float tau,
+                   float* D_img, int64_t* I_img, float* D_txt, int64_t* I_txt, float* feat_img,
+                   float* feat_txt, float* pool_img, float* pool_txt, uint32_t flags,
+                   void* cuda_stream);
 /* Wait for the last asynchronous search on idx and report its device status. */
 int keds_index_sync(keds_index_t* idx, void* cuda_stream);
 int keds_index_last_stats(const keds_index_t* idx, keds_search_stats* out);

@@ -228,35 +228,46 @@ int ensure_q_map(keds_index* ix, int64_t rows_needed) {
   return 0;
 }
 
-int launch_exact(keds_index* ix, keds_index* dbix, int dbi, const float* q_dev, int64_t nq, int k,
-                 float* D, long long* I, int metric, cudaStream_t st) {
-  ExactParams ep;
-  ep.x_f32 = dbix->x_f32.as<float>();
-  ep.n_rows = dbix->n;
-  ep.d = ix->d;
-  ep.metric = metric;
-  ep.k = k;
-  ep.nq = static_cast<int>(nq);
-  ep.q_f32 = q_dev;
-  ep.flagged = ix->flagged[dbi].as<int>();
-  ep.n_flagged = ix->ctrl.as<int>() + dbi;
-  long long fc = (256ll << 20) / (4 * std::max<int64_t>(dbix->n, 1));
-  fc = std::max(1ll, std::min(64ll, fc));
-  fc = std::min<long long>(fc, nq);
-  ep.f_cap = static_cast<int>(fc);
-  CKS(ix->exact_scratch.ensure(static_cast<size_t>(fc) * dbix->n * 4));
-  ep.scratch = ix->exact_scratch.as<float>();
-  ep.D = D;
-  ep.I = I;
-  ep.id_offset = dbix->id_offset;
-  ep.barrier = ix->ctrl.as<unsigned int>() + 3 + dbi;
+// One cooperative launch serves the flagged queries of every database of the call (it returns at
+// once when nothing is flagged).
+int launch_exact(keds_index* ix, keds_index* dbs[2], int n_db, const float* q_dev, int64_t nq, int k,
+                 float* D[2], long long* I[2], int metric, cudaStream_t st) {
+  ExactParams2 ep;
+  memset(&ep, 0, sizeof ep);
+  ep.n_db = n_db;
+  size_t scratch_bytes = 0;
+  for (int i = 0; i < n_db; ++i) {
+    long long fc = (256ll << 20) / (4 * std::max<int64_t>(dbs[i]->n, 1));
+    fc = std::max(1ll, std::min(64ll, fc));
+    fc = std::min<long long>(fc, nq);
+    ep.e[i].f_cap = static_cast<int>(fc);
+    scratch_bytes = std::max(scratch_bytes, static_cast<size_t>(fc) * dbs[i]->n * 4);
+  }
+  CKS(ix->exact_scratch.ensure(scratch_bytes));
+  for (int i = 0; i < n_db; ++i) {
+    ExactParams& e = ep.e[i];
+    e.x_f32 = dbs[i]->x_f32.as<float>();
+    e.n_rows = dbs[i]->n;
+    e.d = ix->d;
+    e.metric = metric;
+    e.k = k;
+    e.nq = static_cast<int>(nq);
+    e.q_f32 = q_dev;
+    e.flagged = ix->flagged[i].as<int>();
+    e.n_flagged = ix->ctrl.as<int>() + i;
+    e.scratch = ix->exact_scratch.as<float>();
+    e.D = D[i];
+    e.I = I[i];
+    e.id_offset = dbs[i]->id_offset;
+    e.barrier = ix->ctrl.as<unsigned int>() + 3;
+  }
   const int dq = (ix->d + 3) & ~3;
   const size_t smem = static_cast<size_t>(EXACT_QG) * dq * 4 + K_MAX * 8 + 256 * 4 + 16 + 16 + 32;
   if (smem > 160 * 1024) return fail(KEDS_ERR_ARG, "d=%d too large for the exact fallback", ix->d);
   int per_sm = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_exact_fallback, EXACT_THREADS, smem));
   if (per_sm < 1) return fail(KEDS_ERR_CUDA, "exact fallback kernel does not fit on an SM");
-  const int grid = ix->num_sms * std::min(per_sm, 4);
+  const int grid = ix->num_sms * std::min(per_sm, 2);
   void* args[] = {&ep};
   CK(cudaLaunchCooperativeKernel((const void*)k_exact_fallback, dim3(grid), dim3(EXACT_THREADS), args,
                                  smem, st));
@@ -271,7 +282,6 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
   const int metric = (flags & KEDS_SEARCH_FORCE_IP) ? METRIC_IP : a->metric;
   CKS(set_kernel_attrs(a));
   CKS(a->ctrl.ensure(CTRL_WORDS * 4));
-  CK(cudaMemsetAsync(a->ctrl.p, 0, CTRL_WORDS * 4, st));
   for (int i = 0; i < n_db; ++i) CKS(a->flagged[i].ensure(static_cast<size_t>(nq) * 4));
 
   int64_t n_min = ix[0]->n, n_max = ix[0]->n;
@@ -287,6 +297,7 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
   a->stats.grid = pl.grid;
 
   if (pl.exact_only) {
+    CK(cudaMemsetAsync(a->ctrl.p, 0, CTRL_WORDS * 4, st));
     for (int i = 0; i < n_db; ++i) {
       k_flag_all<<<static_cast<unsigned>((nq + 255) / 256), 256, 0, st>>>(
           a->flagged[i].as<int>(), a->ctrl.as<int>() + i, static_cast<int>(nq));
@@ -304,7 +315,7 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
           static_cast<unsigned>(std::min<long long>((warps_needed * 32 + threads - 1) / threads, 4096));
       k_prep_rows<<<blocks, threads, 0, st>>>(q_dev, nq, a->d, a->d_pad,
                                               a->q_bf16.as<__nv_bfloat16>(), a->qstat.as<float4>(),
-                                              nullptr, nullptr);
+                                              nullptr, nullptr, a->ctrl.as<unsigned int>(), CTRL_WORDS);
       a->stats.launches++;
     }
     const size_t items = static_cast<size_t>(pl.n_items);
@@ -376,7 +387,7 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
     }
     rp.eps_scale = a->eps_scale;
     const size_t slots = static_cast<size_t>(pl.S) * CAP;
-    const size_t smem = static_cast<size_t>((a->d + 3) & ~3) * 4 + slots * 8 + pl.S * 4 + R_MAX * 8 +
+    const size_t smem = static_cast<size_t>((a->d + 3) & ~3) * 4 + slots * 8 + pl.S * 8 + R_MAX * 8 +
                         256 * 4 + 32 * 4 + 16 + 16;
     if (smem > 200 * 1024) return fail(KEDS_ERR_ARG, "re-rank shared memory %zu too large", smem);
     k_select_rerank<<<dim3(static_cast<unsigned>(nq), n_db), RERANK_THREADS, smem, st>>>(rp);
@@ -384,7 +395,7 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
     CK(cudaGetLastError());
   }
   if (!(flags & KEDS_SEARCH_NO_FALLBACK) || pl.exact_only) {
-    for (int i = 0; i < n_db; ++i) CKS(launch_exact(a, ix[i], i, q_dev, nq, k, D[i], I[i], metric, st));
+    CKS(launch_exact(a, ix, n_db, q_dev, nq, k, D, I, metric, st));
   }
   CK(cudaGetLastError());
   return 0;
@@ -581,7 +592,7 @@ int keds_index_add(keds_index_t* ix, const float* x, int64_t n) {
   const unsigned blocks = static_cast<unsigned>(std::min<int64_t>((n * 32 + 255) / 256, 148 * 16));
   k_prep_rows<<<blocks, 256>>>(ix->x_f32.as<float>() + n0 * d, n, ix->d, ix->d_pad,
                                ix->x_bf16.as<__nv_bfloat16>() + n0 * dp, nullptr,
-                               ix->bias.as<float>() + n0, ix->dbstat.as<unsigned int>());
+                               ix->bias.as<float>() + n0, ix->dbstat.as<unsigned int>(), nullptr, 0);
   const int64_t padded = (n1 + BN - 1) / BN * BN;
   if (padded > n1)
     k_fill_f32<<<static_cast<unsigned>((padded - n1 + 255) / 256), 256>>>(ix->bias.as<float>() + n1,
@@ -644,6 +655,65 @@ int keds_index_search2(keds_index_t* a, keds_index_t* b, const float* q, int64_t
   float* Dv[2] = {Da, Db};
   int64_t* Iv[2] = {Ia, Ib};
   return search_impl(v, 2, q, nq, k, Dv, Iv, flags, stream);
+}
+
+int keds_retrieve2(keds_index_t* img, keds_index_t* txt, const float* q, int64_t nq, int k,
+                   const int32_t* perm_img, const int32_t* perm_txt, int pool_mode, float tau,
+                   float* D_img, int64_t* I_img, float* D_txt, int64_t* I_txt, float* feat_img,
+                   float* feat_txt, float* pool_img, float* pool_txt, uint32_t flags, void* stream) {
+  if (!img || !txt || !q || !D_img || !I_img || !D_txt || !I_txt)
+    return fail(KEDS_ERR_ARG, "retrieve2: null handle, query or result pointer");
+  if (pool_mode < 0 || pool_mode > 2) return fail(KEDS_ERR_ARG, "retrieve2: pool_mode must be 0, 1 or 2");
+  if (!is_device_ptr(q) || !is_device_ptr(D_img) || !is_device_ptr(I_img) || !is_device_ptr(D_txt) ||
+      !is_device_ptr(I_txt))
+    return fail(KEDS_ERR_ARG, "retrieve2: device pointers only");
+  if (k > 1024) return fail(KEDS_ERR_ARG, "retrieve2: k=%d too large for the fused consumer", k);
+  keds_index* v[2] = {img, txt};
+  float* Dv[2] = {D_img, D_txt};
+  int64_t* Iv[2] = {I_img, I_txt};
+  CKS(search_impl(v, 2, q, nq, k, Dv, Iv, flags, stream));
+  if (nq == 0) return 0;
+  const bool want_pool = pool_mode != 0 && (pool_img || pool_txt);
+  if (!feat_img && !feat_txt && !want_pool) return 0;
+  DeviceGuard g(img->device);
+  Consume2Params cp;
+  memset(&cp, 0, sizeof cp);
+  cp.rows[0] = img->x_f32.as<float>();
+  cp.rows[1] = txt->x_f32.as<float>();
+  cp.I[0] = reinterpret_cast<const long long*>(I_img);
+  cp.I[1] = reinterpret_cast<const long long*>(I_txt);
+  cp.D[0] = D_img;
+  cp.D[1] = D_txt;
+  cp.perm[0] = perm_img;
+  cp.perm[1] = perm_txt;
+  cp.feat[0] = feat_img;
+  cp.feat[1] = feat_txt;
+  cp.pool[0] = want_pool ? pool_img : nullptr;
+  cp.pool[1] = want_pool ? pool_txt : nullptr;
+  cp.k = k;
+  cp.d = img->d;
+  cp.mode = pool_mode;
+  cp.metric = (flags & KEDS_SEARCH_FORCE_IP) ? METRIC_IP : img->metric;
+  cp.tau = tau;
+  // thread layout: JG groups of d/4 lanes (one float4 column each), JG neighbours in flight per column
+  int threads = 256;
+  cp.jgroups = 1;
+  size_t smem = (static_cast<size_t>(k) * 12 + 15) & ~size_t(15);
+  if ((img->d & 3) == 0) {
+    const int d4 = img->d >> 2;
+    if (d4 <= 1024) {
+      cp.jgroups = std::max(1, std::min({8, 1024 / d4, k}));
+      threads = (cp.jgroups * d4 + 31) / 32 * 32;
+    } else {
+      threads = 1024;
+    }
+    smem += static_cast<size_t>(cp.jgroups) * d4 * 16;
+  }
+  if (smem > 48 * 1024) return fail(KEDS_ERR_ARG, "retrieve2: d=%d too large for the fused consumer", img->d);
+  k_consume2<<<dim3(static_cast<unsigned>(nq), 2), threads, smem, static_cast<cudaStream_t>(stream)>>>(cp);
+  CK(cudaGetLastError());
+  img->stats.launches++;
+  return 0;
 }
 
 int keds_index_sync(keds_index_t* ix, void* stream) {

@@ -10,7 +10,7 @@ namespace keds {
 
 constexpr int METRIC_IP = 0;
 constexpr int METRIC_L2 = 1;
-constexpr int RERANK_THREADS = 256;
+constexpr int RERANK_THREADS = 512;
 constexpr int R_MAX = 512;      // most candidates one query may send to the fp32 re-rank
 constexpr int K_MAX = 2048;     // largest k (Faiss' GPU flat index has the same limit)
 constexpr int EXACT_THREADS = 256;
@@ -66,6 +66,51 @@ __device__ __forceinline__ float warp_exact_score(const float* __restrict__ q,
   return warp_sum(acc);
 }
 
+// R rows against one query with the loads of all R rows in flight together. Per row the
+// operations and their order are exactly those of warp_exact_score (bit-identical results).
+template <int R>
+__device__ __forceinline__ void warp_exact_score_multi(const float* __restrict__ q,
+                                                       const float* const (&x)[R], int d, int metric,
+                                                       int lane, float (&out)[R]) {
+  bool vec = (d & 3) == 0 && (reinterpret_cast<uintptr_t>(q) & 15) == 0;
+#pragma unroll
+  for (int r = 0; r < R; ++r) vec = vec && (reinterpret_cast<uintptr_t>(x[r]) & 15) == 0;
+  if (!vec) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) out[r] = warp_exact_score(q, x[r], d, metric, lane);
+    return;
+  }
+  const float4* q4 = reinterpret_cast<const float4*>(q);
+  const int d4 = d >> 2;
+  float acc[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) acc[r] = 0.f;
+#pragma unroll 2
+  for (int c = lane; c < d4; c += 32) {
+    const float4 b = q4[c];
+    float4 a[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) a[r] = __ldg(reinterpret_cast<const float4*>(x[r]) + c);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (metric == METRIC_IP) {
+        acc[r] = fmaf(a[r].x, b.x, acc[r]);
+        acc[r] = fmaf(a[r].y, b.y, acc[r]);
+        acc[r] = fmaf(a[r].z, b.z, acc[r]);
+        acc[r] = fmaf(a[r].w, b.w, acc[r]);
+      } else {
+        float t;
+        t = b.x - a[r].x; acc[r] = fmaf(t, t, acc[r]);
+        t = b.y - a[r].y; acc[r] = fmaf(t, t, acc[r]);
+        t = b.z - a[r].z; acc[r] = fmaf(t, t, acc[r]);
+        t = b.w - a[r].w; acc[r] = fmaf(t, t, acc[r]);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) out[r] = warp_sum(acc[r]);
+}
+
 // Total order used everywhere: better score first, then lower row id.
 // `rank_score` is the IP value, or minus the squared distance under L2.
 __device__ __forceinline__ unsigned long long order_key(float rank_score, uint32_t id) {
@@ -82,8 +127,12 @@ __device__ __forceinline__ unsigned long long order_key(float rank_score, uint32
 //   gmax[0] = max_r |bf16(x_r)| , gmax[1] = max_r |x_r - bf16(x_r)|   as float bit patterns
 __global__ void k_prep_rows(const float* __restrict__ x, long long n, int d, int d_pad,
                             __nv_bfloat16* __restrict__ out, float4* __restrict__ stat,
-                            float* __restrict__ bias, unsigned int* __restrict__ gmax) {
+                            float* __restrict__ bias, unsigned int* __restrict__ gmax,
+                            unsigned int* __restrict__ zero_words, int n_zero) {
   const int lane = threadIdx.x & 31;
+  // per-call control words (flag counters, error word, grid barrier) are cleared here instead of
+  // by a separate memset node in front of every search
+  if (zero_words != nullptr && blockIdx.x == 0 && threadIdx.x < n_zero) zero_words[threadIdx.x] = 0u;
   const long long warp0 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
   float mx_b = 0.f, mx_d = 0.f;
@@ -91,15 +140,40 @@ __global__ void k_prep_rows(const float* __restrict__ x, long long n, int d, int
     const float* xr = x + r * d;
     __nv_bfloat16* orow = out + r * d_pad;
     float n2 = 0.f, b2 = 0.f, e2 = 0.f;
-    for (int c = lane; c < d_pad; c += 32) {
-      const float v = c < d ? xr[c] : 0.f;
-      const __nv_bfloat16 b = __float2bfloat16_rn(v);
-      const float bf = __bfloat162float(b);
-      orow[c] = b;
-      n2 = fmaf(v, v, n2);
-      b2 = fmaf(bf, bf, b2);
-      const float e = v - bf;
-      e2 = fmaf(e, e, e2);
+    if ((d & 3) == 0 && (reinterpret_cast<uintptr_t>(xr) & 15) == 0) {
+      // 16-byte loads, 8-byte stores (d_pad is a multiple of 64, rows of `out` are 128-B aligned)
+      const float4* x4 = reinterpret_cast<const float4*>(xr);
+      uint2* o2 = reinterpret_cast<uint2*>(orow);
+      const int d4 = d >> 2, dp4 = d_pad >> 2;
+#pragma unroll 4
+      for (int c = lane; c < dp4; c += 32) {
+        const float4 v = c < d4 ? __ldg(x4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y);
+        const __nv_bfloat162 hi = __floats2bfloat162_rn(v.z, v.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const unsigned int*>(&lo);
+        pk.y = *reinterpret_cast<const unsigned int*>(&hi);
+        o2[c] = pk;
+        const float2 fl = __bfloat1622float2(lo), fh = __bfloat1622float2(hi);
+        n2 = fmaf(v.x, v.x, n2); n2 = fmaf(v.y, v.y, n2); n2 = fmaf(v.z, v.z, n2); n2 = fmaf(v.w, v.w, n2);
+        b2 = fmaf(fl.x, fl.x, b2); b2 = fmaf(fl.y, fl.y, b2); b2 = fmaf(fh.x, fh.x, b2); b2 = fmaf(fh.y, fh.y, b2);
+        float e;
+        e = v.x - fl.x; e2 = fmaf(e, e, e2);
+        e = v.y - fl.y; e2 = fmaf(e, e, e2);
+        e = v.z - fh.x; e2 = fmaf(e, e, e2);
+        e = v.w - fh.y; e2 = fmaf(e, e, e2);
+      }
+    } else {
+      for (int c = lane; c < d_pad; c += 32) {
+        const float v = c < d ? xr[c] : 0.f;
+        const __nv_bfloat16 b = __float2bfloat16_rn(v);
+        const float bf = __bfloat162float(b);
+        orow[c] = b;
+        n2 = fmaf(v, v, n2);
+        b2 = fmaf(bf, bf, b2);
+        const float e = v - bf;
+        e2 = fmaf(e, e, e2);
+      }
     }
     n2 = warp_sum(n2);
     b2 = warp_sum(b2);
@@ -163,6 +237,36 @@ __device__ __forceinline__ float block_max_f(float v, float* red) {
   return r;
 }
 
+// Radix-select step: given a 256-bin histogram, find the bin b with
+//   count(bins > b) < need <= count(bins >= b)
+// and publish bcast[0] = b, bcast[1] = need - count(bins > b). Needs blockDim.x >= 256 and a
+// uniform call; ends with a __syncthreads so every thread may read bcast.
+__device__ __forceinline__ void block_find_bin(const unsigned int* hist, int need, unsigned int* bcast) {
+  __shared__ unsigned int wtot[8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  unsigned int h = 0, suf = 0;
+  if (tid < 256) {
+    h = hist[tid];
+    suf = h;  // inclusive suffix sum inside the warp: bins tid .. warp end
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int up = __shfl_down_sync(0xffffffffu, suf, o);
+      if (lane + o < 32) suf += up;
+    }
+    if (lane == 0) wtot[warp] = suf;
+  }
+  __syncthreads();
+  if (tid < 256) {
+    for (int w = warp + 1; w < 8; ++w) suf += wtot[w];
+    const unsigned int excl = suf - h;
+    if (static_cast<int>(excl) < need && static_cast<int>(suf) >= need) {
+      bcast[0] = static_cast<unsigned int>(tid);
+      bcast[1] = static_cast<unsigned int>(need) - excl;
+    }
+  }
+  __syncthreads();
+}
+
 // k-th largest of keys[0..n) (1 <= k <= n), 4 x 8-bit radix passes with a shared histogram.
 __device__ unsigned int block_kth_largest(const unsigned int* keys, int n, int k,
                                           unsigned int* hist /*256*/, unsigned int* bcast /*2*/) {
@@ -176,17 +280,7 @@ __device__ unsigned int block_kth_largest(const unsigned int* keys, int n, int k
       if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-      int acc = 0, b = 255;
-      for (; b > 0; --b) {
-        const int h = static_cast<int>(hist[b]);
-        if (acc + h >= need) break;
-        acc += h;
-      }
-      bcast[0] = static_cast<unsigned int>(b);
-      bcast[1] = static_cast<unsigned int>(need - acc);
-    }
-    __syncthreads();
+    block_find_bin(hist, need, bcast);
     prefix |= bcast[0] << shift;
     mask |= 255u << shift;
     need = static_cast<int>(bcast[1]);
@@ -206,7 +300,8 @@ k_select_rerank(const RerankParams p) {
   unsigned int* keys = reinterpret_cast<unsigned int*>(qvec + ((p.d + 3) & ~3));
   unsigned int* ids = keys + slots;
   int* s_cnt = reinterpret_cast<int*>(ids + slots);                     // S
-  unsigned int* sel_id = reinterpret_cast<unsigned int*>(s_cnt + p.S);  // R_MAX
+  int* s_off = s_cnt + p.S;                                             // S
+  unsigned int* sel_id = reinterpret_cast<unsigned int*>(s_off + p.S);  // R_MAX
   float* sel_sc = reinterpret_cast<float*>(sel_id + R_MAX);             // R_MAX
   unsigned int* hist = reinterpret_cast<unsigned int*>(sel_sc + R_MAX); // 256
   float* red = reinterpret_cast<float*>(hist + 256);                    // 32
@@ -223,20 +318,49 @@ k_select_rerank(const RerankParams p) {
     th_max = fmaxf(th_max, p.cand_theta[item * BM + ql]);
   }
   th_max = block_max_f(th_max, red);  // (syncs)
-  for (int sl = tid; sl < slots; sl += blockDim.x) {
-    const int s = sl / CAP, e = sl % CAP;
-    if (e < s_cnt[s]) {
-      const long long item = (static_cast<long long>(db) * p.S + s) * p.n_qt + qt;
-      const uint2 en = p.cand[(item * CAP + e) * BM + ql];
-      const int pos = atomicAdd(&counters[0], 1);
-      float sc = __uint_as_float(en.x);
-      if (sc == 0.f) sc = 0.f;
-      keys[pos] = f32_to_key(sc);
-      ids[pos] = en.y;
+  // exclusive scan of the slice counts -> where each slice's run lands in keys[] / ids[]
+  // (S <= blockDim.x; one slice per thread)
+  {
+    const int c = tid < p.S ? s_cnt[tid] : 0;
+    int inc = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int up = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += up;
     }
+    int* wsum = reinterpret_cast<int*>(red);
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    int base = 0;
+    for (int w = 0; w < warp; ++w) base += wsum[w];
+    if (tid < p.S) s_off[tid] = base + inc - c;
+    if (tid == blockDim.x - 1) counters[0] = base + inc;
+    __syncthreads();
+  }
+  const int n = counters[0];
+  // each warp copies whole slices: a slice's run is contiguous in global memory (<= 512 B)
+  for (int s = warp; s < p.S; s += (blockDim.x >> 5)) {
+    const int cnt = s_cnt[s], off = s_off[s];
+    const long long item = (static_cast<long long>(db) * p.S + s) * p.n_qt + qt;
+    const uint2* run = p.cand + (item * BM + ql) * CAP;
+    unsigned int kmax = 0u;
+#pragma unroll
+    for (int e0 = 0; e0 < CAP; e0 += 32) {
+      const int e = e0 + lane;
+      if (e < cnt) {
+        const uint2 en = run[e];
+        float sc = __uint_as_float(en.x);
+        if (sc == 0.f) sc = 0.f;
+        const unsigned int key = f32_to_key(sc);
+        keys[off + e] = key;
+        ids[off + e] = en.y;
+        kmax = max(kmax, key);
+      }
+    }
+    kmax = __reduce_max_sync(0xffffffffu, kmax);
+    if (lane == 0) hist[s] = kmax;  // slice maximum (0 = empty slice), S <= 256
   }
   __syncthreads();
-  const int n = counters[0];
 
   // eps: |a - s| <= |dq| |bf(x)| + |q| |dx| + accumulation allowance
   const float4 qs = p.qstat[q];
@@ -249,7 +373,49 @@ k_select_rerank(const RerankParams p) {
 
   float tau = -INFINITY;
   if (n >= p.k) {
-    const unsigned int kth = block_kth_largest(keys, n, p.k, hist, bcast);
+    unsigned int kth = 0u;
+    bool fast = false;
+    if (p.S >= p.k) {
+      // t0 = k-th largest slice maximum <= k-th largest score overall, so the keys >= t0 (usually
+      // a few dozen) contain the whole approximate top-k: select among them by rank counting
+      if (tid < p.S) {
+        const unsigned int mine = hist[tid];
+        int rank = 0;
+        for (int u = 0; u < p.S; ++u) {
+          const unsigned int o = hist[u];
+          rank += (o > mine) || (o == mine && u < tid);
+        }
+        if (rank == p.k - 1) bcast[2] = mine;
+      }
+      __syncthreads();
+      const unsigned int t0 = bcast[2];
+      for (int i = tid; i < n; i += blockDim.x) {
+        const unsigned int key = keys[i];
+        if (key >= t0) {
+          const int pos = atomicAdd(&counters[2], 1);
+          if (pos < R_MAX) sel_id[pos] = key;  // sel_id doubles as the survivor list here
+        }
+      }
+      __syncthreads();
+      const int na = counters[2];
+      if (na <= R_MAX) {
+        fast = true;
+        for (int c = tid; c < na; c += blockDim.x) {
+          const unsigned int mine = sel_id[c];
+          int gt = 0, ge = 0;
+          for (int j = 0; j < na; ++j) {
+            const unsigned int o = sel_id[j];
+            gt += o > mine;
+            ge += o >= mine;
+          }
+          if (gt < p.k && ge >= p.k) bcast[3] = mine;
+        }
+        __syncthreads();
+        kth = bcast[3];
+      }
+      __syncthreads();
+    }
+    if (!fast) kth = block_kth_largest(keys, n, p.k, hist, bcast);
     tau = key_to_f32(kth) - 2.f * eps;
   }
   for (int i = tid; i < n; i += blockDim.x) {
@@ -268,10 +434,19 @@ k_select_rerank(const RerankParams p) {
   m = min(m, R_MAX);
 
   const float* xbase = p.x_f32[db];
-  for (int c = warp; c < m; c += (blockDim.x >> 5)) {
-    const float sc = warp_exact_score(qvec, xbase + static_cast<long long>(sel_id[c]) * p.d, p.d,
-                                      p.metric, lane);
-    if (lane == 0) sel_sc[c] = sc;
+  // three candidate rows per warp in flight (same per-row arithmetic as warp_exact_score)
+  for (int c0 = warp * 3; c0 < m; c0 += (blockDim.x >> 5) * 3) {
+    const float* xr[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+      xr[r] = xbase + static_cast<long long>(sel_id[min(c0 + r, m - 1)]) * p.d;
+    float sc[3];
+    warp_exact_score_multi<3>(qvec, xr, p.d, p.metric, lane, sc);
+    if (lane == 0) {
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+        if (c0 + r < m) sel_sc[c0 + r] = sc[r];
+    }
   }
   __syncthreads();
   float* Dq = p.D[db] + static_cast<long long>(q) * p.k;
@@ -331,10 +506,18 @@ __device__ __forceinline__ void grid_barrier(unsigned int* ctr, unsigned int& ta
   target += gridDim.x;
 }
 
+struct ExactParams2 {
+  int n_db;
+  ExactParams e[2];
+};
+
 __global__ void __launch_bounds__(EXACT_THREADS)
-k_exact_fallback(const ExactParams p) {
+k_exact_fallback(const ExactParams2 pp) {
+  unsigned int bar_target = gridDim.x;
+  for (int dbi = 0; dbi < pp.n_db; ++dbi) {
+  const ExactParams& p = pp.e[dbi];
   const int nfl = *reinterpret_cast<const volatile int*>(p.n_flagged);
-  if (nfl <= 0) return;
+  if (nfl <= 0) continue;
   extern __shared__ uint8_t ex_smem[];
   float* qs = reinterpret_cast<float*>(ex_smem);                       // EXACT_QG * dq
   const int dq = (p.d + 3) & ~3;
@@ -348,7 +531,6 @@ k_exact_fallback(const ExactParams p) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wpb = blockDim.x >> 5;
   const long long groups = (p.n_rows + 31) / 32;
-  unsigned int bar_target = gridDim.x;
 
   for (int r0 = 0; r0 < nfl; r0 += p.f_cap) {
     const int F = min(p.f_cap, nfl - r0);
@@ -407,17 +589,7 @@ k_exact_fallback(const ExactParams p) {
           if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
         }
         __syncthreads();
-        if (tid == 0) {
-          int acc = 0, b = 255;
-          for (; b > 0; --b) {
-            const int h = static_cast<int>(hist[b]);
-            if (acc + h >= need) break;
-            acc += h;
-          }
-          bcast[0] = static_cast<unsigned int>(b);
-          bcast[1] = static_cast<unsigned int>(need - acc);
-        }
-        __syncthreads();
+        block_find_bin(hist, need, bcast);
         prefix |= bcast[0] << shift;
         mask |= 255u << shift;
         need = static_cast<int>(bcast[1]);
@@ -488,6 +660,116 @@ k_exact_fallback(const ExactParams p) {
       __syncthreads();
     }
     grid_barrier(p.barrier, bar_target);
+  }
+  }  // databases
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused neighbour consumer for both streams: for stream s (0 = image, 1 = text) and query b
+//   feat[s][b][j][:] = rows_s[I_s[b][perm_s ? perm_s[j] : j]][:]                    (optional)
+//   pool[s][b][0][:] = sum_j w_j * rows_s[I_s[b][j]][:]                             (optional)
+// with w = uniform 1/k (mode 1) or softmax_j(sign * tau * D_s[b][j]) (mode 2; sign = -1 for L2).
+// Each neighbour row is read once for both outputs. One block per (query, stream).
+struct Consume2Params {
+  const float* rows[2];
+  const long long* I[2];
+  const float* D[2];
+  const int* perm[2];
+  float* feat[2];
+  float* pool[2];
+  int k, d, mode, metric, jgroups;
+  float tau;
+};
+
+__global__ void __launch_bounds__(1024)
+k_consume2(const Consume2Params p) {
+  extern __shared__ uint8_t c2_smem[];
+  long long* ids = reinterpret_cast<long long*>(c2_smem);  // k (rank order)
+  float* w = reinterpret_cast<float*>(ids + p.k);           // k (rank order)
+  const long long b = blockIdx.x;
+  const int s = blockIdx.y;
+  const int tid = threadIdx.x;
+  for (int j = tid; j < p.k; j += blockDim.x) {
+    ids[j] = p.I[s][b * p.k + j];
+    w[j] = 0.f;
+  }
+  __syncthreads();
+  if (p.pool[s] != nullptr && tid == 0) {
+    // k <= a few hundred: a serial pass is cheaper than a block reduction here
+    if (p.mode == 2) {
+      const float sign = p.metric == METRIC_L2 ? -1.f : 1.f;
+      float mx = -INFINITY;
+      for (int j = 0; j < p.k; ++j)
+        if (ids[j] >= 0) mx = fmaxf(mx, sign * p.tau * p.D[s][b * p.k + j]);
+      float sum = 0.f;
+      for (int j = 0; j < p.k; ++j) {
+        const float e = ids[j] >= 0 ? __expf(sign * p.tau * p.D[s][b * p.k + j] - mx) : 0.f;
+        w[j] = e;
+        sum += e;
+      }
+      const float inv = sum > 0.f ? 1.f / sum : 0.f;
+      for (int j = 0; j < p.k; ++j) w[j] *= inv;
+    } else {
+      for (int j = 0; j < p.k; ++j) w[j] = 1.f / static_cast<float>(p.k);
+    }
+  }
+  __syncthreads();
+  const float* rows = p.rows[s];
+  float* feat = p.feat[s] ? p.feat[s] + b * p.k * p.d : nullptr;
+  const int* perm = p.perm[s];
+  const bool vec = (p.d & 3) == 0 && ((reinterpret_cast<uintptr_t>(rows) |
+                                       reinterpret_cast<uintptr_t>(p.feat[s]) |
+                                       reinterpret_cast<uintptr_t>(p.pool[s])) & 15) == 0;
+  if (vec) {
+    // threads form JG groups of `cols` lanes; group g takes neighbours g, g+JG, ... so that
+    // several 3-KB row reads are in flight per column; partial pools meet in shared memory
+    const int d4 = p.d >> 2;
+    const int cols = min(d4, static_cast<int>(blockDim.x));
+    const int JG = max(1, min(p.jgroups, static_cast<int>(blockDim.x) / cols));
+    const int g = tid / cols, c0 = tid % cols;
+    float4* part = reinterpret_cast<float4*>(c2_smem + ((p.k * 12 + 15) & ~15));  // [JG][d4]
+    if (g < JG) {
+      for (int c = c0; c < d4; c += cols) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+        for (int jo = g; jo < p.k; jo += JG) {
+          const int j = perm ? perm[jo] : jo;       // output slot jo shows rank j
+          const long long id = ids[j];
+          const float4 v = id >= 0 ? __ldg(reinterpret_cast<const float4*>(rows + id * p.d) + c)
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+          if (feat) reinterpret_cast<float4*>(feat + static_cast<long long>(jo) * p.d)[c] = v;
+          const float wj = w[j];
+          acc.x = fmaf(wj, v.x, acc.x);
+          acc.y = fmaf(wj, v.y, acc.y);
+          acc.z = fmaf(wj, v.z, acc.z);
+          acc.w = fmaf(wj, v.w, acc.w);
+        }
+        if (p.pool[s]) part[g * d4 + c] = acc;
+      }
+    }
+    if (p.pool[s]) {
+      __syncthreads();
+      for (int c = tid; c < d4; c += blockDim.x) {
+        float4 acc = part[c];
+        for (int gg = 1; gg < JG; ++gg) {
+          const float4 o = part[gg * d4 + c];
+          acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+        }
+        reinterpret_cast<float4*>(p.pool[s] + b * p.d)[c] = acc;
+      }
+    }
+  } else {
+    for (int c = tid; c < p.d; c += blockDim.x) {
+      float acc = 0.f;
+      for (int jo = 0; jo < p.k; ++jo) {
+        const int j = perm ? perm[jo] : jo;
+        const long long id = ids[j];
+        const float v = id >= 0 ? rows[id * p.d + c] : 0.f;
+        if (feat) feat[static_cast<long long>(jo) * p.d + c] = v;
+        acc = fmaf(w[j], v, acc);
+      }
+      if (p.pool[s]) p.pool[s][b * p.d + c] = acc;
+    }
   }
 }
 

@@ -49,7 +49,7 @@ struct ScoreParams {
   int n_rows[2];     // rows per database
   int n_tiles[2];    // ceil(n_rows / BN)
   const float* bias[2];  // nullable; additive per-row bias padded with -inf to n_tiles * BN
-  uint2* cand;       // [n_items][CAP][BM] {approx score bits, row id}
+  uint2* cand;       // [n_items][BM][CAP] {approx score bits, row id}
   int* cand_cnt;     // [n_items][BM]
   float* cand_theta; // [n_items][BM]  everything the slice dropped scored <= theta
   uint32_t* err;     // device error word (0 = ok)
@@ -314,13 +314,14 @@ k_score_topk(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
-      // flush this item's candidates: [item][e][query] so each store instruction is one 256-B row
+      // flush this item's candidates as [item][query][e]: each query's run is contiguous, so the
+      // re-rank kernel reads it with one coalesced warp load
       int maxc = cnt;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) maxc = max(maxc, __shfl_xor_sync(0xffffffffu, maxc, o));
-      uint2* cbase = p.cand + static_cast<long long>(item) * CAP * BM + q_local;
+      uint2* cbase = p.cand + (static_cast<long long>(item) * BM + q_local) * CAP;
       for (int e = 0; e < maxc; ++e) {
-        if (e < cnt) cbase[static_cast<long long>(e) * BM] = lds64(slot0 + e * 256);
+        if (e < cnt) cbase[e] = lds64(slot0 + e * 256);
       }
       p.cand_cnt[static_cast<long long>(item) * BM + q_local] = cnt;
       p.cand_theta[static_cast<long long>(item) * BM + q_local] = theta;

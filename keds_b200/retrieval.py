@@ -125,11 +125,58 @@ def get_retrieved_features(feature, database, args=None, topk: int = 16, use_fai
     dev = torch.device("cuda", image_index.device)
     q = feature.detach().to(device=dev, dtype=torch.float32).contiguous()
     flags = 0 if use_faiss else _capi.SEARCH_FORCE_IP  # the torch branch ranks by raw inner product
-    (_, Ii), (_, It) = search2(image_index, text_index, q, topk, flags)
     perm = torch.randperm(topk) if use_faiss else None  # CPU generator, like the reference (:218)
-    topk_image_features = gather_rows(image_index, Ii, perm)
-    topk_text_features = gather_rows(text_index, It, None)
-    return topk_image_features.to(feature.device), topk_text_features.to(feature.device)
+    out = retrieve2(image_index, text_index, q, topk, perm_img=perm, want_feats=True, pool_mode=0, flags=flags)
+    return out["feat_img"].to(feature.device), out["feat_txt"].to(feature.device)
+
+
+POOL_NONE, POOL_MEAN, POOL_SOFTMAX = 0, 1, 2
+
+
+def retrieve2(image_index: GpuIndexFlat, text_index: GpuIndexFlat, q: torch.Tensor, topk: int = 16,
+              perm_img: Optional[torch.Tensor] = None, perm_txt: Optional[torch.Tensor] = None,
+              want_feats: bool = True, pool_mode: int = POOL_NONE, tau: float = 100.0, flags: int = 0,
+              out: Optional[dict] = None) -> dict:
+    """One native call for the whole operator: fused two-database search, then for each stream the
+    gathered neighbours [B, k, d] (image stream permuted by perm_img) and/or the pooled stream
+    [B, d].  `out` may carry preallocated tensors from a previous call (keys as returned) so a
+    steady-state loop allocates nothing."""
+    lib = _capi.load()
+    q = image_index._check_q_tensor(q)
+    dev, B, d, k = q.device, q.shape[0], image_index.d, int(topk)
+    o = out if out is not None else {}
+
+    def buf(name, shape, dtype):
+        t = o.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype or t.device != dev:
+            t = torch.empty(shape, dtype=dtype, device=dev)
+            o[name] = t
+        return t
+
+    Di, Ii = buf("D_img", (B, k), torch.float32), buf("I_img", (B, k), torch.int64)
+    Dt, It = buf("D_txt", (B, k), torch.float32), buf("I_txt", (B, k), torch.int64)
+    fi = ft = pi = pt = None
+    if want_feats:
+        fi, ft = buf("feat_img", (B, k, d), torch.float32), buf("feat_txt", (B, k, d), torch.float32)
+    if pool_mode != POOL_NONE:
+        pi, pt = buf("pool_img", (B, d), torch.float32), buf("pool_txt", (B, d), torch.float32)
+
+    def perm_ptr(p):
+        if p is None:
+            return 0, None
+        p = p.to(device=dev, dtype=torch.int32).contiguous()
+        assert p.numel() == k
+        return p.data_ptr(), p
+
+    pi_ptr, _keep1 = perm_ptr(perm_img)
+    pt_ptr, _keep2 = perm_ptr(perm_txt)
+    ptr = lambda t: 0 if t is None else t.data_ptr()
+    _capi.check(
+        lib.keds_retrieve2(image_index._h, text_index._h, q.data_ptr(), B, k, pi_ptr, pt_ptr, int(pool_mode),
+                           float(tau), Di.data_ptr(), Ii.data_ptr(), Dt.data_ptr(), It.data_ptr(), ptr(fi),
+                           ptr(ft), ptr(pi), ptr(pt), int(flags), _stream_ptr(image_index.device))
+    )
+    return o
 
 
 def get_extra_cap_features(feature, database, args=None, topk: int = 2):
@@ -154,8 +201,5 @@ def retrieve_and_pool(feature: torch.Tensor, database, topk: int = 16, tau: floa
     image_index, text_index = database[3], database[4]
     dev = torch.device("cuda", image_index.device)
     q = feature.detach().to(device=dev, dtype=torch.float32).contiguous()
-    (Di, Ii), (Dt, It) = search2(image_index, text_index, q, topk)
-    sign = -1.0 if image_index.metric_type == METRIC_L2 else 1.0
-    Wi = torch.softmax(sign * tau * Di, dim=1).unsqueeze(1)
-    Wt = torch.softmax(sign * tau * Dt, dim=1).unsqueeze(1)
-    return weighted_pool(image_index, Ii, Wi), weighted_pool(text_index, It, Wt)
+    o = retrieve2(image_index, text_index, q, topk, want_feats=False, pool_mode=POOL_SOFTMAX, tau=tau)
+    return o["pool_img"].unsqueeze(1), o["pool_txt"].unsqueeze(1)

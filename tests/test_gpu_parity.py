@@ -287,6 +287,31 @@ def test_gather_and_weighted_pool_match_oracle():
     assert (kr.gather_rows(ix, Ineg)[:, -1] == 0).all()
 
 
+@pytest.mark.parametrize("metric", ["ip", "l2"])
+def test_fused_retrieve2_matches_oracle(metric):
+    """one native call: two-DB search + gather (image stream permuted) + mean / softmax pool"""
+    a, b, q = unit(9000, 768, 91), unit(9000, 768, 92), unit(70, 768, 93)
+    ia, ib = build(a, metric), build(b, metric)
+    perm = torch.randperm(16, generator=torch.Generator().manual_seed(5))
+    qd = torch.from_numpy(q).cuda()
+    o = kr.retrieve2(ia, ib, qd, 16, perm_img=perm, want_feats=True, pool_mode=kr.POOL_SOFTMAX, tau=50.0)
+    ia.sync()
+    for name, db, ix_perm in (("img", a, perm.numpy()), ("txt", b, None)):
+        Dr, Ir = orc.search(db, q, 16, metric)
+        D, I = o[f"D_{name}"].cpu().numpy(), o[f"I_{name}"].cpu().numpy()
+        assert orc.compare_topk(Dr, Ir, D, I, db, q, metric, TIE_GAP, D_TOL)["ok"]
+        assert np.array_equal(o[f"feat_{name}"].cpu().numpy(), orc.gather(db, I, ix_perm))
+        W = orc.softmax_weights(D if metric == "ip" else -D, 50.0)
+        ref = orc.weighted_pool(db, I, W)[:, 0]
+        assert np.abs(o[f"pool_{name}"].cpu().numpy() - ref).max() < 2e-5   # fp32 softmax + 16-term sum
+    o2 = kr.retrieve2(ia, ib, qd, 16, want_feats=False, pool_mode=kr.POOL_MEAN, out=o)
+    ia.sync()
+    ref = orc.gather(a, o2["I_img"].cpu().numpy()).astype(np.float64).mean(1)
+    assert np.abs(o2["pool_img"].cpu().numpy() - ref).max() < 1e-6
+    pi, pt = kr.retrieve_and_pool(qd, [None, None, None, ia, ib], 16, tau=50.0)
+    assert pi.shape == (70, 1, 768) and pt.shape == (70, 1, 768)
+
+
 # ------------------------------------------------------------------ reference-shaped operators vs golden
 def test_get_retrieved_features_matches_the_reference_outputs(golden_dir):
     z = np.load(os.path.join(golden_dir, "retrieval.npz"))
