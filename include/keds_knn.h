@@ -97,11 +97,19 @@ int keds_retrieve2(keds_index_t* img, keds_index_t* txt, const float* q, int64_t
 /* Wait for the last asynchronous search on idx and report its device status. */
 int keds_index_sync(keds_index_t* idx, void* cuda_stream);
 int keds_index_last_stats(const keds_index_t* idx, keds_search_stats* out);
-/* Per-launch CUDA-event timing of the scoring kernel on the caller's stream (bench.py's roofline
- * leg). set_profiling(1) starts recording; profile() waits for the recorded launches and returns
- * their summed duration in ms and their count, then clears the record. */
+/* Timing of the scoring kernel inside a running loop (bench.py's roofline leg).
+ * set_profiling(1): every launch stamps %globaltimer at the start of its first CTA and the end of
+ *   its last one -- no stream events, the launch chain (programmatic dependent launches) is left
+ *   untouched; profile() returns the summed kernel duration in ms and the number of launches.
+ * set_profiling(2): diagnostic stage marks (stream events between the kernels, which serialise
+ *   them); profile_stages() splits stream time by stage.
+ * set_profiling(0): off. */
 int keds_index_set_profiling(keds_index_t* idx, int enable);
 int keds_index_profile(keds_index_t* idx, double* score_ms_total, int64_t* score_launches);
+/* Stage marks (mode 2): index 1 prep_rows, 2 score_topk, 3 select_rerank (+ neighbour consumer),
+ * 4 exact-fallback pair (indices 0 and 5 unused); each entry is the stream time from the previous
+ * mark to the end of that stage. n_stages >= 6. */
+int keds_index_profile_stages(keds_index_t* idx, double* ms_total, int64_t* launches, int n_stages);
 
 /* ---- neighbour gather / weighted pool ---------------------------------------------------------
  * W == NULL:  out[b][j][:] = base[I[b][perm ? perm[j] : j]][:]   (out: [B][k][d])
@@ -143,6 +151,9 @@ int keds_label_hits(const int64_t* I, int64_t nq, int kmax, const int64_t* label
  * Approximate (bf16 tensor-core) scores of q against every row: out [nq][ntotal] device float32.
  * Test hook for the GEMM alone; not a product path. */
 int keds_debug_scores(keds_index_t* idx, const float* q, int64_t nq, float* out, void* cuda_stream);
+/* Programmatic dependent launch between the kernels of a search (default on; env KEDS_NO_PDL=1
+ * turns the default off). Tuning/diagnostic switch; results do not depend on it. */
+int keds_index_set_pdl(keds_index_t* idx, int enable);
 /* Scale the certificate's error bound (1.0 = rigorous bound). Test hook for the fallback. */
 int keds_index_set_eps_scale(keds_index_t* idx, float scale);
 

@@ -60,6 +60,7 @@ SIGNATURES = {
     "keds_index_last_stats": (C.c_int, [_vp, C.POINTER(SearchStats)]),
     "keds_index_set_profiling": (C.c_int, [_vp, C.c_int]),
     "keds_index_profile": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "keds_index_profile_stages": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int]),
     "keds_gather_pool": (
         C.c_int,
         [_vp, C.c_int64, _vp, _vp, _vp, C.c_int64, C.c_int, C.c_int, C.c_int, _vp, _vp],
@@ -73,6 +74,7 @@ SIGNATURES = {
     "keds_label_hits": (C.c_int, [_vp, C.c_int64, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp]),
     "keds_debug_scores": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp]),
     "keds_index_set_eps_scale": (C.c_int, [_vp, C.c_float]),
+    "keds_index_set_pdl": (C.c_int, [_vp, C.c_int]),
     "keds_last_error": (C.c_char_p, []),
     "keds_device_count": (C.c_int, []),
     "keds_version": (C.c_char_p, []),

@@ -135,6 +135,7 @@ constexpr int CTRL_WORDS = 8;  // [0],[1] n_flagged per db, [2] err word, [3],[4
 constexpr int S_MAX = 192;
 constexpr size_t CAND_BUDGET = size_t(1) << 30;
 constexpr int64_t Q_PASS_MAX = 16384;
+constexpr size_t TIMING_RING = 8192;
 
 struct Plan {
   int exact_only = 0;
@@ -159,9 +160,15 @@ struct keds_index {
   int64_t tm_q_rows = 0;
   keds_search_stats stats;
   bool attrs_set = false;
+  bool use_pdl = true;
+  // in-kernel timing of the scoring kernel (bench.py's roofline leg): {min start, max end} ns
+  bool timing_on = false;
+  DevBuf timing;
+  size_t timing_launches = 0;
   // optional per-launch timing of the scoring kernel (bench.py's roofline leg)
   bool profiling = false;
-  std::vector<cudaEvent_t> prof_ev;  // pairs: [2i] before, [2i+1] after
+  std::vector<cudaEvent_t> prof_ev;
+  std::vector<int> prof_tag;
   size_t prof_used = 0;
 };
 
@@ -172,8 +179,32 @@ int set_kernel_attrs(keds_index* ix) {
   CK(cudaFuncSetAttribute(k_score_topk, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)SCORE_SMEM_BYTES));
   CK(cudaFuncSetAttribute(k_select_rerank, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  CK(cudaFuncSetAttribute(k_exact_fallback, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  CK(cudaFuncSetAttribute(k_exact_scores, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  CK(cudaFuncSetAttribute(k_exact_select, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  const char* no_pdl = getenv("KEDS_NO_PDL");
+  ix->use_pdl = !(no_pdl && no_pdl[0] == '1');
   ix->attrs_set = true;
+  return 0;
+}
+
+// Launch on `st`; with pdl the kernel may be scheduled while its predecessor in the stream is
+// still draining (programmatic dependent launch) -- every kernel of the search chain calls
+// griddep_wait() before it touches anything an earlier kernel wrote.
+template <typename... KArgs, typename... Args>
+int launch_k(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+             Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  CK(cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...));
   return 0;
 }
 
@@ -228,59 +259,83 @@ int ensure_q_map(keds_index* ix, int64_t rows_needed) {
   return 0;
 }
 
-// One cooperative launch serves the flagged queries of every database of the call (it returns at
-// once when nothing is flagged).
-int launch_exact(keds_index* ix, keds_index* dbs[2], int n_db, const float* q_dev, int64_t nq, int k,
-                 float* D[2], long long* I[2], int metric, cudaStream_t st) {
-  ExactParams2 ep;
-  memset(&ep, 0, sizeof ep);
-  ep.n_db = n_db;
-  size_t scratch_bytes = 0;
-  for (int i = 0; i < n_db; ++i) {
-    long long fc = (256ll << 20) / (4 * std::max<int64_t>(dbs[i]->n, 1));
-    fc = std::max(1ll, std::min(64ll, fc));
-    fc = std::min<long long>(fc, nq);
-    ep.e[i].f_cap = static_cast<int>(fc);
-    scratch_bytes = std::max(scratch_bytes, static_cast<size_t>(fc) * dbs[i]->n * 4);
+// Stage marks (diagnostics; they sit between the kernels, so they suppress the programmatic
+// overlap they measure around): tag 0 opens a search, tag t closes stage t
+// (1 prep_rows, 2 score_topk, 3 select_rerank, 4 exact fallback pair).
+constexpr int PROF_STAGES = 6;
+int prof_mark(keds_index* a, cudaStream_t st, int tag) {
+  if (!a->profiling) return 0;
+  if (a->prof_used == a->prof_ev.size()) {
+    cudaEvent_t e;
+    CK(cudaEventCreate(&e));
+    a->prof_ev.push_back(e);
+    a->prof_tag.push_back(0);
   }
-  CKS(ix->exact_scratch.ensure(scratch_bytes));
+  CK(cudaEventRecord(a->prof_ev[a->prof_used], st));
+  a->prof_tag[a->prof_used] = tag;
+  a->prof_used++;
+  return 0;
+}
+
+// The exact-fallback kernel pair, ceil(nq / f_cap) passes; every launch returns at once when its
+// slice of the flagged list is empty.
+int launch_exact(keds_index* ix, keds_index* dbs[2], int n_db, const float* q_dev, int64_t nq, int k,
+                 float* D[2], long long* I[2], int metric, const ConsumeParams& cons, cudaStream_t st) {
+  ExactParams ep;
+  memset(&ep, 0, sizeof ep);
+  ep.cons = cons;
+  ep.n_db = n_db;
+  ep.d = ix->d;
+  ep.metric = metric;
+  ep.k = k;
+  ep.q_f32 = q_dev;
+  // queries per pass: as many as a 512 MB score scratch holds (all of a 128-query batch at 0.5M rows)
+  int64_t rows_sum = 0;
+  for (int i = 0; i < n_db; ++i) rows_sum += dbs[i]->n;
+  long long fc = (512ll << 20) / (4 * std::max<int64_t>(rows_sum, 1));
+  fc = std::max(1ll, std::min<long long>(fc, nq));
+  ep.f_cap = static_cast<int>(fc);
+  CKS(ix->exact_scratch.ensure(static_cast<size_t>(fc) * rows_sum * 4));
+  float* scratch = ix->exact_scratch.as<float>();
   for (int i = 0; i < n_db; ++i) {
-    ExactParams& e = ep.e[i];
+    ExactDb& e = ep.db[i];
     e.x_f32 = dbs[i]->x_f32.as<float>();
     e.n_rows = dbs[i]->n;
-    e.d = ix->d;
-    e.metric = metric;
-    e.k = k;
-    e.nq = static_cast<int>(nq);
-    e.q_f32 = q_dev;
     e.flagged = ix->flagged[i].as<int>();
     e.n_flagged = ix->ctrl.as<int>() + i;
-    e.scratch = ix->exact_scratch.as<float>();
+    e.scratch = scratch;
+    scratch += static_cast<size_t>(fc) * dbs[i]->n;
     e.D = D[i];
     e.I = I[i];
     e.id_offset = dbs[i]->id_offset;
-    e.barrier = ix->ctrl.as<unsigned int>() + 3;
   }
   const int dq = (ix->d + 3) & ~3;
-  const size_t smem = static_cast<size_t>(EXACT_QG) * dq * 4 + K_MAX * 8 + 256 * 4 + 16 + 16 + 32;
-  if (smem > 160 * 1024) return fail(KEDS_ERR_ARG, "d=%d too large for the exact fallback", ix->d);
-  int per_sm = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_exact_fallback, EXACT_THREADS, smem));
-  if (per_sm < 1) return fail(KEDS_ERR_CUDA, "exact fallback kernel does not fit on an SM");
-  const int grid = ix->num_sms * std::min(per_sm, 2);
-  void* args[] = {&ep};
-  CK(cudaLaunchCooperativeKernel((const void*)k_exact_fallback, dim3(grid), dim3(EXACT_THREADS), args,
-                                 smem, st));
-  ix->stats.launches++;
+  const size_t smem_sc = static_cast<size_t>(EXACT_QG) * dq * 4;
+  const size_t smem_sel = static_cast<size_t>(cons.part4) * 16 + static_cast<size_t>(k) * 20 + 256 * 4 + 16 + 16 + 32;
+  if (smem_sc > 160 * 1024 || smem_sel > 160 * 1024)
+    return fail(KEDS_ERR_ARG, "d=%d / k=%d too large for the exact fallback", ix->d, k);
+  const int passes = static_cast<int>((nq + fc - 1) / fc);
+  const unsigned sel_blocks = static_cast<unsigned>(std::min<long long>(fc, 4 * ix->num_sms));
+  for (int pass = 0; pass < passes; ++pass) {
+    ep.pass = pass;
+    CKS(launch_k(ix->use_pdl, k_exact_scores, dim3(ix->num_sms * 2), dim3(EXACT_THREADS), smem_sc, st, ep));
+    CKS(launch_k(ix->use_pdl, k_exact_select, dim3(sel_blocks, n_db), dim3(EXACT_THREADS), smem_sel, st, ep));
+    ix->stats.launches += 2;
+  }
   return 0;
 }
 
 // One pass (<= Q_PASS_MAX queries). q_dev: device fp32 [nq][d]. D/I: device outputs.
+// cons_in (nullable): neighbour-consumer outputs for this pass, already offset to its first query.
 int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int k, float* D[2],
-                long long* I[2], uint32_t flags, cudaStream_t st, float* dump, int64_t ld_dump) {
+                long long* I[2], uint32_t flags, cudaStream_t st, float* dump, int64_t ld_dump,
+                const ConsumeParams* cons_in) {
   keds_index* a = ix[0];
   const int metric = (flags & KEDS_SEARCH_FORCE_IP) ? METRIC_IP : a->metric;
   CKS(set_kernel_attrs(a));
+  ConsumeParams cons;
+  memset(&cons, 0, sizeof cons);
+  if (cons_in) cons = *cons_in;
   CKS(a->ctrl.ensure(CTRL_WORDS * 4));
   for (int i = 0; i < n_db; ++i) CKS(a->flagged[i].ensure(static_cast<size_t>(nq) * 4));
 
@@ -309,13 +364,15 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
     CKS(ensure_q_map(a, q_rows));
     CKS(a->qstat.ensure(static_cast<size_t>(nq) * sizeof(float4)));
     {
+      CKS(prof_mark(a, st, 0));
       const int threads = 256;
       const long long warps_needed = nq;
       const unsigned blocks =
           static_cast<unsigned>(std::min<long long>((warps_needed * 32 + threads - 1) / threads, 4096));
-      k_prep_rows<<<blocks, threads, 0, st>>>(q_dev, nq, a->d, a->d_pad,
-                                              a->q_bf16.as<__nv_bfloat16>(), a->qstat.as<float4>(),
-                                              nullptr, nullptr, a->ctrl.as<unsigned int>(), CTRL_WORDS);
+      CKS(launch_k(a->use_pdl, k_prep_rows, dim3(blocks), dim3(threads), 0, st, q_dev,
+                   static_cast<long long>(nq), a->d, a->d_pad, a->q_bf16.as<__nv_bfloat16>(),
+                   a->qstat.as<float4>(), static_cast<float*>(nullptr), static_cast<unsigned int*>(nullptr),
+                   a->ctrl.as<unsigned int>(), CTRL_WORDS));
       a->stats.launches++;
     }
     const size_t items = static_cast<size_t>(pl.n_items);
@@ -342,22 +399,17 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
     sp.err = a->ctrl.as<uint32_t>() + 2;
     sp.dump = dump;
     sp.ld_dump = ld_dump;
-    cudaEvent_t ev_after = nullptr;
-    if (a->profiling) {
-      if (a->prof_used + 2 > a->prof_ev.size()) {
-        cudaEvent_t e0, e1;
-        CK(cudaEventCreate(&e0));
-        CK(cudaEventCreate(&e1));
-        a->prof_ev.push_back(e0);
-        a->prof_ev.push_back(e1);
-      }
-      CK(cudaEventRecord(a->prof_ev[a->prof_used], st));
-      ev_after = a->prof_ev[a->prof_used + 1];
-      a->prof_used += 2;
+    sp.timing = nullptr;
+    if (a->timing_on && a->timing_launches < TIMING_RING) {
+      // in-kernel %globaltimer stamps: one {min start, max end} pair per launch (the first
+      // TIMING_RING launches after set_profiling(1) are timed)
+      sp.timing = a->timing.as<unsigned long long>() + 2 * a->timing_launches;
+      a->timing_launches++;
     }
-    k_score_topk<<<pl.grid, SCORE_THREADS, SCORE_SMEM_BYTES, st>>>(
-        a->tm_q, ix[0]->tm_x, n_db > 1 ? ix[1]->tm_x : ix[0]->tm_x, sp);
-    if (ev_after) CK(cudaEventRecord(ev_after, st));
+    CKS(prof_mark(a, st, 1));
+    CKS(launch_k(a->use_pdl, k_score_topk, dim3(pl.grid), dim3(SCORE_THREADS), SCORE_SMEM_BYTES, st, a->tm_q,
+                 ix[0]->tm_x, n_db > 1 ? ix[1]->tm_x : ix[0]->tm_x, sp));
+    CKS(prof_mark(a, st, 2));
     a->stats.launches++;
     CK(cudaGetLastError());
     if (dump) return 0;
@@ -386,16 +438,21 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
       rp.n_flagged[i] = a->ctrl.as<int>() + i;
     }
     rp.eps_scale = a->eps_scale;
+    rp.cons = cons;
     const size_t slots = static_cast<size_t>(pl.S) * CAP;
-    const size_t smem = static_cast<size_t>((a->d + 3) & ~3) * 4 + slots * 8 + pl.S * 8 + R_MAX * 8 +
-                        256 * 4 + 32 * 4 + 16 + 16;
+    const size_t smem = static_cast<size_t>((a->d + 3) & ~3) * 4 + static_cast<size_t>(cons.part4) * 16 +
+                        slots * 8 + pl.S * 8 + R_MAX * 8 + 256 * 4 + 32 * 4 + 16 + 16 +
+                        static_cast<size_t>(k) * 12;
     if (smem > 200 * 1024) return fail(KEDS_ERR_ARG, "re-rank shared memory %zu too large", smem);
-    k_select_rerank<<<dim3(static_cast<unsigned>(nq), n_db), RERANK_THREADS, smem, st>>>(rp);
+    CKS(launch_k(a->use_pdl, k_select_rerank, dim3(static_cast<unsigned>(nq), n_db), dim3(RERANK_THREADS), smem,
+                 st, rp));
+    CKS(prof_mark(a, st, 3));
     a->stats.launches++;
     CK(cudaGetLastError());
   }
   if (!(flags & KEDS_SEARCH_NO_FALLBACK) || pl.exact_only) {
-    CKS(launch_exact(a, ix, n_db, q_dev, nq, k, D, I, metric, st));
+    CKS(launch_exact(a, ix, n_db, q_dev, nq, k, D, I, metric, cons, st));
+    CKS(prof_mark(a, st, 4));
   }
   CK(cudaGetLastError());
   return 0;
@@ -422,7 +479,7 @@ int finish_sync(keds_index* a, cudaStream_t st) {
 }
 
 int search_impl(keds_index* ix[2], int n_db, const float* q, int64_t nq, int k, float* D[2],
-                int64_t* I[2], uint32_t flags, void* stream) {
+                int64_t* I[2], uint32_t flags, void* stream, const ConsumeParams* cons = nullptr) {
   keds_index* a = ix[0];
   if (!a || !q || nq < 0 || k <= 0) return fail(KEDS_ERR_ARG, "search: null handle/query or bad nq/k");
   if (k > K_MAX) return fail(KEDS_ERR_ARG, "search: k=%d exceeds the maximum %d", k, K_MAX);
@@ -470,6 +527,7 @@ int search_impl(keds_index* ix[2], int n_db, const float* q, int64_t nq, int k, 
   bool any_empty = false;
   for (int i = 0; i < n_db; ++i) any_empty = any_empty || ix[i]->n == 0;
   if (any_empty) {
+    if (cons) return fail(KEDS_ERR_ARG, "retrieve2: both databases must hold rows");
     for (int i = 0; i < n_db; ++i) {
       if (ix[i]->n != 0) {
         keds_index* one[2] = {ix[i], nullptr};
@@ -479,7 +537,7 @@ int search_impl(keds_index* ix[2], int n_db, const float* q, int64_t nq, int k, 
           const int64_t nb = std::min<int64_t>(Q_PASS_MAX, nq - q0);
           float* Dp[2] = {D1[0] + q0 * k, nullptr};
           long long* Ip[2] = {I1[0] + q0 * k, nullptr};
-          CKS(search_pass(one, 1, qd + q0 * a->d, nb, k, Dp, Ip, flags, st, nullptr, 0));
+          CKS(search_pass(one, 1, qd + q0 * a->d, nb, k, Dp, Ip, flags, st, nullptr, 0, nullptr));
           if (q0 + nb < nq) CKS(finish_sync(one[0], st));
         }
       } else {
@@ -494,8 +552,16 @@ int search_impl(keds_index* ix[2], int n_db, const float* q, int64_t nq, int k, 
       const int64_t nb = std::min<int64_t>(Q_PASS_MAX, nq - q0);
       float* Dp[2] = {Dd[0] + q0 * k, n_db > 1 ? Dd[1] + q0 * k : nullptr};
       long long* Ip[2] = {Id[0] + q0 * k, n_db > 1 ? Id[1] + q0 * k : nullptr};
-      CKS(search_pass(ix, n_db, qd + q0 * a->d, nb, k, Dp, Ip, flags, st, nullptr, 0));
-      // scratch is reused by the next pass: drain this one first
+      ConsumeParams cp;
+      if (cons) {
+        cp = *cons;
+        for (int s = 0; s < 2; ++s) {
+          if (cp.feat[s]) cp.feat[s] += q0 * k * a->d;
+          if (cp.pool[s]) cp.pool[s] += q0 * a->d;
+        }
+      }
+      CKS(search_pass(ix, n_db, qd + q0 * a->d, nb, k, Dp, Ip, flags, st, nullptr, 0, cons ? &cp : nullptr));
+      // the per-call status words are rewritten by the next pass: read this pass's first
       if (q0 + nb < nq) CKS(finish_sync(a, st));
     }
   }
@@ -567,7 +633,7 @@ void keds_index_free(keds_index_t* ix) {
   DevBuf* bufs[] = {&ix->x_f32, &ix->x_bf16, &ix->bias, &ix->dbstat, &ix->q_f32, &ix->q_bf16,
                     &ix->qstat, &ix->cand, &ix->cand_cnt, &ix->cand_theta, &ix->flagged[0],
                     &ix->flagged[1], &ix->ctrl, &ix->exact_scratch, &ix->D_stage[0], &ix->D_stage[1],
-                    &ix->I_stage[0], &ix->I_stage[1]};
+                    &ix->I_stage[0], &ix->I_stage[1], &ix->timing};
   for (DevBuf* b : bufs) b->release();
   for (cudaEvent_t e : ix->prof_ev) cudaEventDestroy(e);
   delete ix;
@@ -630,6 +696,14 @@ int keds_index_set_id_offset(keds_index_t* ix, int64_t offset) {
   return 0;
 }
 
+int keds_index_set_pdl(keds_index_t* ix, int enable) {
+  if (!ix) return fail(KEDS_ERR_ARG, "set_pdl: null handle");
+  DeviceGuard g(ix->device);
+  CKS(set_kernel_attrs(ix));
+  ix->use_pdl = enable != 0;
+  return 0;
+}
+
 int keds_index_set_eps_scale(keds_index_t* ix, float scale) {
   if (!ix || !(scale >= 0.f)) return fail(KEDS_ERR_ARG, "set_eps_scale: bad argument");
   ix->eps_scale = scale;
@@ -671,49 +745,28 @@ int keds_retrieve2(keds_index_t* img, keds_index_t* txt, const float* q, int64_t
   keds_index* v[2] = {img, txt};
   float* Dv[2] = {D_img, D_txt};
   int64_t* Iv[2] = {I_img, I_txt};
-  CKS(search_impl(v, 2, q, nq, k, Dv, Iv, flags, stream));
-  if (nq == 0) return 0;
   const bool want_pool = pool_mode != 0 && (pool_img || pool_txt);
-  if (!feat_img && !feat_txt && !want_pool) return 0;
-  DeviceGuard g(img->device);
-  Consume2Params cp;
+  ConsumeParams cp;
   memset(&cp, 0, sizeof cp);
-  cp.rows[0] = img->x_f32.as<float>();
-  cp.rows[1] = txt->x_f32.as<float>();
-  cp.I[0] = reinterpret_cast<const long long*>(I_img);
-  cp.I[1] = reinterpret_cast<const long long*>(I_txt);
-  cp.D[0] = D_img;
-  cp.D[1] = D_txt;
+  cp.enabled = (feat_img || feat_txt || want_pool) ? 1 : 0;
+  cp.mode = want_pool ? pool_mode : 0;
+  cp.tau = tau;
   cp.perm[0] = perm_img;
   cp.perm[1] = perm_txt;
   cp.feat[0] = feat_img;
   cp.feat[1] = feat_txt;
   cp.pool[0] = want_pool ? pool_img : nullptr;
   cp.pool[1] = want_pool ? pool_txt : nullptr;
-  cp.k = k;
-  cp.d = img->d;
-  cp.mode = pool_mode;
-  cp.metric = (flags & KEDS_SEARCH_FORCE_IP) ? METRIC_IP : img->metric;
-  cp.tau = tau;
-  // thread layout: JG groups of d/4 lanes (one float4 column each), JG neighbours in flight per column
-  int threads = 256;
+  // the ranking block (512 threads) splits into groups of d/4 lanes, one float4 column per lane,
+  // each group streaming different neighbours; the groups' partial pools meet in shared memory
   cp.jgroups = 1;
-  size_t smem = (static_cast<size_t>(k) * 12 + 15) & ~size_t(15);
+  cp.part4 = 0;
   if ((img->d & 3) == 0) {
     const int d4 = img->d >> 2;
-    if (d4 <= 1024) {
-      cp.jgroups = std::max(1, std::min({8, 1024 / d4, k}));
-      threads = (cp.jgroups * d4 + 31) / 32 * 32;
-    } else {
-      threads = 1024;
-    }
-    smem += static_cast<size_t>(cp.jgroups) * d4 * 16;
+    cp.jgroups = std::max(1, std::min({4, RERANK_THREADS / std::max(1, std::min(d4, RERANK_THREADS)), k}));
+    cp.part4 = cp.jgroups * d4;
   }
-  if (smem > 48 * 1024) return fail(KEDS_ERR_ARG, "retrieve2: d=%d too large for the fused consumer", img->d);
-  k_consume2<<<dim3(static_cast<unsigned>(nq), 2), threads, smem, static_cast<cudaStream_t>(stream)>>>(cp);
-  CK(cudaGetLastError());
-  img->stats.launches++;
-  return 0;
+  return search_impl(v, 2, q, nq, k, Dv, Iv, flags, stream, cp.enabled ? &cp : nullptr);
 }
 
 int keds_index_sync(keds_index_t* ix, void* stream) {
@@ -724,23 +777,68 @@ int keds_index_sync(keds_index_t* ix, void* stream) {
 
 int keds_index_set_profiling(keds_index_t* ix, int enable) {
   if (!ix) return fail(KEDS_ERR_ARG, "set_profiling: null handle");
-  ix->profiling = enable != 0;
+  DeviceGuard g(ix->device);
+  ix->profiling = enable == 2;  // stage marks (stream events between the kernels)
   ix->prof_used = 0;
+  ix->timing_on = enable == 1;  // in-kernel timer of the scoring kernel, launch chain untouched
+  ix->timing_launches = 0;
+  if (ix->timing_on) {
+    CKS(ix->timing.ensure(TIMING_RING * 16));
+    std::vector<unsigned long long> init(TIMING_RING * 2);
+    for (size_t i = 0; i < TIMING_RING; ++i) {
+      init[2 * i] = ~0ull;
+      init[2 * i + 1] = 0ull;
+    }
+    CK(cudaMemcpy(ix->timing.p, init.data(), TIMING_RING * 16, cudaMemcpyHostToDevice));
+  }
   return 0;
 }
 
 int keds_index_profile(keds_index_t* ix, double* score_ms_total, int64_t* score_launches) {
   if (!ix || !score_ms_total || !score_launches) return fail(KEDS_ERR_ARG, "profile: null argument");
-  DeviceGuard g(ix->device);
-  double tot = 0.0;
-  for (size_t i = 0; i + 1 < ix->prof_used; i += 2) {
-    CK(cudaEventSynchronize(ix->prof_ev[i + 1]));
-    float ms = 0.f;
-    CK(cudaEventElapsedTime(&ms, ix->prof_ev[i], ix->prof_ev[i + 1]));
-    tot += ms;
+  if (ix->timing_on) {
+    DeviceGuard g(ix->device);
+    CK(cudaDeviceSynchronize());
+    std::vector<unsigned long long> t(TIMING_RING * 2);
+    CK(cudaMemcpy(t.data(), ix->timing.p, TIMING_RING * 16, cudaMemcpyDeviceToHost));
+    const size_t used = std::min(ix->timing_launches, TIMING_RING);
+    double ms = 0.0;
+    int64_t cnt = 0;
+    for (size_t i = 0; i < used; ++i) {
+      if (t[2 * i + 1] > t[2 * i]) {
+        ms += static_cast<double>(t[2 * i + 1] - t[2 * i]) * 1e-6;
+        cnt++;
+      }
+    }
+    *score_ms_total = ms;
+    *score_launches = cnt;
+    return keds_index_set_profiling(ix, 1);  // re-arm the ring
   }
-  *score_ms_total = tot;
-  *score_launches = static_cast<int64_t>(ix->prof_used / 2);
+  double ms[PROF_STAGES];
+  int64_t cnt[PROF_STAGES];
+  CKS(keds_index_profile_stages(ix, ms, cnt, PROF_STAGES));
+  *score_ms_total = ms[2];
+  *score_launches = cnt[2];
+  return 0;
+}
+
+int keds_index_profile_stages(keds_index_t* ix, double* ms_total, int64_t* launches, int n_stages) {
+  if (!ix || !ms_total || !launches || n_stages < PROF_STAGES)
+    return fail(KEDS_ERR_ARG, "profile_stages: need room for %d stages", PROF_STAGES);
+  DeviceGuard g(ix->device);
+  for (int t = 0; t < n_stages; ++t) {
+    ms_total[t] = 0.0;
+    launches[t] = 0;
+  }
+  for (size_t i = 1; i < ix->prof_used; ++i) {
+    const int tag = ix->prof_tag[i];
+    if (tag <= 0 || tag >= PROF_STAGES) continue;  // tag 0 opens a new search
+    CK(cudaEventSynchronize(ix->prof_ev[i]));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, ix->prof_ev[i - 1], ix->prof_ev[i]));
+    ms_total[tag] += ms;
+    launches[tag]++;
+  }
   ix->prof_used = 0;
   return 0;
 }
@@ -761,7 +859,7 @@ int keds_debug_scores(keds_index_t* ix, const float* q, int64_t nq, float* out, 
   keds_index* v[2] = {ix, nullptr};
   float* Dv[2] = {nullptr, nullptr};
   long long* Iv[2] = {nullptr, nullptr};
-  CKS(search_pass(v, 1, q, nq, 1, Dv, Iv, 0u, st, out, ix->n));
+  CKS(search_pass(v, 1, q, nq, 1, Dv, Iv, 0u, st, out, ix->n, nullptr));
   return finish_sync(ix, st);
 }
 

@@ -10,7 +10,7 @@ namespace keds {
 
 constexpr int METRIC_IP = 0;
 constexpr int METRIC_L2 = 1;
-constexpr int RERANK_THREADS = 512;
+constexpr int RERANK_THREADS = 256;  // ~112 regs/thread: two blocks per SM, one wave for 2 x 128 queries
 constexpr int R_MAX = 512;      // most candidates one query may send to the fp32 re-rank
 constexpr int K_MAX = 2048;     // largest k (Faiss' GPU flat index has the same limit)
 constexpr int EXACT_THREADS = 256;
@@ -85,25 +85,37 @@ __device__ __forceinline__ void warp_exact_score_multi(const float* __restrict__
   float acc[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) acc[r] = 0.f;
-#pragma unroll 2
-  for (int c = lane; c < d4; c += 32) {
-    const float4 b = q4[c];
-    float4 a[R];
+  constexpr int U = 6;  // float4 chunks per lane per block: d = 768 is exactly one block
+  for (int cb = 0; cb < d4; cb += 32 * U) {
+    float4 a[R][U];
+    // issue every load of the block (R rows x U chunks) before the first use
 #pragma unroll
-    for (int r = 0; r < R; ++r) a[r] = __ldg(reinterpret_cast<const float4*>(x[r]) + c);
+    for (int u = 0; u < U; ++u) {
+      const int c = cb + u * 32 + lane;
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      if (metric == METRIC_IP) {
-        acc[r] = fmaf(a[r].x, b.x, acc[r]);
-        acc[r] = fmaf(a[r].y, b.y, acc[r]);
-        acc[r] = fmaf(a[r].z, b.z, acc[r]);
-        acc[r] = fmaf(a[r].w, b.w, acc[r]);
-      } else {
-        float t;
-        t = b.x - a[r].x; acc[r] = fmaf(t, t, acc[r]);
-        t = b.y - a[r].y; acc[r] = fmaf(t, t, acc[r]);
-        t = b.z - a[r].z; acc[r] = fmaf(t, t, acc[r]);
-        t = b.w - a[r].w; acc[r] = fmaf(t, t, acc[r]);
+      for (int r = 0; r < R; ++r)
+        a[r][u] = c < d4 ? __ldg(reinterpret_cast<const float4*>(x[r]) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int c = cb + u * 32 + lane;
+      if (c < d4) {
+        const float4 b = q4[c];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          if (metric == METRIC_IP) {
+            acc[r] = fmaf(a[r][u].x, b.x, acc[r]);
+            acc[r] = fmaf(a[r][u].y, b.y, acc[r]);
+            acc[r] = fmaf(a[r][u].z, b.z, acc[r]);
+            acc[r] = fmaf(a[r][u].w, b.w, acc[r]);
+          } else {
+            float t;
+            t = b.x - a[r][u].x; acc[r] = fmaf(t, t, acc[r]);
+            t = b.y - a[r][u].y; acc[r] = fmaf(t, t, acc[r]);
+            t = b.z - a[r][u].z; acc[r] = fmaf(t, t, acc[r]);
+            t = b.w - a[r][u].w; acc[r] = fmaf(t, t, acc[r]);
+          }
+        }
       }
     }
   }
@@ -130,8 +142,10 @@ __global__ void k_prep_rows(const float* __restrict__ x, long long n, int d, int
                             float* __restrict__ bias, unsigned int* __restrict__ gmax,
                             unsigned int* __restrict__ zero_words, int n_zero) {
   const int lane = threadIdx.x & 31;
-  // per-call control words (flag counters, error word, grid barrier) are cleared here instead of
-  // by a separate memset node in front of every search
+  griddep_wait();               // earlier kernels of the stream may still read what is rewritten here
+  griddep_launch_dependents();  // the scoring kernel may start its prologue
+  // per-call control words (flag counters, error word) are cleared here instead of by a separate
+  // memset node in front of every search
   if (zero_words != nullptr && blockIdx.x == 0 && threadIdx.x < n_zero) zero_words[threadIdx.x] = 0u;
   const long long warp0 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
@@ -207,7 +221,112 @@ __global__ void k_fill_f32(float* p, long long n, float v) {
 // C = { n : a(n) >= tau }, tau = a_(k) - 2 eps, contains the exact answer provided no slice
 // dropped a row scoring >= tau, i.e. every slice threshold theta < tau. If that (or |C| <= R_MAX)
 // fails the query is queued for the exact fallback instead of being answered from C.
+// ---------------------------------------------------------------------------------------------
+// Neighbour consumer, run by the block that has just ranked query b of stream s (0 = image,
+// 1 = text) while the neighbour rows are still hot in L1/L2:
+//   feat[s][b][j][:] = rows_s[id[perm_s ? perm_s[j] : j]][:]                       (optional)
+//   pool[s][b][:]    = sum_j w_j * rows_s[id[j]][:]                                (optional)
+// w = 1/k (mode 1) or softmax_j(sign * tau * D[j]) (mode 2; sign = -1 under L2).
+// Replaces the CPU index_select + randperm copy + H2D of src/trainer.py:214-230 and the attn@v
+// shaped reduction of src/model/model.py:69-73.
+struct ConsumeParams {
+  int enabled;      // 0: plain search
+  int mode;         // 0 no pool, 1 mean, 2 softmax
+  int jgroups;      // thread groups working on different neighbours of the same column
+  int part4;        // float4 slots of shared scratch: jgroups * d / 4 (0 when d % 4 != 0)
+  float tau;
+  const int* perm[2];
+  float* feat[2];   // [nq][k][d]
+  float* pool[2];   // [nq][d]
+};
+
+// top_id: local row ids in rank order (0xFFFFFFFF = padding), top_d: their D values.
+__device__ __forceinline__ void consume_query(const ConsumeParams& c, const float* __restrict__ rows,
+                                              int s, long long b, int k, int d, int metric,
+                                              const unsigned int* top_id, const float* top_d,
+                                              float* w, float4* part) {
+  const int tid = threadIdx.x;
+  float* pool = c.mode != 0 ? c.pool[s] : nullptr;
+  float* feat = c.feat[s] ? c.feat[s] + b * k * d : nullptr;
+  if (pool == nullptr && feat == nullptr) return;
+  if (tid == 0) {
+    // k is small (16 in KEDs): a serial pass beats a block reduction
+    if (pool != nullptr && c.mode == 2) {
+      const float sign = metric == METRIC_L2 ? -1.f : 1.f;
+      float mx = -INFINITY;
+      for (int j = 0; j < k; ++j)
+        if (top_id[j] != 0xFFFFFFFFu) mx = fmaxf(mx, sign * c.tau * top_d[j]);
+      float sum = 0.f;
+      for (int j = 0; j < k; ++j) {
+        const float e = top_id[j] != 0xFFFFFFFFu ? __expf(sign * c.tau * top_d[j] - mx) : 0.f;
+        w[j] = e;
+        sum += e;
+      }
+      const float inv = sum > 0.f ? 1.f / sum : 0.f;
+      for (int j = 0; j < k; ++j) w[j] *= inv;
+    } else {
+      for (int j = 0; j < k; ++j) w[j] = 1.f / static_cast<float>(k);
+    }
+  }
+  __syncthreads();
+  const int* perm = c.perm[s];
+  const bool vec = c.part4 > 0 && ((reinterpret_cast<uintptr_t>(rows) | reinterpret_cast<uintptr_t>(c.feat[s]) |
+                                    reinterpret_cast<uintptr_t>(c.pool[s])) & 15) == 0;
+  if (vec) {
+    // threads form JG groups of `cols` lanes; group g takes neighbours g, g+JG, ... so several
+    // 3-KB row reads are in flight per column; partial pools meet in shared memory
+    const int d4 = d >> 2;
+    const int cols = min(d4, static_cast<int>(blockDim.x));
+    const int JG = max(1, min(c.jgroups, static_cast<int>(blockDim.x) / cols));
+    const int g = tid / cols, c0 = tid % cols;
+    if (g < JG) {
+      for (int col = c0; col < d4; col += cols) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+        for (int jo = g; jo < k; jo += JG) {
+          const int j = perm ? perm[jo] : jo;  // output slot jo shows rank j
+          const unsigned int id = top_id[j];
+          const float4 v = id != 0xFFFFFFFFu
+                               ? __ldg(reinterpret_cast<const float4*>(rows + static_cast<long long>(id) * d) + col)
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+          if (feat) reinterpret_cast<float4*>(feat + static_cast<long long>(jo) * d)[col] = v;
+          const float wj = w[j];
+          acc.x = fmaf(wj, v.x, acc.x);
+          acc.y = fmaf(wj, v.y, acc.y);
+          acc.z = fmaf(wj, v.z, acc.z);
+          acc.w = fmaf(wj, v.w, acc.w);
+        }
+        if (pool) part[g * d4 + col] = acc;
+      }
+    }
+    if (pool) {
+      __syncthreads();
+      for (int col = tid; col < d4; col += blockDim.x) {
+        float4 acc = part[col];
+        for (int gg = 1; gg < JG; ++gg) {
+          const float4 o = part[gg * d4 + col];
+          acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+        }
+        reinterpret_cast<float4*>(pool + b * d)[col] = acc;
+      }
+    }
+  } else {
+    for (int col = tid; col < d; col += blockDim.x) {
+      float acc = 0.f;
+      for (int jo = 0; jo < k; ++jo) {
+        const int j = perm ? perm[jo] : jo;
+        const unsigned int id = top_id[j];
+        const float v = id != 0xFFFFFFFFu ? rows[static_cast<long long>(id) * d + col] : 0.f;
+        if (feat) feat[static_cast<long long>(jo) * d + col] = v;
+        acc = fmaf(w[j], v, acc);
+      }
+      if (pool) pool[b * d + col] = acc;
+    }
+  }
+}
+
 struct RerankParams {
+  ConsumeParams cons;
   int n_db, n_qt, S, nq, k, d, metric;
   const uint2* cand;
   const int* cand_cnt;
@@ -297,7 +416,8 @@ k_select_rerank(const RerankParams p) {
   const int slots = p.S * CAP;
   // shared layout
   float* qvec = reinterpret_cast<float*>(rr_smem);                      // d (16-B aligned)
-  unsigned int* keys = reinterpret_cast<unsigned int*>(qvec + ((p.d + 3) & ~3));
+  float4* part = reinterpret_cast<float4*>(qvec + ((p.d + 3) & ~3));    // cons.part4 (16-B aligned)
+  unsigned int* keys = reinterpret_cast<unsigned int*>(part + p.cons.part4);
   unsigned int* ids = keys + slots;
   int* s_cnt = reinterpret_cast<int*>(ids + slots);                     // S
   int* s_off = s_cnt + p.S;                                             // S
@@ -307,10 +427,16 @@ k_select_rerank(const RerankParams p) {
   float* red = reinterpret_cast<float*>(hist + 256);                    // 32
   unsigned int* bcast = reinterpret_cast<unsigned int*>(red + 32);      // 4
   int* counters = reinterpret_cast<int*>(bcast + 4);                    // 4
+  unsigned int* top_id = reinterpret_cast<unsigned int*>(counters + 4); // k  (rank order)
+  float* top_d = reinterpret_cast<float*>(top_id + p.k);                // k
+  float* top_w = top_d + p.k;                                           // k
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid < 4) counters[tid] = 0;
+  for (int r = tid; r < p.k; r += blockDim.x) top_id[r] = 0xFFFFFFFFu;
   for (int c = tid; c < p.d; c += blockDim.x) qvec[c] = p.q_f32[static_cast<long long>(q) * p.d + c];
+  griddep_wait();               // candidates come from the scoring kernel
+  griddep_launch_dependents();
   float th_max = -INFINITY;
   for (int s = tid; s < p.S; s += blockDim.x) {
     const long long item = (static_cast<long long>(db) * p.S + s) * p.n_qt + qt;
@@ -462,11 +588,18 @@ k_select_rerank(const RerankParams p) {
     if (rank < p.k) {
       Dq[rank] = sc;
       Iq[rank] = static_cast<long long>(sel_id[c]) + p.id_offset[db];
+      top_id[rank] = sel_id[c];
+      top_d[rank] = sc;
     }
   }
   for (int r = m + tid; r < p.k; r += blockDim.x) {
     Dq[r] = p.metric == METRIC_L2 ? FLT_MAX : -FLT_MAX;
     Iq[r] = -1;
+  }
+  // a flagged query is consumed by the exact fallback instead, once its answer is final
+  if (p.cons.enabled && ok) {
+    __syncthreads();
+    consume_query(p.cons, xbase, db, q, p.k, p.d, p.metric, top_id, top_d, top_w, part);
   }
 }
 
@@ -476,302 +609,11 @@ __global__ void k_flag_all(int* flagged, int* n_flagged, int nq) {
   if (i == 0) *n_flagged = nq;
 }
 
-// ---------------------------------------------------------------------------------------------
-// Exact fp32 fallback: one persistent cooperative launch answers every flagged query, however
-// many there are, and returns at once when there are none.
-struct ExactParams {
-  const float* x_f32;
-  long long n_rows;
-  int d, metric, k, nq;
-  const float* q_f32;
-  const int* flagged;
-  const int* n_flagged;
-  float* scratch;          // [f_cap][n_rows] rank scores (IP, or -dist)
-  int f_cap;
-  float* D;
-  long long* I;
-  long long id_offset;
-  unsigned int* barrier;   // zeroed before launch
-};
+}  // namespace keds
 
-__device__ __forceinline__ void grid_barrier(unsigned int* ctr, unsigned int& target) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(ctr, 1u);
-    while (*reinterpret_cast<volatile unsigned int*>(ctr) < target) { __nanosleep(64); }
-    __threadfence();
-  }
-  __syncthreads();
-  target += gridDim.x;
-}
+#include "exact_fallback.cuh"
 
-struct ExactParams2 {
-  int n_db;
-  ExactParams e[2];
-};
-
-__global__ void __launch_bounds__(EXACT_THREADS)
-k_exact_fallback(const ExactParams2 pp) {
-  unsigned int bar_target = gridDim.x;
-  for (int dbi = 0; dbi < pp.n_db; ++dbi) {
-  const ExactParams& p = pp.e[dbi];
-  const int nfl = *reinterpret_cast<const volatile int*>(p.n_flagged);
-  if (nfl <= 0) continue;
-  extern __shared__ uint8_t ex_smem[];
-  float* qs = reinterpret_cast<float*>(ex_smem);                       // EXACT_QG * dq
-  const int dq = (p.d + 3) & ~3;
-  unsigned int* sel_key = reinterpret_cast<unsigned int*>(qs + EXACT_QG * dq);  // K_MAX
-  unsigned int* sel_id = sel_key + K_MAX;                              // K_MAX
-  unsigned int* hist = sel_id + K_MAX;                                 // 256
-  unsigned int* bcast = hist + 256;                                    // 4
-  int* counters = reinterpret_cast<int*>(bcast + 4);                   // 4
-  int* wsum = counters + 4;                                            // 8 (per-warp tie counts)
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wpb = blockDim.x >> 5;
-  const long long groups = (p.n_rows + 31) / 32;
-
-  for (int r0 = 0; r0 < nfl; r0 += p.f_cap) {
-    const int F = min(p.f_cap, nfl - r0);
-    // ---- phase 1: rank scores of F flagged queries against every row
-    for (int g0 = 0; g0 < F; g0 += EXACT_QG) {
-      const int G = min(EXACT_QG, F - g0);
-      __syncthreads();
-      for (int i = tid; i < G * dq; i += blockDim.x) {
-        const int qi = i / dq, c = i % dq;
-        const int q = p.flagged[r0 + g0 + qi];
-        qs[i] = c < p.d ? p.q_f32[static_cast<long long>(q) * p.d + c] : 0.f;
-      }
-      __syncthreads();
-      for (long long g = static_cast<long long>(blockIdx.x) * wpb + warp; g < groups;
-           g += static_cast<long long>(gridDim.x) * wpb) {
-        float keep[EXACT_QG];
-#pragma unroll
-        for (int i = 0; i < EXACT_QG; ++i) keep[i] = 0.f;
-        for (int rr = 0; rr < 32; ++rr) {
-          const long long row = g * 32 + rr;
-          if (row >= p.n_rows) break;
-          const float* xr = p.x_f32 + row * p.d;
-#pragma unroll
-          for (int i = 0; i < EXACT_QG; ++i) {
-            if (i < G) {
-              const float sc = warp_exact_score(qs + i * dq, xr, p.d, p.metric, lane);
-              if (lane == rr) keep[i] = p.metric == METRIC_L2 ? -sc : sc;
-            }
-          }
-        }
-        const long long row = g * 32 + lane;
-        if (row < p.n_rows) {
-#pragma unroll
-          for (int i = 0; i < EXACT_QG; ++i)
-            if (i < G) p.scratch[static_cast<long long>(g0 + i) * p.n_rows + row] = keep[i];
-        }
-      }
-    }
-    grid_barrier(p.barrier, bar_target);
-    // ---- phase 2: one block per flagged query selects and orders its top-k
-    for (int f = blockIdx.x; f < F; f += gridDim.x) {
-      const int q = p.flagged[r0 + f];
-      const float* sc = p.scratch + static_cast<long long>(f) * p.n_rows;
-      const long long n = p.n_rows;
-      const int keff = static_cast<int>(min(static_cast<long long>(p.k), n));
-      // k-th largest rank score (radix select over global memory)
-      unsigned int prefix = 0, mask = 0;
-      int need = keff;
-      for (int shift = 24; shift >= 0; shift -= 8) {
-        for (int i = tid; i < 256; i += blockDim.x) hist[i] = 0;
-        __syncthreads();
-        for (long long i = tid; i < n; i += blockDim.x) {
-          float v = sc[i];
-          if (v == 0.f) v = 0.f;
-          const unsigned int key = f32_to_key(v);
-          if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
-        }
-        __syncthreads();
-        block_find_bin(hist, need, bcast);
-        prefix |= bcast[0] << shift;
-        mask |= 255u << shift;
-        need = static_cast<int>(bcast[1]);
-        __syncthreads();
-      }
-      const unsigned int kth = prefix;  // `need` rows equal to kth are wanted, lowest ids first
-      if (tid < 4) counters[tid] = 0;
-      __syncthreads();
-      // rows strictly better than kth: any order; rows equal to kth: in id order until `need`
-      for (long long base = 0; base < n; base += blockDim.x) {
-        const long long i = base + tid;
-        unsigned int key = 0;
-        bool gt = false, eq = false;
-        if (i < n) {
-          float v = sc[i];
-          if (v == 0.f) v = 0.f;
-          key = f32_to_key(v);
-          gt = key > kth;
-          eq = key == kth;
-        }
-        if (gt) {
-          const int pos = atomicAdd(&counters[0], 1);
-          sel_key[pos] = key;
-          sel_id[pos] = static_cast<unsigned int>(i);
-        }
-        const int taken = counters[1];  // ties taken so far (stable: updated after the sync below)
-        if (taken < need) {
-          const unsigned int bal = __ballot_sync(0xffffffffu, eq);
-          if (lane == 0) wsum[warp] = __popc(bal);
-          __syncthreads();
-          int before = 0;
-          for (int w = 0; w < warp; ++w) before += wsum[w];
-          const int my = taken + before + __popc(bal & ((1u << lane) - 1u));
-          if (eq && my < need) {
-            const int pos = (keff - need) + my;  // ties fill the tail slots
-            sel_key[pos] = key;
-            sel_id[pos] = static_cast<unsigned int>(i);
-          }
-          __syncthreads();
-          if (tid == 0) {
-            int tot = 0;
-            for (int w = 0; w < wpb; ++w) tot += wsum[w];
-            counters[1] = taken + tot;
-          }
-          __syncthreads();
-        }
-      }
-      __syncthreads();
-      float* Dq = p.D + static_cast<long long>(q) * p.k;
-      long long* Iq = p.I + static_cast<long long>(q) * p.k;
-      for (int c = tid; c < keff; c += blockDim.x) {
-        const unsigned long long mine =
-            (static_cast<unsigned long long>(sel_key[c]) << 32) | (0xFFFFFFFFu - sel_id[c]);
-        int rank = 0;
-        for (int j = 0; j < keff; ++j) {
-          const unsigned long long other =
-              (static_cast<unsigned long long>(sel_key[j]) << 32) | (0xFFFFFFFFu - sel_id[j]);
-          rank += other > mine;
-        }
-        const float v = key_to_f32(sel_key[c]);
-        Dq[rank] = p.metric == METRIC_L2 ? -v : v;
-        Iq[rank] = static_cast<long long>(sel_id[c]) + p.id_offset;
-      }
-      for (int r = keff + tid; r < p.k; r += blockDim.x) {
-        Dq[r] = p.metric == METRIC_L2 ? FLT_MAX : -FLT_MAX;
-        Iq[r] = -1;
-      }
-      __syncthreads();
-    }
-    grid_barrier(p.barrier, bar_target);
-  }
-  }  // databases
-}
-
-// ---------------------------------------------------------------------------------------------
-// Fused neighbour consumer for both streams: for stream s (0 = image, 1 = text) and query b
-//   feat[s][b][j][:] = rows_s[I_s[b][perm_s ? perm_s[j] : j]][:]                    (optional)
-//   pool[s][b][0][:] = sum_j w_j * rows_s[I_s[b][j]][:]                             (optional)
-// with w = uniform 1/k (mode 1) or softmax_j(sign * tau * D_s[b][j]) (mode 2; sign = -1 for L2).
-// Each neighbour row is read once for both outputs. One block per (query, stream).
-struct Consume2Params {
-  const float* rows[2];
-  const long long* I[2];
-  const float* D[2];
-  const int* perm[2];
-  float* feat[2];
-  float* pool[2];
-  int k, d, mode, metric, jgroups;
-  float tau;
-};
-
-__global__ void __launch_bounds__(1024)
-k_consume2(const Consume2Params p) {
-  extern __shared__ uint8_t c2_smem[];
-  long long* ids = reinterpret_cast<long long*>(c2_smem);  // k (rank order)
-  float* w = reinterpret_cast<float*>(ids + p.k);           // k (rank order)
-  const long long b = blockIdx.x;
-  const int s = blockIdx.y;
-  const int tid = threadIdx.x;
-  for (int j = tid; j < p.k; j += blockDim.x) {
-    ids[j] = p.I[s][b * p.k + j];
-    w[j] = 0.f;
-  }
-  __syncthreads();
-  if (p.pool[s] != nullptr && tid == 0) {
-    // k <= a few hundred: a serial pass is cheaper than a block reduction here
-    if (p.mode == 2) {
-      const float sign = p.metric == METRIC_L2 ? -1.f : 1.f;
-      float mx = -INFINITY;
-      for (int j = 0; j < p.k; ++j)
-        if (ids[j] >= 0) mx = fmaxf(mx, sign * p.tau * p.D[s][b * p.k + j]);
-      float sum = 0.f;
-      for (int j = 0; j < p.k; ++j) {
-        const float e = ids[j] >= 0 ? __expf(sign * p.tau * p.D[s][b * p.k + j] - mx) : 0.f;
-        w[j] = e;
-        sum += e;
-      }
-      const float inv = sum > 0.f ? 1.f / sum : 0.f;
-      for (int j = 0; j < p.k; ++j) w[j] *= inv;
-    } else {
-      for (int j = 0; j < p.k; ++j) w[j] = 1.f / static_cast<float>(p.k);
-    }
-  }
-  __syncthreads();
-  const float* rows = p.rows[s];
-  float* feat = p.feat[s] ? p.feat[s] + b * p.k * p.d : nullptr;
-  const int* perm = p.perm[s];
-  const bool vec = (p.d & 3) == 0 && ((reinterpret_cast<uintptr_t>(rows) |
-                                       reinterpret_cast<uintptr_t>(p.feat[s]) |
-                                       reinterpret_cast<uintptr_t>(p.pool[s])) & 15) == 0;
-  if (vec) {
-    // threads form JG groups of `cols` lanes; group g takes neighbours g, g+JG, ... so that
-    // several 3-KB row reads are in flight per column; partial pools meet in shared memory
-    const int d4 = p.d >> 2;
-    const int cols = min(d4, static_cast<int>(blockDim.x));
-    const int JG = max(1, min(p.jgroups, static_cast<int>(blockDim.x) / cols));
-    const int g = tid / cols, c0 = tid % cols;
-    float4* part = reinterpret_cast<float4*>(c2_smem + ((p.k * 12 + 15) & ~15));  // [JG][d4]
-    if (g < JG) {
-      for (int c = c0; c < d4; c += cols) {
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-        for (int jo = g; jo < p.k; jo += JG) {
-          const int j = perm ? perm[jo] : jo;       // output slot jo shows rank j
-          const long long id = ids[j];
-          const float4 v = id >= 0 ? __ldg(reinterpret_cast<const float4*>(rows + id * p.d) + c)
-                                   : make_float4(0.f, 0.f, 0.f, 0.f);
-          if (feat) reinterpret_cast<float4*>(feat + static_cast<long long>(jo) * p.d)[c] = v;
-          const float wj = w[j];
-          acc.x = fmaf(wj, v.x, acc.x);
-          acc.y = fmaf(wj, v.y, acc.y);
-          acc.z = fmaf(wj, v.z, acc.z);
-          acc.w = fmaf(wj, v.w, acc.w);
-        }
-        if (p.pool[s]) part[g * d4 + c] = acc;
-      }
-    }
-    if (p.pool[s]) {
-      __syncthreads();
-      for (int c = tid; c < d4; c += blockDim.x) {
-        float4 acc = part[c];
-        for (int gg = 1; gg < JG; ++gg) {
-          const float4 o = part[gg * d4 + c];
-          acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
-        }
-        reinterpret_cast<float4*>(p.pool[s] + b * p.d)[c] = acc;
-      }
-    }
-  } else {
-    for (int c = tid; c < p.d; c += blockDim.x) {
-      float acc = 0.f;
-      for (int jo = 0; jo < p.k; ++jo) {
-        const int j = perm ? perm[jo] : jo;
-        const long long id = ids[j];
-        const float v = id >= 0 ? rows[id * p.d + c] : 0.f;
-        if (feat) feat[static_cast<long long>(jo) * p.d + c] = v;
-        acc = fmaf(w[j], v, acc);
-      }
-      if (p.pool[s]) p.pool[s][b * p.d + c] = acc;
-    }
-  }
-}
+namespace keds {
 
 // ---------------------------------------------------------------------------------------------
 // Merge `parts` per-shard results (part p at Dp + p*stride_d, Ip + p*stride_i, each [nq][k]) into the global top-k (same total order; ids are

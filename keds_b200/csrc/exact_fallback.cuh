@@ -1,0 +1,212 @@
+// Exact fp32 fallback for the queries whose certificate failed (and the whole batch in exact-only
+// mode): two ordinary kernels per pass, both of which return at once when nothing is flagged, so
+// they can sit in every search's launch chain (programmatic dependent launch hides their launch
+// latency) without a host round trip.
+//
+//   k_exact_scores   rank scores (IP, or -squared-L2) of up to f_cap flagged queries per database
+//                    against every row -> scratch[db][f][row]
+//   k_exact_select   one block per (flagged query, database): radix-select the k-th best, take ties
+//                    in id order, order by (score desc, id asc), write D/I, then run the neighbour
+//                    consumer for that query (the re-rank kernel skipped it)
+//
+// Pass p handles flagged[p * f_cap ... (p+1) * f_cap); the host launches ceil(nq / f_cap) passes.
+// Included by aux_kernels.cuh (uses warp_exact_score, block_find_bin, consume_query).
+#pragma once
+
+namespace keds {
+
+struct ExactDb {
+  const float* x_f32;
+  long long n_rows;
+  const int* flagged;
+  const int* n_flagged;
+  float* scratch;  // [f_cap][n_rows]
+  float* D;
+  long long* I;
+  long long id_offset;
+};
+
+struct ExactParams {
+  ConsumeParams cons;
+  ExactDb db[2];
+  int n_db, d, metric, k, f_cap, pass;
+  const float* q_f32;
+};
+
+__global__ void __launch_bounds__(EXACT_THREADS)
+k_exact_scores(const ExactParams p) {
+  griddep_wait();
+  griddep_launch_dependents();
+  extern __shared__ uint8_t ex_smem[];
+  float* qs = reinterpret_cast<float*>(ex_smem);  // EXACT_QG * dq
+  const int dq = (p.d + 3) & ~3;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wpb = blockDim.x >> 5;
+  for (int dbi = 0; dbi < p.n_db; ++dbi) {
+    const ExactDb& e = p.db[dbi];
+    const int nfl = *e.n_flagged;
+    const int r0 = p.pass * p.f_cap;
+    if (nfl <= r0) continue;
+    const int F = min(p.f_cap, nfl - r0);
+    const long long groups = (e.n_rows + 31) / 32;
+    for (int g0 = 0; g0 < F; g0 += EXACT_QG) {
+      const int G = min(EXACT_QG, F - g0);
+      __syncthreads();
+      for (int i = tid; i < G * dq; i += blockDim.x) {
+        const int qi = i / dq, c = i % dq;
+        const int q = e.flagged[r0 + g0 + qi];
+        qs[i] = c < p.d ? p.q_f32[static_cast<long long>(q) * p.d + c] : 0.f;
+      }
+      __syncthreads();
+      for (long long g = static_cast<long long>(blockIdx.x) * wpb + warp; g < groups;
+           g += static_cast<long long>(gridDim.x) * wpb) {
+        float keep[EXACT_QG];
+#pragma unroll
+        for (int i = 0; i < EXACT_QG; ++i) keep[i] = 0.f;
+        for (int rr = 0; rr < 32; ++rr) {
+          const long long row = g * 32 + rr;
+          if (row >= e.n_rows) break;
+          const float* xr = e.x_f32 + row * p.d;
+#pragma unroll
+          for (int i = 0; i < EXACT_QG; ++i) {
+            if (i < G) {
+              const float sc = warp_exact_score(qs + i * dq, xr, p.d, p.metric, lane);
+              if (lane == rr) keep[i] = p.metric == METRIC_L2 ? -sc : sc;
+            }
+          }
+        }
+        const long long row = g * 32 + lane;
+        if (row < e.n_rows) {
+#pragma unroll
+          for (int i = 0; i < EXACT_QG; ++i)
+            if (i < G) e.scratch[static_cast<long long>(g0 + i) * e.n_rows + row] = keep[i];
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(EXACT_THREADS)
+k_exact_select(const ExactParams p) {
+  griddep_wait();
+  griddep_launch_dependents();
+  const int dbi = blockIdx.y;
+  const ExactDb& e = p.db[dbi];
+  const int nfl = *e.n_flagged;
+  const int r0 = p.pass * p.f_cap;
+  if (nfl <= r0) return;
+  const int F = min(p.f_cap, nfl - r0);
+
+  extern __shared__ uint8_t ex_smem[];
+  float4* part = reinterpret_cast<float4*>(ex_smem);                            // cons.part4
+  unsigned int* sel_key = reinterpret_cast<unsigned int*>(part + p.cons.part4); // k
+  unsigned int* sel_id = sel_key + p.k;                                         // k
+  unsigned int* top_id = sel_id + p.k;                                          // k (rank order)
+  float* top_d = reinterpret_cast<float*>(top_id + p.k);                        // k
+  float* top_w = top_d + p.k;                                                   // k
+  unsigned int* hist = reinterpret_cast<unsigned int*>(top_w + p.k);            // 256
+  unsigned int* bcast = hist + 256;                                             // 4
+  int* counters = reinterpret_cast<int*>(bcast + 4);                            // 4
+  int* wsum = counters + 4;                                                     // 8
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wpb = blockDim.x >> 5;
+  for (int f = blockIdx.x; f < F; f += gridDim.x) {
+    const int q = e.flagged[r0 + f];
+    const float* sc = e.scratch + static_cast<long long>(f) * e.n_rows;
+    const long long n = e.n_rows;
+    const int keff = static_cast<int>(min(static_cast<long long>(p.k), n));
+    __syncthreads();
+    for (int r = tid; r < p.k; r += blockDim.x) top_id[r] = 0xFFFFFFFFu;
+    // k-th largest rank score: 4 x 8-bit radix passes over the score row (global / L2)
+    unsigned int prefix = 0, mask = 0;
+    int need = keff;
+    for (int shift = 24; shift >= 0; shift -= 8) {
+      for (int i = tid; i < 256; i += blockDim.x) hist[i] = 0;
+      __syncthreads();
+      for (long long i = tid; i < n; i += blockDim.x) {
+        float v = sc[i];
+        if (v == 0.f) v = 0.f;
+        const unsigned int key = f32_to_key(v);
+        if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+      }
+      __syncthreads();
+      block_find_bin(hist, need, bcast);
+      prefix |= bcast[0] << shift;
+      mask |= 255u << shift;
+      need = static_cast<int>(bcast[1]);
+      __syncthreads();
+    }
+    const unsigned int kth = prefix;  // `need` rows equal to kth are wanted, lowest ids first
+    if (tid < 4) counters[tid] = 0;
+    __syncthreads();
+    // rows strictly better than kth: any order; rows equal to kth: in id order until `need`
+    for (long long base = 0; base < n; base += blockDim.x) {
+      const long long i = base + tid;
+      unsigned int key = 0;
+      bool gt = false, eq = false;
+      if (i < n) {
+        float v = sc[i];
+        if (v == 0.f) v = 0.f;
+        key = f32_to_key(v);
+        gt = key > kth;
+        eq = key == kth;
+      }
+      if (gt) {
+        const int pos = atomicAdd(&counters[0], 1);
+        sel_key[pos] = key;
+        sel_id[pos] = static_cast<unsigned int>(i);
+      }
+      const int taken = counters[1];  // uniform: only updated between the syncs below
+      if (taken < need) {
+        const unsigned int bal = __ballot_sync(0xffffffffu, eq);
+        if (lane == 0) wsum[warp] = __popc(bal);
+        __syncthreads();
+        int before = 0;
+        for (int w = 0; w < warp; ++w) before += wsum[w];
+        const int my = taken + before + __popc(bal & ((1u << lane) - 1u));
+        if (eq && my < need) {
+          const int pos = (keff - need) + my;  // ties fill the tail slots
+          sel_key[pos] = key;
+          sel_id[pos] = static_cast<unsigned int>(i);
+        }
+        __syncthreads();
+        if (tid == 0) {
+          int tot = 0;
+          for (int w = 0; w < wpb; ++w) tot += wsum[w];
+          counters[1] = taken + tot;
+        }
+        __syncthreads();
+      }
+    }
+    __syncthreads();
+    float* Dq = e.D + static_cast<long long>(q) * p.k;
+    long long* Iq = e.I + static_cast<long long>(q) * p.k;
+    for (int c = tid; c < keff; c += blockDim.x) {
+      const unsigned long long mine =
+          (static_cast<unsigned long long>(sel_key[c]) << 32) | (0xFFFFFFFFu - sel_id[c]);
+      int rank = 0;
+      for (int j = 0; j < keff; ++j) {
+        const unsigned long long other =
+            (static_cast<unsigned long long>(sel_key[j]) << 32) | (0xFFFFFFFFu - sel_id[j]);
+        rank += other > mine;
+      }
+      const float v = key_to_f32(sel_key[c]);
+      const float dv = p.metric == METRIC_L2 ? -v : v;
+      Dq[rank] = dv;
+      Iq[rank] = static_cast<long long>(sel_id[c]) + e.id_offset;
+      top_id[rank] = sel_id[c];
+      top_d[rank] = dv;
+    }
+    for (int r = keff + tid; r < p.k; r += blockDim.x) {
+      Dq[r] = p.metric == METRIC_L2 ? FLT_MAX : -FLT_MAX;
+      Iq[r] = -1;
+    }
+    if (p.cons.enabled) {
+      __syncthreads();
+      consume_query(p.cons, e.x_f32, dbi, q, p.k, p.d, p.metric, top_id, top_d, top_w, part);
+    }
+  }
+}
+
+}  // namespace keds

@@ -29,6 +29,22 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// wait: block until every kernel this launch depends on has completed and its writes are visible
+// (no-op when the kernel was launched without the programmatic attribute).
+__device__ __forceinline__ void griddep_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+// allow the next kernel in the stream to be scheduled (it still waits in its own griddep_wait)
+__device__ __forceinline__ void griddep_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");

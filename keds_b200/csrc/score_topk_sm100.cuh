@@ -55,6 +55,7 @@ struct ScoreParams {
   uint32_t* err;     // device error word (0 = ok)
   float* dump;       // debug: full approx scores [n_db][nq][ld_dump], or nullptr
   long long ld_dump;
+  unsigned long long* timing;  // nullable: {min start ns, max end ns} of this launch (%globaltimer)
 };
 
 struct ItemCoord {
@@ -172,6 +173,14 @@ k_score_topk(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+
+  // Programmatic dependent launch: everything above overlapped the tail of the previous kernel
+  // (k_prep_rows); from here on its outputs (bf16 queries) are needed. Let the next kernel
+  // (k_select_rerank) start its own prologue as soon as SMs free up.
+  griddep_wait();
+  griddep_launch_dependents();
+  unsigned long long t_start = 0;
+  if (p.timing != nullptr && threadIdx.x == 0) t_start = global_timer_ns();
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -331,7 +340,13 @@ k_score_topk(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
 
   tc_fence_before();
   __syncthreads();
+  if (p.timing != nullptr && threadIdx.x == 0) {
+    // kernel duration without stream events: min start / max end over the CTAs of this launch
+    atomicMin(p.timing + 0, t_start);
+    atomicMax(p.timing + 1, global_timer_ns());
+  }
   if (warp == 1) {
+    __syncwarp();
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }

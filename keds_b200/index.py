@@ -150,6 +150,9 @@ class GpuIndexFlat:
     def set_id_offset(self, offset: int) -> None:
         _capi.check(self._lib.keds_index_set_id_offset(self._h, int(offset)))
 
+    def set_pdl(self, enable: bool) -> None:
+        _capi.check(self._lib.keds_index_set_pdl(self._h, int(bool(enable))))
+
     def set_eps_scale(self, scale: float) -> None:
         _capi.check(self._lib.keds_index_set_eps_scale(self._h, float(scale)))
 
@@ -221,14 +224,24 @@ class GpuIndexFlat:
             "err_word": int(st.err_word),
         }
 
-    def set_profiling(self, enable: bool) -> None:
-        _capi.check(self._lib.keds_index_set_profiling(self._h, int(bool(enable))))
+    def set_profiling(self, mode: int) -> None:
+        """0 off; 1 in-kernel timer of the scoring kernel (launch chain untouched); 2 stage marks."""
+        _capi.check(self._lib.keds_index_set_profiling(self._h, int(mode)))
 
     def profile(self):
         """(summed ms, launches) of the scoring kernel since set_profiling(True); waits for them."""
         ms, n = C.c_double(0.0), C.c_int64(0)
         _capi.check(self._lib.keds_index_profile(self._h, C.byref(ms), C.byref(n)))
         return float(ms.value), int(n.value)
+
+    STAGES = ("", "k_prep_rows", "k_score_topk", "k_select_rerank", "k_exact_scores+select", "")
+
+    def profile_stages(self) -> dict:
+        """{kernel: (summed ms, launches)} since set_profiling(True); stream time per stage."""
+        ms = (C.c_double * 6)()
+        n = (C.c_int64 * 6)()
+        _capi.check(self._lib.keds_index_profile_stages(self._h, ms, n, 6))
+        return {self.STAGES[i]: (float(ms[i]), int(n[i])) for i in range(1, 5)}
 
     def rows_ptr(self) -> int:
         """Device address of the resident fp32 rows [ntotal, d]."""
