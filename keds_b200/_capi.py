@@ -60,6 +60,8 @@ SIGNATURES = {
     "keds_index_last_stats": (C.c_int, [_vp, C.POINTER(SearchStats)]),
     "keds_index_set_profiling": (C.c_int, [_vp, C.c_int]),
     "keds_index_profile": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "keds_index_profile_chain": (
+        C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int]),
     "keds_index_profile_stages": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int]),
     "keds_gather_pool": (
         C.c_int,

@@ -136,6 +136,7 @@ constexpr int S_MAX = 192;
 constexpr size_t CAND_BUDGET = size_t(1) << 30;
 constexpr int64_t Q_PASS_MAX = 16384;
 constexpr size_t TIMING_RING = 8192;
+constexpr size_t TIMING_PAIRS = 5;  // k_prep_rows, k_score_topk, k_select_rerank, k_exact_scores, k_exact_select
 
 struct Plan {
   int exact_only = 0;
@@ -219,7 +220,7 @@ Plan make_plan(const keds_index* ix, int n_db, int64_t nq, int k, int64_t n_min,
   const int S_sel = std::max(1, (3 * k + LKEEP - 1) / LKEEP);
   const int groups = n_db * pl.n_qt;
   int S_hi = std::min(T_min, S_MAX);
-  const long long by_mem = static_cast<long long>(CAND_BUDGET / (size_t(CAP) * BM * 8)) / groups;
+  const long long by_mem = static_cast<long long>(CAND_BUDGET / (size_t(LKEEP) * BM * 8)) / groups;
   S_hi = static_cast<int>(std::min<long long>(S_hi, by_mem));
   if ((flags & KEDS_SEARCH_EXACT_ONLY) || S_hi < S_sel || k > R_MAX / 2) {
     pl.exact_only = 1;
@@ -280,7 +281,8 @@ int prof_mark(keds_index* a, cudaStream_t st, int tag) {
 // The exact-fallback kernel pair, ceil(nq / f_cap) passes; every launch returns at once when its
 // slice of the flagged list is empty.
 int launch_exact(keds_index* ix, keds_index* dbs[2], int n_db, const float* q_dev, int64_t nq, int k,
-                 float* D[2], long long* I[2], int metric, const ConsumeParams& cons, cudaStream_t st) {
+                 float* D[2], long long* I[2], int metric, const ConsumeParams& cons,
+                 unsigned long long* timing, cudaStream_t st) {
   ExactParams ep;
   memset(&ep, 0, sizeof ep);
   ep.cons = cons;
@@ -318,6 +320,7 @@ int launch_exact(keds_index* ix, keds_index* dbs[2], int n_db, const float* q_de
   const unsigned sel_blocks = static_cast<unsigned>(std::min<long long>(fc, 4 * ix->num_sms));
   for (int pass = 0; pass < passes; ++pass) {
     ep.pass = pass;
+    ep.timing = pass == 0 ? timing : nullptr;
     CKS(launch_k(ix->use_pdl, k_exact_scores, dim3(ix->num_sms * 2), dim3(EXACT_THREADS), smem_sc, st, ep));
     CKS(launch_k(ix->use_pdl, k_exact_select, dim3(sel_blocks, n_db), dim3(EXACT_THREADS), smem_sel, st, ep));
     ix->stats.launches += 2;
@@ -336,6 +339,13 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
   ConsumeParams cons;
   memset(&cons, 0, sizeof cons);
   if (cons_in) cons = *cons_in;
+  // in-kernel %globaltimer stamps, one {min start, max end} pair per kernel of this chain
+  // (prep, score, rerank, exact scores, exact select); the first TIMING_RING searches are timed
+  unsigned long long* tchain = nullptr;
+  if (a->timing_on && a->timing_launches < TIMING_RING && !dump) {
+    tchain = a->timing.as<unsigned long long>() + TIMING_PAIRS * 2 * a->timing_launches;
+    a->timing_launches++;
+  }
   CKS(a->ctrl.ensure(CTRL_WORDS * 4));
   for (int i = 0; i < n_db; ++i) CKS(a->flagged[i].ensure(static_cast<size_t>(nq) * 4));
 
@@ -372,11 +382,11 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
       CKS(launch_k(a->use_pdl, k_prep_rows, dim3(blocks), dim3(threads), 0, st, q_dev,
                    static_cast<long long>(nq), a->d, a->d_pad, a->q_bf16.as<__nv_bfloat16>(),
                    a->qstat.as<float4>(), static_cast<float*>(nullptr), static_cast<unsigned int*>(nullptr),
-                   a->ctrl.as<unsigned int>(), CTRL_WORDS));
+                   a->ctrl.as<unsigned int>(), CTRL_WORDS, tchain));
       a->stats.launches++;
     }
     const size_t items = static_cast<size_t>(pl.n_items);
-    CKS(a->cand.ensure(items * CAP * BM * 8));
+    CKS(a->cand.ensure(items * LKEEP * BM * 8));
     CKS(a->cand_cnt.ensure(items * BM * 4));
     CKS(a->cand_theta.ensure(items * BM * 4));
 
@@ -399,13 +409,7 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
     sp.err = a->ctrl.as<uint32_t>() + 2;
     sp.dump = dump;
     sp.ld_dump = ld_dump;
-    sp.timing = nullptr;
-    if (a->timing_on && a->timing_launches < TIMING_RING) {
-      // in-kernel %globaltimer stamps: one {min start, max end} pair per launch (the first
-      // TIMING_RING launches after set_profiling(1) are timed)
-      sp.timing = a->timing.as<unsigned long long>() + 2 * a->timing_launches;
-      a->timing_launches++;
-    }
+    sp.timing = tchain ? tchain + 2 : nullptr;
     CKS(prof_mark(a, st, 1));
     CKS(launch_k(a->use_pdl, k_score_topk, dim3(pl.grid), dim3(SCORE_THREADS), SCORE_SMEM_BYTES, st, a->tm_q,
                  ix[0]->tm_x, n_db > 1 ? ix[1]->tm_x : ix[0]->tm_x, sp));
@@ -439,9 +443,11 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
     }
     rp.eps_scale = a->eps_scale;
     rp.cons = cons;
-    const size_t slots = static_cast<size_t>(pl.S) * CAP;
+    rp.timing = tchain ? tchain + 4 : nullptr;
+    const size_t slots = static_cast<size_t>(pl.S) * LKEEP;
+    // qvec | part | keys, ids | smax | a_key, a_id, sel_id, sel_sc | hist | red | bcast | counters | top_*
     const size_t smem = static_cast<size_t>((a->d + 3) & ~3) * 4 + static_cast<size_t>(cons.part4) * 16 +
-                        slots * 8 + pl.S * 8 + R_MAX * 8 + 256 * 4 + 32 * 4 + 16 + 16 +
+                        slots * 8 + pl.S * 4 + R_MAX * 16 + 256 * 4 + 32 * 4 + 16 + 16 +
                         static_cast<size_t>(k) * 12;
     if (smem > 200 * 1024) return fail(KEDS_ERR_ARG, "re-rank shared memory %zu too large", smem);
     CKS(launch_k(a->use_pdl, k_select_rerank, dim3(static_cast<unsigned>(nq), n_db), dim3(RERANK_THREADS), smem,
@@ -451,7 +457,7 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
     CK(cudaGetLastError());
   }
   if (!(flags & KEDS_SEARCH_NO_FALLBACK) || pl.exact_only) {
-    CKS(launch_exact(a, ix, n_db, q_dev, nq, k, D, I, metric, cons, st));
+    CKS(launch_exact(a, ix, n_db, q_dev, nq, k, D, I, metric, cons, tchain ? tchain + 6 : nullptr, st));
     CKS(prof_mark(a, st, 4));
   }
   CK(cudaGetLastError());
@@ -658,7 +664,7 @@ int keds_index_add(keds_index_t* ix, const float* x, int64_t n) {
   const unsigned blocks = static_cast<unsigned>(std::min<int64_t>((n * 32 + 255) / 256, 148 * 16));
   k_prep_rows<<<blocks, 256>>>(ix->x_f32.as<float>() + n0 * d, n, ix->d, ix->d_pad,
                                ix->x_bf16.as<__nv_bfloat16>() + n0 * dp, nullptr,
-                               ix->bias.as<float>() + n0, ix->dbstat.as<unsigned int>(), nullptr, 0);
+                               ix->bias.as<float>() + n0, ix->dbstat.as<unsigned int>(), nullptr, 0, nullptr);
   const int64_t padded = (n1 + BN - 1) / BN * BN;
   if (padded > n1)
     k_fill_f32<<<static_cast<unsigned>((padded - n1 + 255) / 256), 256>>>(ix->bias.as<float>() + n1,
@@ -783,35 +789,63 @@ int keds_index_set_profiling(keds_index_t* ix, int enable) {
   ix->timing_on = enable == 1;  // in-kernel timer of the scoring kernel, launch chain untouched
   ix->timing_launches = 0;
   if (ix->timing_on) {
-    CKS(ix->timing.ensure(TIMING_RING * 16));
-    std::vector<unsigned long long> init(TIMING_RING * 2);
-    for (size_t i = 0; i < TIMING_RING; ++i) {
-      init[2 * i] = ~0ull;
-      init[2 * i + 1] = 0ull;
+    const size_t words = TIMING_RING * TIMING_PAIRS * 2;
+    CKS(ix->timing.ensure(words * 8));
+    std::vector<unsigned long long> init(words);
+    for (size_t i = 0; i < words; i += 2) {
+      init[i] = ~0ull;
+      init[i + 1] = 0ull;
     }
-    CK(cudaMemcpy(ix->timing.p, init.data(), TIMING_RING * 16, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ix->timing.p, init.data(), words * 8, cudaMemcpyHostToDevice));
   }
+  return 0;
+}
+
+int keds_index_profile_chain(keds_index_t* ix, double* dur_ms, double* gap_ms, int64_t* searches, int n) {
+  if (!ix || !dur_ms || !gap_ms || !searches || n < static_cast<int>(TIMING_PAIRS))
+    return fail(KEDS_ERR_ARG, "profile_chain: need room for %d kernels", (int)TIMING_PAIRS);
+  if (!ix->timing_on) return fail(KEDS_ERR_ARG, "profile_chain: call set_profiling(1) first");
+  DeviceGuard g(ix->device);
+  CK(cudaDeviceSynchronize());
+  const size_t words = TIMING_RING * TIMING_PAIRS * 2;
+  std::vector<unsigned long long> t(words);
+  CK(cudaMemcpy(t.data(), ix->timing.p, words * 8, cudaMemcpyDeviceToHost));
+  const size_t used = std::min(ix->timing_launches, TIMING_RING);
+  double dur[TIMING_PAIRS] = {0}, gap[TIMING_PAIRS] = {0};
+  int64_t nd[TIMING_PAIRS] = {0}, ng[TIMING_PAIRS] = {0};
+  for (size_t s = 0; s < used; ++s) {
+    const unsigned long long* c = t.data() + s * TIMING_PAIRS * 2;
+    unsigned long long prev_end = 0;
+    for (size_t i = 0; i < TIMING_PAIRS; ++i) {
+      const unsigned long long b = c[2 * i], e = c[2 * i + 1];
+      if (e <= b || b == ~0ull) continue;  // kernel not part of this search
+      dur[i] += static_cast<double>(e - b) * 1e-6;
+      nd[i]++;
+      if (prev_end != 0 && b >= prev_end) {
+        gap[i] += static_cast<double>(b - prev_end) * 1e-6;
+        ng[i]++;
+      } else if (prev_end != 0) {
+        ng[i]++;  // overlapped its predecessor (programmatic launch): gap 0
+      }
+      prev_end = e;
+    }
+  }
+  for (size_t i = 0; i < TIMING_PAIRS; ++i) {
+    dur_ms[i] = nd[i] ? dur[i] / nd[i] : 0.0;
+    gap_ms[i] = ng[i] ? gap[i] / ng[i] : 0.0;
+  }
+  *searches = static_cast<int64_t>(used);
   return 0;
 }
 
 int keds_index_profile(keds_index_t* ix, double* score_ms_total, int64_t* score_launches) {
   if (!ix || !score_ms_total || !score_launches) return fail(KEDS_ERR_ARG, "profile: null argument");
   if (ix->timing_on) {
-    DeviceGuard g(ix->device);
-    CK(cudaDeviceSynchronize());
-    std::vector<unsigned long long> t(TIMING_RING * 2);
-    CK(cudaMemcpy(t.data(), ix->timing.p, TIMING_RING * 16, cudaMemcpyDeviceToHost));
-    const size_t used = std::min(ix->timing_launches, TIMING_RING);
-    double ms = 0.0;
-    int64_t cnt = 0;
-    for (size_t i = 0; i < used; ++i) {
-      if (t[2 * i + 1] > t[2 * i]) {
-        ms += static_cast<double>(t[2 * i + 1] - t[2 * i]) * 1e-6;
-        cnt++;
-      }
-    }
-    *score_ms_total = ms;
-    *score_launches = cnt;
+    double dur[TIMING_PAIRS], gap[TIMING_PAIRS];
+    int64_t n = 0;
+    CKS(keds_index_profile_chain(ix, dur, gap, &n, TIMING_PAIRS));
+    *score_ms_total = dur[1] * static_cast<double>(n);
+    *score_launches = n;
     return keds_index_set_profiling(ix, 1);  // re-arm the ring
   }
   double ms[PROF_STAGES];

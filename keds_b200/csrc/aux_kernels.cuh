@@ -140,10 +140,12 @@ __device__ __forceinline__ unsigned long long order_key(float rank_score, uint32
 __global__ void k_prep_rows(const float* __restrict__ x, long long n, int d, int d_pad,
                             __nv_bfloat16* __restrict__ out, float4* __restrict__ stat,
                             float* __restrict__ bias, unsigned int* __restrict__ gmax,
-                            unsigned int* __restrict__ zero_words, int n_zero) {
+                            unsigned int* __restrict__ zero_words, int n_zero,
+                            unsigned long long* timing) {
   const int lane = threadIdx.x & 31;
   griddep_wait();               // earlier kernels of the stream may still read what is rewritten here
   griddep_launch_dependents();  // the scoring kernel may start its prologue
+  const unsigned long long t_start = ktimer_begin(timing);
   // per-call control words (flag counters, error word) are cleared here instead of by a separate
   // memset node in front of every search
   if (zero_words != nullptr && blockIdx.x == 0 && threadIdx.x < n_zero) zero_words[threadIdx.x] = 0u;
@@ -205,6 +207,7 @@ __global__ void k_prep_rows(const float* __restrict__ x, long long n, int d, int
     atomicMax(gmax + 0, __float_as_uint(mx_b * 1.000001f));
     atomicMax(gmax + 1, __float_as_uint(mx_d * 1.000001f));
   }
+  ktimer_end(timing, t_start);
 }
 
 __global__ void k_fill_f32(float* p, long long n, float v) {
@@ -325,23 +328,6 @@ __device__ __forceinline__ void consume_query(const ConsumeParams& c, const floa
   }
 }
 
-struct RerankParams {
-  ConsumeParams cons;
-  int n_db, n_qt, S, nq, k, d, metric;
-  const uint2* cand;
-  const int* cand_cnt;
-  const float* cand_theta;
-  const float* q_f32;      // [nq][d]
-  const float4* qstat;     // [nq] {|q|^2, |bf16 q|, |q - bf16 q|}
-  const float* x_f32[2];
-  const unsigned int* dbstat[2];
-  float* D[2];
-  long long* I[2];
-  long long id_offset[2];
-  int* flagged[2];
-  int* n_flagged[2];
-  float eps_scale;         // 1.0 normally; tests shrink/grow it to exercise the fallback
-};
 
 __device__ __forceinline__ float block_max_f(float v, float* red) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -408,200 +394,11 @@ __device__ unsigned int block_kth_largest(const unsigned int* keys, int n, int k
   return prefix;
 }
 
-__global__ void __launch_bounds__(RERANK_THREADS)
-k_select_rerank(const RerankParams p) {
-  extern __shared__ uint8_t rr_smem[];
-  const int q = blockIdx.x, db = blockIdx.y;
-  const int qt = q / BM, ql = q % BM;
-  const int slots = p.S * CAP;
-  // shared layout
-  float* qvec = reinterpret_cast<float*>(rr_smem);                      // d (16-B aligned)
-  float4* part = reinterpret_cast<float4*>(qvec + ((p.d + 3) & ~3));    // cons.part4 (16-B aligned)
-  unsigned int* keys = reinterpret_cast<unsigned int*>(part + p.cons.part4);
-  unsigned int* ids = keys + slots;
-  int* s_cnt = reinterpret_cast<int*>(ids + slots);                     // S
-  int* s_off = s_cnt + p.S;                                             // S
-  unsigned int* sel_id = reinterpret_cast<unsigned int*>(s_off + p.S);  // R_MAX
-  float* sel_sc = reinterpret_cast<float*>(sel_id + R_MAX);             // R_MAX
-  unsigned int* hist = reinterpret_cast<unsigned int*>(sel_sc + R_MAX); // 256
-  float* red = reinterpret_cast<float*>(hist + 256);                    // 32
-  unsigned int* bcast = reinterpret_cast<unsigned int*>(red + 32);      // 4
-  int* counters = reinterpret_cast<int*>(bcast + 4);                    // 4
-  unsigned int* top_id = reinterpret_cast<unsigned int*>(counters + 4); // k  (rank order)
-  float* top_d = reinterpret_cast<float*>(top_id + p.k);                // k
-  float* top_w = top_d + p.k;                                           // k
+}  // namespace keds
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid < 4) counters[tid] = 0;
-  for (int r = tid; r < p.k; r += blockDim.x) top_id[r] = 0xFFFFFFFFu;
-  for (int c = tid; c < p.d; c += blockDim.x) qvec[c] = p.q_f32[static_cast<long long>(q) * p.d + c];
-  griddep_wait();               // candidates come from the scoring kernel
-  griddep_launch_dependents();
-  float th_max = -INFINITY;
-  for (int s = tid; s < p.S; s += blockDim.x) {
-    const long long item = (static_cast<long long>(db) * p.S + s) * p.n_qt + qt;
-    s_cnt[s] = p.cand_cnt[item * BM + ql];
-    th_max = fmaxf(th_max, p.cand_theta[item * BM + ql]);
-  }
-  th_max = block_max_f(th_max, red);  // (syncs)
-  // exclusive scan of the slice counts -> where each slice's run lands in keys[] / ids[]
-  // (S <= blockDim.x; one slice per thread)
-  {
-    const int c = tid < p.S ? s_cnt[tid] : 0;
-    int inc = c;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int up = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += up;
-    }
-    int* wsum = reinterpret_cast<int*>(red);
-    if (lane == 31) wsum[warp] = inc;
-    __syncthreads();
-    int base = 0;
-    for (int w = 0; w < warp; ++w) base += wsum[w];
-    if (tid < p.S) s_off[tid] = base + inc - c;
-    if (tid == blockDim.x - 1) counters[0] = base + inc;
-    __syncthreads();
-  }
-  const int n = counters[0];
-  // each warp copies whole slices: a slice's run is contiguous in global memory (<= 512 B)
-  for (int s = warp; s < p.S; s += (blockDim.x >> 5)) {
-    const int cnt = s_cnt[s], off = s_off[s];
-    const long long item = (static_cast<long long>(db) * p.S + s) * p.n_qt + qt;
-    const uint2* run = p.cand + (item * BM + ql) * CAP;
-    unsigned int kmax = 0u;
-#pragma unroll
-    for (int e0 = 0; e0 < CAP; e0 += 32) {
-      const int e = e0 + lane;
-      if (e < cnt) {
-        const uint2 en = run[e];
-        float sc = __uint_as_float(en.x);
-        if (sc == 0.f) sc = 0.f;
-        const unsigned int key = f32_to_key(sc);
-        keys[off + e] = key;
-        ids[off + e] = en.y;
-        kmax = max(kmax, key);
-      }
-    }
-    kmax = __reduce_max_sync(0xffffffffu, kmax);
-    if (lane == 0) hist[s] = kmax;  // slice maximum (0 = empty slice), S <= 256
-  }
-  __syncthreads();
+#include "rerank.cuh"
 
-  // eps: |a - s| <= |dq| |bf(x)| + |q| |dx| + accumulation allowance
-  const float4 qs = p.qstat[q];
-  const float xb = __uint_as_float(p.dbstat[db][0]);
-  const float xd = __uint_as_float(p.dbstat[db][1]);
-  const float qn = sqrtf(qs.x);
-  const int d_pad = (p.d + BK - 1) / BK * BK;
-  float eps = qs.z * xb + qn * xd + (static_cast<float>(d_pad) * 2.4e-7f) * qs.y * xb;
-  eps *= 1.0001f * p.eps_scale;
-
-  float tau = -INFINITY;
-  if (n >= p.k) {
-    unsigned int kth = 0u;
-    bool fast = false;
-    if (p.S >= p.k) {
-      // t0 = k-th largest slice maximum <= k-th largest score overall, so the keys >= t0 (usually
-      // a few dozen) contain the whole approximate top-k: select among them by rank counting
-      if (tid < p.S) {
-        const unsigned int mine = hist[tid];
-        int rank = 0;
-        for (int u = 0; u < p.S; ++u) {
-          const unsigned int o = hist[u];
-          rank += (o > mine) || (o == mine && u < tid);
-        }
-        if (rank == p.k - 1) bcast[2] = mine;
-      }
-      __syncthreads();
-      const unsigned int t0 = bcast[2];
-      for (int i = tid; i < n; i += blockDim.x) {
-        const unsigned int key = keys[i];
-        if (key >= t0) {
-          const int pos = atomicAdd(&counters[2], 1);
-          if (pos < R_MAX) sel_id[pos] = key;  // sel_id doubles as the survivor list here
-        }
-      }
-      __syncthreads();
-      const int na = counters[2];
-      if (na <= R_MAX) {
-        fast = true;
-        for (int c = tid; c < na; c += blockDim.x) {
-          const unsigned int mine = sel_id[c];
-          int gt = 0, ge = 0;
-          for (int j = 0; j < na; ++j) {
-            const unsigned int o = sel_id[j];
-            gt += o > mine;
-            ge += o >= mine;
-          }
-          if (gt < p.k && ge >= p.k) bcast[3] = mine;
-        }
-        __syncthreads();
-        kth = bcast[3];
-      }
-      __syncthreads();
-    }
-    if (!fast) kth = block_kth_largest(keys, n, p.k, hist, bcast);
-    tau = key_to_f32(kth) - 2.f * eps;
-  }
-  for (int i = tid; i < n; i += blockDim.x) {
-    if (key_to_f32(keys[i]) >= tau) {
-      const int pos = atomicAdd(&counters[1], 1);
-      if (pos < R_MAX) sel_id[pos] = ids[i];
-    }
-  }
-  __syncthreads();
-  int m = counters[1];
-  const bool ok = (m <= R_MAX) && (th_max == -INFINITY || th_max < tau);
-  if (!ok && tid == 0) {
-    const int pos = atomicAdd(p.n_flagged[db], 1);
-    p.flagged[db][pos] = q;
-  }
-  m = min(m, R_MAX);
-
-  const float* xbase = p.x_f32[db];
-  // three candidate rows per warp in flight (same per-row arithmetic as warp_exact_score)
-  for (int c0 = warp * 3; c0 < m; c0 += (blockDim.x >> 5) * 3) {
-    const float* xr[3];
-#pragma unroll
-    for (int r = 0; r < 3; ++r)
-      xr[r] = xbase + static_cast<long long>(sel_id[min(c0 + r, m - 1)]) * p.d;
-    float sc[3];
-    warp_exact_score_multi<3>(qvec, xr, p.d, p.metric, lane, sc);
-    if (lane == 0) {
-#pragma unroll
-      for (int r = 0; r < 3; ++r)
-        if (c0 + r < m) sel_sc[c0 + r] = sc[r];
-    }
-  }
-  __syncthreads();
-  float* Dq = p.D[db] + static_cast<long long>(q) * p.k;
-  long long* Iq = p.I[db] + static_cast<long long>(q) * p.k;
-  for (int c = tid; c < m; c += blockDim.x) {
-    const float sc = sel_sc[c];
-    const unsigned long long mine = order_key(p.metric == METRIC_L2 ? -sc : sc, sel_id[c]);
-    int rank = 0;
-    for (int j = 0; j < m; ++j) {
-      const float sj = sel_sc[j];
-      rank += order_key(p.metric == METRIC_L2 ? -sj : sj, sel_id[j]) > mine;
-    }
-    if (rank < p.k) {
-      Dq[rank] = sc;
-      Iq[rank] = static_cast<long long>(sel_id[c]) + p.id_offset[db];
-      top_id[rank] = sel_id[c];
-      top_d[rank] = sc;
-    }
-  }
-  for (int r = m + tid; r < p.k; r += blockDim.x) {
-    Dq[r] = p.metric == METRIC_L2 ? FLT_MAX : -FLT_MAX;
-    Iq[r] = -1;
-  }
-  // a flagged query is consumed by the exact fallback instead, once its answer is final
-  if (p.cons.enabled && ok) {
-    __syncthreads();
-    consume_query(p.cons, xbase, db, q, p.k, p.d, p.metric, top_id, top_d, top_w, part);
-  }
-}
+namespace keds {
 
 __global__ void k_flag_all(int* flagged, int* n_flagged, int nq) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;

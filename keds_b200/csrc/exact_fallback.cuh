@@ -31,12 +31,13 @@ struct ExactParams {
   ExactDb db[2];
   int n_db, d, metric, k, f_cap, pass;
   const float* q_f32;
+  unsigned long long* timing;  // nullable: pair 0 = k_exact_scores, pair 1 = k_exact_select
 };
 
 __global__ void __launch_bounds__(EXACT_THREADS)
 k_exact_scores(const ExactParams p) {
-  griddep_wait();
-  griddep_launch_dependents();
+  griddep_wait();  // no early trigger: when this kernel has real work its successor must not take its SM slots
+  const unsigned long long t_start = ktimer_begin(p.timing);
   extern __shared__ uint8_t ex_smem[];
   float* qs = reinterpret_cast<float*>(ex_smem);  // EXACT_QG * dq
   const int dq = (p.d + 3) & ~3;
@@ -84,17 +85,22 @@ k_exact_scores(const ExactParams p) {
       }
     }
   }
+  ktimer_end(p.timing, t_start);
 }
 
 __global__ void __launch_bounds__(EXACT_THREADS)
 k_exact_select(const ExactParams p) {
-  griddep_wait();
-  griddep_launch_dependents();
+  griddep_wait();  // no early trigger: when this kernel has real work its successor must not take its SM slots
+  unsigned long long* timing = p.timing ? p.timing + 2 : nullptr;
+  const unsigned long long t_start = ktimer_begin(timing);
   const int dbi = blockIdx.y;
   const ExactDb& e = p.db[dbi];
   const int nfl = *e.n_flagged;
   const int r0 = p.pass * p.f_cap;
-  if (nfl <= r0) return;
+  if (nfl <= r0) {
+    ktimer_end(timing, t_start);
+    return;
+  }
   const int F = min(p.f_cap, nfl - r0);
 
   extern __shared__ uint8_t ex_smem[];
@@ -207,6 +213,7 @@ k_exact_select(const ExactParams p) {
       consume_query(p.cons, e.x_f32, dbi, q, p.k, p.d, p.metric, top_id, top_d, top_w, part);
     }
   }
+  ktimer_end(timing, t_start);
 }
 
 }  // namespace keds

@@ -45,6 +45,18 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
   return t;
 }
 
+// In-kernel launch timer: t[0] = min start, t[1] = max end over the CTAs of one launch
+// (t == nullptr: off). Costs two atomics per CTA and leaves the launch chain untouched.
+__device__ __forceinline__ unsigned long long ktimer_begin(const unsigned long long* t) {
+  return (t != nullptr && threadIdx.x == 0) ? global_timer_ns() : 0ull;
+}
+__device__ __forceinline__ void ktimer_end(unsigned long long* t, unsigned long long t0) {
+  if (t != nullptr && threadIdx.x == 0) {
+    atomicMin(t, t0);
+    atomicMax(t + 1, global_timer_ns());
+  }
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");

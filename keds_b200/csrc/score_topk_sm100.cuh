@@ -49,7 +49,7 @@ struct ScoreParams {
   int n_rows[2];     // rows per database
   int n_tiles[2];    // ceil(n_rows / BN)
   const float* bias[2];  // nullable; additive per-row bias padded with -inf to n_tiles * BN
-  uint2* cand;       // [n_items][BM][CAP] {approx score bits, row id}
+  uint2* cand;       // [n_items][BM][LKEEP] {approx score bits, row id}, padded {-inf, ~0}
   int* cand_cnt;     // [n_items][BM]
   float* cand_theta; // [n_items][BM]  everything the slice dropped scored <= theta
   uint32_t* err;     // device error word (0 = ok)
@@ -179,8 +179,7 @@ k_score_topk(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
   // (k_select_rerank) start its own prologue as soon as SMs free up.
   griddep_wait();
   griddep_launch_dependents();
-  unsigned long long t_start = 0;
-  if (p.timing != nullptr && threadIdx.x == 0) t_start = global_timer_ns();
+  const unsigned long long t_start = ktimer_begin(p.timing);
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -323,14 +322,22 @@ k_score_topk(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
-      // flush this item's candidates as [item][query][e]: each query's run is contiguous, so the
-      // re-rank kernel reads it with one coalesced warp load
-      int maxc = cnt;
+      // Final compaction: at most LKEEP - 1 entries survive (those strictly above the slice's
+      // LKEEP-th best, which becomes theta). They leave as one 128-byte line per (item, query):
+      // [item][query][LKEEP] {score bits, row id}, padded with {-inf, ~0}; the re-rank kernel
+      // reads a slice with a single coalesced half-warp load.
+      if (__any_sync(0xffffffffu, cnt >= LKEEP)) {
+        const CandState st = compact_candidates(slot0, cnt, theta);
+        cnt = st.cnt;
+        theta = st.theta;
+      }
+      uint2* cbase = p.cand + (static_cast<long long>(item) * BM + q_local) * LKEEP;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) maxc = max(maxc, __shfl_xor_sync(0xffffffffu, maxc, o));
-      uint2* cbase = p.cand + (static_cast<long long>(item) * BM + q_local) * CAP;
-      for (int e = 0; e < maxc; ++e) {
-        if (e < cnt) cbase[e] = lds64(slot0 + e * 256);
+      for (int e = 0; e < LKEEP; e += 2) {
+        uint2 a = make_uint2(0xff800000u, 0xffffffffu), b = a;
+        if (e < cnt) a = lds64(slot0 + e * 256);
+        if (e + 1 < cnt) b = lds64(slot0 + (e + 1) * 256);
+        *reinterpret_cast<uint4*>(cbase + e) = make_uint4(a.x, a.y, b.x, b.y);
       }
       p.cand_cnt[static_cast<long long>(item) * BM + q_local] = cnt;
       p.cand_theta[static_cast<long long>(item) * BM + q_local] = theta;
@@ -340,11 +347,7 @@ k_score_topk(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
 
   tc_fence_before();
   __syncthreads();
-  if (p.timing != nullptr && threadIdx.x == 0) {
-    // kernel duration without stream events: min start / max end over the CTAs of this launch
-    atomicMin(p.timing + 0, t_start);
-    atomicMax(p.timing + 1, global_timer_ns());
-  }
+  ktimer_end(p.timing, t_start);  // kernel duration without stream events
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();

@@ -234,6 +234,17 @@ class GpuIndexFlat:
         _capi.check(self._lib.keds_index_profile(self._h, C.byref(ms), C.byref(n)))
         return float(ms.value), int(n.value)
 
+    CHAIN = ("k_prep_rows", "k_score_topk", "k_select_rerank", "k_exact_scores", "k_exact_select")
+
+    def profile_chain(self) -> dict:
+        """In-loop timeline of a search (mode 1): per kernel {'ms': duration, 'gap_ms': idle gap
+        before it}, averaged over the searches since set_profiling(1)."""
+        dur, gap, n = (C.c_double * 5)(), (C.c_double * 5)(), C.c_int64(0)
+        _capi.check(self._lib.keds_index_profile_chain(self._h, dur, gap, C.byref(n), 5))
+        out = {name: {"ms": float(dur[i]), "gap_ms": float(gap[i])} for i, name in enumerate(self.CHAIN)}
+        out["searches"] = int(n.value)
+        return out
+
     STAGES = ("", "k_prep_rows", "k_score_topk", "k_select_rerank", "k_exact_scores+select", "")
 
     def profile_stages(self) -> dict:

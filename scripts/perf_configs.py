@@ -53,10 +53,10 @@ def run(name, ix_list, q, k, iters, fn):
         a.set_pdl(bool(pdl))
         a.set_profiling(1)
         ms = timeit(fn, iters)
-        kms, kn = a.profile()
+        chain = a.profile_chain()
         a.set_profiling(0)
         key = f"pdl{pdl}"
-        out.setdefault(key, []).append({"ms": ms, "score_kernel_ms": kms / max(kn, 1)})
+        out.setdefault(key, []).append({"ms": ms, "score_kernel_ms": chain["k_score_topk"]["ms"], "chain": chain})
     a.set_pdl(True)
     b = q.shape[0]
     n = a.ntotal
