@@ -179,7 +179,8 @@ int set_kernel_attrs(keds_index* ix) {
   if (ix->attrs_set) return 0;
   CK(cudaFuncSetAttribute(k_score_topk, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)SCORE_SMEM_BYTES));
-  CK(cudaFuncSetAttribute(k_select_rerank, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(k_select_rerank<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(k_select_rerank<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaFuncSetAttribute(k_exact_scores, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   CK(cudaFuncSetAttribute(k_exact_select, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   const char* no_pdl = getenv("KEDS_NO_PDL");
@@ -217,7 +218,10 @@ Plan make_plan(const keds_index* ix, int n_db, int64_t nq, int k, int64_t n_min,
   pl.n_qt = static_cast<int>((nq + BM - 1) / BM);
   const int T_min = static_cast<int>((n_min + BN - 1) / BN);
   const int T_max = static_cast<int>((n_max + BN - 1) / BN);
-  const int S_sel = std::max(1, (3 * k + LKEEP - 1) / LKEEP);
+  // a slice hands over its best LKEEP-1 rows and drops the rest (theta = its LKEEP-th best): for
+  // the certificate to pass, theta must sit well below the k-th best score overall, i.e. the
+  // top-k must be spread over many slices (expected share per slice <= LKEEP / 6)
+  const int S_sel = std::max(1, (6 * k + LKEEP - 1) / LKEEP);
   const int groups = n_db * pl.n_qt;
   int S_hi = std::min(T_min, S_MAX);
   const long long by_mem = static_cast<long long>(CAND_BUDGET / (size_t(LKEEP) * BM * 8)) / groups;
@@ -450,8 +454,14 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
                         slots * 8 + pl.S * 4 + R_MAX * 16 + 256 * 4 + 32 * 4 + 16 + 16 +
                         static_cast<size_t>(k) * 12;
     if (smem > 200 * 1024) return fail(KEDS_ERR_ARG, "re-rank shared memory %zu too large", smem);
-    CKS(launch_k(a->use_pdl, k_select_rerank, dim3(static_cast<unsigned>(nq), n_db), dim3(RERANK_THREADS), smem,
-                 st, rp));
+    // one wave of blocks (two per SM): the latency variant; more: the four-per-SM throughput variant
+    const bool small_batch = nq * n_db <= 2ll * a->num_sms;
+    if (small_batch)
+      CKS(launch_k(a->use_pdl, k_select_rerank<3, 2>, dim3(static_cast<unsigned>(nq), n_db),
+                   dim3(RERANK_THREADS), smem, st, rp));
+    else
+      CKS(launch_k(a->use_pdl, k_select_rerank<1, 4>, dim3(static_cast<unsigned>(nq), n_db),
+                   dim3(RERANK_THREADS), smem, st, rp));
     CKS(prof_mark(a, st, 3));
     a->stats.launches++;
     CK(cudaGetLastError());
@@ -763,15 +773,9 @@ int keds_retrieve2(keds_index_t* img, keds_index_t* txt, const float* q, int64_t
   cp.feat[1] = feat_txt;
   cp.pool[0] = want_pool ? pool_img : nullptr;
   cp.pool[1] = want_pool ? pool_txt : nullptr;
-  // the ranking block (512 threads) splits into groups of d/4 lanes, one float4 column per lane,
-  // each group streaming different neighbours; the groups' partial pools meet in shared memory
-  cp.jgroups = 1;
-  cp.part4 = 0;
-  if ((img->d & 3) == 0) {
-    const int d4 = img->d >> 2;
-    cp.jgroups = std::max(1, std::min({4, RERANK_THREADS / std::max(1, std::min(d4, RERANK_THREADS)), k}));
-    cp.part4 = cp.jgroups * d4;
-  }
+  // one warp per neighbour row; per-warp partial pools meet in shared memory ([warps][d/4] float4)
+  static_assert(RERANK_THREADS == EXACT_THREADS, "the consumer scratch is sized for one block shape");
+  cp.part4 = (img->d & 3) == 0 ? (RERANK_THREADS / 32) * (img->d >> 2) : 0;
   return search_impl(v, 2, q, nq, k, Dv, Iv, flags, stream, cp.enabled ? &cp : nullptr);
 }
 

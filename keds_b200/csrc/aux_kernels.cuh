@@ -235,8 +235,7 @@ __global__ void k_fill_f32(float* p, long long n, float v) {
 struct ConsumeParams {
   int enabled;      // 0: plain search
   int mode;         // 0 no pool, 1 mean, 2 softmax
-  int jgroups;      // thread groups working on different neighbours of the same column
-  int part4;        // float4 slots of shared scratch: jgroups * d / 4 (0 when d % 4 != 0)
+  int part4;        // float4 slots of shared scratch: warps per block * d / 4 (0 when d % 4 != 0)
   float tau;
   const int* perm[2];
   float* feat[2];   // [nq][k][d]
@@ -244,6 +243,8 @@ struct ConsumeParams {
 };
 
 // top_id: local row ids in rank order (0xFFFFFFFF = padding), top_d: their D values.
+// NIF = neighbour rows in flight per warp (2 for latency, 1 where registers are scarce).
+template <int NIF>
 __device__ __forceinline__ void consume_query(const ConsumeParams& c, const float* __restrict__ rows,
                                               int s, long long b, int k, int d, int metric,
                                               const unsigned int* top_id, const float* top_d,
@@ -276,37 +277,65 @@ __device__ __forceinline__ void consume_query(const ConsumeParams& c, const floa
   const bool vec = c.part4 > 0 && ((reinterpret_cast<uintptr_t>(rows) | reinterpret_cast<uintptr_t>(c.feat[s]) |
                                     reinterpret_cast<uintptr_t>(c.pool[s])) & 15) == 0;
   if (vec) {
-    // threads form JG groups of `cols` lanes; group g takes neighbours g, g+JG, ... so several
-    // 3-KB row reads are in flight per column; partial pools meet in shared memory
+    // One warp per neighbour row, two neighbours per warp in flight: every lane issues all its
+    // 16-byte loads of both rows before the first store, so the whole gather of a query costs
+    // about one memory round trip. Each warp keeps the weighted sum of its own neighbours; the
+    // per-warp partial pools meet in shared memory (part: [warps][d/4]).
     const int d4 = d >> 2;
-    const int cols = min(d4, static_cast<int>(blockDim.x));
-    const int JG = max(1, min(c.jgroups, static_cast<int>(blockDim.x) / cols));
-    const int g = tid / cols, c0 = tid % cols;
-    if (g < JG) {
-      for (int col = c0; col < d4; col += cols) {
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 8
-        for (int jo = g; jo < k; jo += JG) {
-          const int j = perm ? perm[jo] : jo;  // output slot jo shows rank j
-          const unsigned int id = top_id[j];
-          const float4 v = id != 0xFFFFFFFFu
-                               ? __ldg(reinterpret_cast<const float4*>(rows + static_cast<long long>(id) * d) + col)
-                               : make_float4(0.f, 0.f, 0.f, 0.f);
-          if (feat) reinterpret_cast<float4*>(feat + static_cast<long long>(jo) * d)[col] = v;
-          const float wj = w[j];
-          acc.x = fmaf(wj, v.x, acc.x);
-          acc.y = fmaf(wj, v.y, acc.y);
-          acc.z = fmaf(wj, v.z, acc.z);
-          acc.w = fmaf(wj, v.w, acc.w);
+    const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    constexpr int U = 6;  // float4 per lane per pass: d = 768 is one pass
+    for (int cb = 0; cb < d4; cb += 32 * U) {
+      float4 acc[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int jo0 = warp * NIF; jo0 < k; jo0 += nwarps * NIF) {
+        float4 v[NIF][U];
+        unsigned int idv[NIF];
+        int jr[NIF];
+#pragma unroll
+        for (int t = 0; t < NIF; ++t) {
+          const int jo = jo0 + t;
+          jr[t] = jo < k ? (perm ? perm[jo] : jo) : 0;  // output slot jo shows rank jr
+          idv[t] = jo < k ? top_id[jr[t]] : 0xFFFFFFFFu;
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int col = cb + u * 32 + lane;
+            v[t][u] = (idv[t] != 0xFFFFFFFFu && col < d4)
+                          ? __ldg(reinterpret_cast<const float4*>(rows + static_cast<long long>(idv[t]) * d) + col)
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
         }
-        if (pool) part[g * d4 + col] = acc;
+#pragma unroll
+        for (int t = 0; t < NIF; ++t) {
+          const int jo = jo0 + t;
+          if (jo >= k) continue;
+          const float wj = w[jr[t]];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int col = cb + u * 32 + lane;
+            if (col < d4) {
+              if (feat) reinterpret_cast<float4*>(feat + static_cast<long long>(jo) * d)[col] = v[t][u];
+              acc[u].x = fmaf(wj, v[t][u].x, acc[u].x);
+              acc[u].y = fmaf(wj, v[t][u].y, acc[u].y);
+              acc[u].z = fmaf(wj, v[t][u].z, acc[u].z);
+              acc[u].w = fmaf(wj, v[t][u].w, acc[u].w);
+            }
+          }
+        }
+      }
+      if (pool) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int col = cb + u * 32 + lane;
+          if (col < d4) part[warp * d4 + col] = acc[u];
+        }
       }
     }
     if (pool) {
       __syncthreads();
       for (int col = tid; col < d4; col += blockDim.x) {
         float4 acc = part[col];
-        for (int gg = 1; gg < JG; ++gg) {
+        for (int gg = 1; gg < nwarps; ++gg) {
           const float4 o = part[gg * d4 + col];
           acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
         }

@@ -210,7 +210,7 @@ k_exact_select(const ExactParams p) {
     }
     if (p.cons.enabled) {
       __syncthreads();
-      consume_query(p.cons, e.x_f32, dbi, q, p.k, p.d, p.metric, top_id, top_d, top_w, part);
+      consume_query<1>(p.cons, e.x_f32, dbi, q, p.k, p.d, p.metric, top_id, top_d, top_w, part);
     }
   }
   ktimer_end(timing, t_start);

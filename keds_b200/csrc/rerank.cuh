@@ -37,7 +37,11 @@ struct RerankParams {
 
 constexpr unsigned int PAD_ID = 0xFFFFFFFFu;
 
-__global__ void __launch_bounds__(RERANK_THREADS)
+// R = candidate rows per warp in flight during the fp32 re-score. <3, 2>: small batches, shortest
+// dependency chain (two blocks per SM). <1, 4>: large batches, four blocks per SM so that many
+// queries overlap their phases.
+template <int R, int MINB>
+__global__ void __launch_bounds__(RERANK_THREADS, MINB)
 k_select_rerank(const RerankParams p) {
   extern __shared__ uint8_t rr_smem[];
   const int q = blockIdx.x, db = blockIdx.y;
@@ -230,18 +234,18 @@ k_select_rerank(const RerankParams p) {
   }
   m = min(m, R_MAX);
 
-  // ---- C: exact fp32 scores of the candidates, three rows per warp in flight
+  // ---- C: exact fp32 scores of the candidates, R rows per warp in flight
   const float* xbase = p.x_f32[db];
-  for (int c0 = warp * 3; c0 < m; c0 += nwarps * 3) {
-    const float* xr[3];
+  for (int c0 = warp * R; c0 < m; c0 += nwarps * R) {
+    const float* xr[R];
 #pragma unroll
-    for (int r = 0; r < 3; ++r)
+    for (int r = 0; r < R; ++r)
       xr[r] = xbase + static_cast<long long>(sel_id[min(c0 + r, m - 1)]) * p.d;
-    float sc[3];
-    warp_exact_score_multi<3>(qvec, xr, p.d, p.metric, lane, sc);
+    float sc[R];
+    warp_exact_score_multi<R>(qvec, xr, p.d, p.metric, lane, sc);
     if (lane == 0) {
 #pragma unroll
-      for (int r = 0; r < 3; ++r)
+      for (int r = 0; r < R; ++r)
         if (c0 + r < m) sel_sc[c0 + r] = sc[r];
     }
   }
@@ -272,7 +276,7 @@ k_select_rerank(const RerankParams p) {
   // a flagged query is consumed by the exact fallback instead, once its answer is final
   if (p.cons.enabled && ok) {
     __syncthreads();  // (7)
-    consume_query(p.cons, xbase, db, q, p.k, p.d, p.metric, top_id, top_d, top_w, part);
+    consume_query<(R >= 2 ? 2 : 1)>(p.cons, xbase, db, q, p.k, p.d, p.metric, top_id, top_d, top_w, part);
   }
   ktimer_end(p.timing, t_start);
 }
