@@ -172,14 +172,22 @@ class GpuIndexFlat:
         _capi.check(self._lib.keds_index_add(self._h, a.ctypes.data, a.shape[0]))
 
     # -- search
-    def search(self, x, k: int, flags: int = 0):
+    def search(self, x, k: int, flags: int = 0, out=None):
+        """numpy in -> numpy (D, I) out, synchronous. CUDA tensor in -> CUDA tensors out,
+        stream-ordered; `out=(D, I)` may name preallocated contiguous CUDA tensors to fill."""
         k = int(k)
         if k <= 0:
             raise ValueError("k must be positive")
         if _is_tensor(x) and x.is_cuda:
             q = self._check_q_tensor(x)
-            D = torch.empty((q.shape[0], k), dtype=torch.float32, device=q.device)
-            I = torch.empty((q.shape[0], k), dtype=torch.int64, device=q.device)
+            if out is not None:
+                D, I = out
+                assert D.is_cuda and I.is_cuda and D.is_contiguous() and I.is_contiguous()
+                assert D.dtype == torch.float32 and I.dtype == torch.int64
+                assert D.numel() == q.shape[0] * k and I.numel() == q.shape[0] * k
+            else:
+                D = torch.empty((q.shape[0], k), dtype=torch.float32, device=q.device)
+                I = torch.empty((q.shape[0], k), dtype=torch.int64, device=q.device)
             _capi.check(
                 self._lib.keds_index_search_ex(
                     self._h, q.data_ptr(), q.shape[0], k, D.data_ptr(), I.data_ptr(), flags,

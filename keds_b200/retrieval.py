@@ -179,6 +179,70 @@ def retrieve2(image_index: GpuIndexFlat, text_index: GpuIndexFlat, q: torch.Tens
     return o
 
 
+class RetrievalStep:
+    """The steady-state retrieval step of a training loop, captured once into a CUDA graph:
+
+        pinned host queries --H2D--> fused two-database search + gather + pool --D2H--> (D, I)
+
+    One graph launch per step replaces ~10 stream operations, so the host cost of a step is a
+    few microseconds. Write the batch into `q_host` (pinned, [batch, d]) or pass it to `run()`;
+    after `run()` returns, `D_img/I_img/D_txt/I_txt` (pinned host) hold what `index.search` gives
+    the host in the reference, and `out` holds the device tensors (gathered / pooled streams).
+    """
+
+    def __init__(self, image_index: GpuIndexFlat, text_index: GpuIndexFlat, batch: int, topk: int = 16,
+                 perm_img: Optional[torch.Tensor] = None, want_feats: bool = True,
+                 pool_mode: int = POOL_NONE, tau: float = 100.0) -> None:
+        self.ia, self.ib = image_index, text_index
+        dev = torch.device("cuda", image_index.device)
+        d, k = image_index.d, int(topk)
+        self.q_host = torch.empty((batch, d), dtype=torch.float32).pin_memory()
+        self.q_dev = torch.empty((batch, d), dtype=torch.float32, device=dev)
+        # (I_img | I_txt | D_img | D_txt) live in one device block mirrored by one pinned host block,
+        # so the results leave the GPU with a single copy
+        nI, nD = batch * k * 8, batch * k * 4
+        self._res_dev = torch.empty(2 * nI + 2 * nD, dtype=torch.uint8, device=dev)
+        self._res_host = torch.empty(2 * nI + 2 * nD, dtype=torch.uint8).pin_memory()
+
+        def views(blk):
+            return (blk[0:nI].view(torch.int64).view(batch, k), blk[nI:2 * nI].view(torch.int64).view(batch, k),
+                    blk[2 * nI:2 * nI + nD].view(torch.float32).view(batch, k),
+                    blk[2 * nI + nD:].view(torch.float32).view(batch, k))
+
+        self.I_img, self.I_txt, self.D_img, self.D_txt = views(self._res_host)
+        Ii, It, Di, Dt = views(self._res_dev)
+        self.perm = None if perm_img is None else perm_img.to(device=dev, dtype=torch.int32).contiguous()
+        self.out: dict = {"I_img": Ii, "I_txt": It, "D_img": Di, "D_txt": Dt}
+        self._args = dict(topk=k, perm_img=self.perm, want_feats=want_feats, pool_mode=pool_mode, tau=tau)
+        self.h2d_bytes = self.q_host.numel() * 4
+        self.d2h_bytes = sum(t.numel() * t.element_size() for t in (self.D_img, self.D_txt, self.I_img, self.I_txt))
+        self.q_host.zero_()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(3):  # warm up: every scratch buffer reaches its final size before capture
+                self._body()
+            side.synchronize()
+            self.ia.sync()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, stream=side):
+                self._body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+
+    def _body(self) -> None:
+        self.q_dev.copy_(self.q_host, non_blocking=True)
+        retrieve2(self.ia, self.ib, self.q_dev, out=self.out, **self._args)
+        self._res_host.copy_(self._res_dev, non_blocking=True)
+
+    def run(self, q: Optional[torch.Tensor] = None, sync: bool = True) -> dict:
+        if q is not None:
+            self.q_host.copy_(q)
+        self.graph.replay()
+        if sync:
+            torch.cuda.current_stream(self.q_dev.device).synchronize()
+        return self.out
+
+
 def get_extra_cap_features(feature, database, args=None, topk: int = 2):
     """src/trainer.py:262-283: top-`topk` text neighbours + their basenames (row-major order)."""
     image_base, text_base, basenames, image_index, text_index = (database[i] for i in range(5))

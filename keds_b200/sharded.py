@@ -72,14 +72,18 @@ class ShardedIndex:
     def search(self, q: torch.Tensor, k: int):
         """q: [nq, d] float32 on this rank's device, identical on all ranks. Returns (D, I)."""
         nq = int(q.shape[0])
-        D, I = self.local.search(q, k)
-        D = torch.as_tensor(D)
-        I = torch.as_tensor(I)
         total, off_i, d_bytes = packed_layout(nq, k)
-        send = torch.empty(total, dtype=torch.uint8, device=D.device)
-        send[:d_bytes].view(torch.float32).copy_(D.reshape(-1))
-        send[off_i:].view(torch.int64).copy_(I.reshape(-1))
-        recv = torch.empty(self.world * total, dtype=torch.uint8, device=D.device)
+        if isinstance(self.local, GpuIndexFlat):
+            # the local search writes straight into the exchange buffer: no repacking copies
+            send = torch.empty(total, dtype=torch.uint8, device=q.device)
+            self.local.search(q, k, out=(send[:d_bytes].view(torch.float32), send[off_i:].view(torch.int64)))
+        else:  # CPU test stand-in
+            D, I = self.local.search(q, k)
+            D, I = torch.as_tensor(D), torch.as_tensor(I)
+            send = torch.empty(total, dtype=torch.uint8, device=D.device)
+            send[:d_bytes].view(torch.float32).copy_(D.reshape(-1))
+            send[off_i:].view(torch.int64).copy_(I.reshape(-1))
+        recv = torch.empty(self.world * total, dtype=torch.uint8, device=send.device)
         dist.all_gather_into_tensor(recv, send, group=self.group)
         if self._merge is not None:  # CPU test hook
             parts = recv.view(self.world, total)
@@ -87,8 +91,8 @@ class ShardedIndex:
             Ip = torch.stack([parts[r, off_i:].view(torch.int64).view(nq, k) for r in range(self.world)])
             return self._merge(Dp, Ip, k, self.metric_type)
         lib = _capi.load()
-        Dg = torch.empty((nq, k), dtype=torch.float32, device=D.device)
-        Ig = torch.empty((nq, k), dtype=torch.int64, device=D.device)
+        Dg = torch.empty((nq, k), dtype=torch.float32, device=send.device)
+        Ig = torch.empty((nq, k), dtype=torch.int64, device=send.device)
         base = recv.data_ptr()
         _capi.check(
             lib.keds_topk_merge_strided(base, base + off_i, total // 4, total // 8, self.world, nq, k,

@@ -312,6 +312,25 @@ def test_fused_retrieve2_matches_oracle(metric):
     assert pi.shape == (70, 1, 768) and pt.shape == (70, 1, 768)
 
 
+def test_graph_captured_retrieval_step_matches_the_stream_path():
+    """RetrievalStep: H2D + search + gather + pool + D2H captured in a CUDA graph; replays with new
+    host queries give the same answers as the plain calls and as the oracle."""
+    a, b = unit(20000, 768, 101), unit(20000, 768, 102)
+    ia, ib = build(a, "ip"), build(b, "ip")
+    perm = torch.randperm(16, generator=torch.Generator().manual_seed(9))
+    step = kr.RetrievalStep(ia, ib, 128, 16, perm_img=perm, want_feats=True, pool_mode=kr.POOL_MEAN)
+    for seed in (103, 104, 105):
+        q = unit(128, 768, seed)
+        out = step.run(torch.from_numpy(q))
+        Dr, Ir = orc.search(a, q, 16)
+        assert orc.compare_topk(Dr, Ir, step.D_img.numpy(), step.I_img.numpy(), a, q)["ok"]
+        Dr, Ir = orc.search(b, q, 16)
+        assert orc.compare_topk(Dr, Ir, step.D_txt.numpy(), step.I_txt.numpy(), b, q)["ok"]
+        assert np.array_equal(out["feat_img"].cpu().numpy(), orc.gather(a, step.I_img.numpy(), perm.numpy()))
+        ref = orc.gather(b, step.I_txt.numpy()).astype(np.float64).mean(1)
+        assert np.abs(out["pool_txt"].cpu().numpy() - ref).max() < 1e-6
+
+
 # ------------------------------------------------------------------ reference-shaped operators vs golden
 def test_get_retrieved_features_matches_the_reference_outputs(golden_dir):
     z = np.load(os.path.join(golden_dir, "retrieval.npz"))
