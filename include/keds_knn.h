@@ -59,6 +59,14 @@ void keds_index_free(keds_index_t* idx);
  * device. Copies; the caller may free x on return. Builds the fp32 master, the bf16 operand copy
  * and the per-row norms on the index's device. */
 int keds_index_add(keds_index_t* idx, const float* x, int64_t n);
+/* add with options. KEDS_ADD_NORMALIZE: rows are L2-normalised on the device while they are added
+ * (the database builder's `bases / bases.norm(dim=1, keepdim=True)`, src/main.py:465-466), so the
+ * fp32 master, the bf16 operand copy and the norms come out of one pass over the upload. */
+#define KEDS_ADD_NORMALIZE 1u
+int keds_index_add_ex(keds_index_t* idx, const float* x, int64_t n, uint32_t flags);
+/* copy rows [first, first+n) of the resident fp32 master to out (host or device) -- e.g. to save a
+ * database built on the device back into the .pt layout */
+int keds_index_get_rows(const keds_index_t* idx, int64_t first, int64_t n, float* out);
 int keds_index_reset(keds_index_t* idx);                 /* index.reset() */
 int64_t keds_index_ntotal(const keds_index_t* idx);      /* index.ntotal */
 int keds_index_dim(const keds_index_t* idx);             /* index.d */

@@ -38,6 +38,8 @@ SIGNATURES = {
     "keds_index_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
     "keds_index_free": (None, [_vp]),
     "keds_index_add": (C.c_int, [_vp, _vp, C.c_int64]),
+    "keds_index_add_ex": (C.c_int, [_vp, _vp, C.c_int64, C.c_uint32]),
+    "keds_index_get_rows": (C.c_int, [_vp, C.c_int64, C.c_int64, _vp]),
     "keds_index_reset": (C.c_int, [_vp]),
     "keds_index_ntotal": (C.c_int64, [_vp]),
     "keds_index_dim": (C.c_int, [_vp]),

@@ -655,7 +655,20 @@ void keds_index_free(keds_index_t* ix) {
   delete ix;
 }
 
-int keds_index_add(keds_index_t* ix, const float* x, int64_t n) {
+int keds_index_add(keds_index_t* ix, const float* x, int64_t n) { return keds_index_add_ex(ix, x, n, 0u); }
+
+int keds_index_get_rows(const keds_index_t* ix, int64_t first, int64_t n, float* out) {
+  if (!ix || !out || first < 0 || n < 0 || first + n > ix->n)
+    return fail(KEDS_ERR_ARG, "get_rows: bad range [%lld, %lld) of %lld rows", (long long)first,
+                (long long)(first + n), (long long)(ix ? ix->n : 0));
+  if (n == 0) return 0;
+  DeviceGuard g(ix->device);
+  CK(cudaMemcpy(out, ix->x_f32.as<float>() + first * ix->d, static_cast<size_t>(n) * ix->d * 4,
+                cudaMemcpyDefault));
+  return 0;
+}
+
+int keds_index_add_ex(keds_index_t* ix, const float* x, int64_t n, uint32_t flags) {
   if (!ix || (n > 0 && !x) || n < 0) return fail(KEDS_ERR_ARG, "add: null handle/data or negative n");
   if (n == 0) return 0;
   DeviceGuard g(ix->device);
@@ -672,6 +685,7 @@ int keds_index_add(keds_index_t* ix, const float* x, int64_t n) {
   }
   CK(cudaMemcpy(ix->x_f32.as<float>() + n0 * d, x, static_cast<size_t>(n) * d * 4, cudaMemcpyDefault));
   const unsigned blocks = static_cast<unsigned>(std::min<int64_t>((n * 32 + 255) / 256, 148 * 16));
+  if (flags & KEDS_ADD_NORMALIZE) k_normalize_rows<<<blocks, 256>>>(ix->x_f32.as<float>() + n0 * d, n, ix->d);
   k_prep_rows<<<blocks, 256>>>(ix->x_f32.as<float>() + n0 * d, n, ix->d, ix->d_pad,
                                ix->x_bf16.as<__nv_bfloat16>() + n0 * dp, nullptr,
                                ix->bias.as<float>() + n0, ix->dbstat.as<unsigned int>(), nullptr, 0, nullptr);

@@ -210,6 +210,23 @@ __global__ void k_prep_rows(const float* __restrict__ x, long long n, int d, int
   ktimer_end(timing, t_start);
 }
 
+// In-place L2 normalisation of fp32 rows (x / |x|, zero rows stay zero): the database builder's
+// `bases / bases.norm(dim=1, keepdim=True)` (src/main.py:465-466). One warp per row.
+__global__ void k_normalize_rows(float* __restrict__ x, long long n, int d) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  for (long long r = warp0; r < n; r += nwarps) {
+    float* xr = x + r * d;
+    float n2 = 0.f;
+    for (int c = lane; c < d; c += 32) n2 = fmaf(xr[c], xr[c], n2);
+    n2 = warp_sum(n2);
+    const float nrm = sqrtf(n2);
+    if (nrm > 0.f)
+      for (int c = lane; c < d; c += 32) xr[c] = xr[c] / nrm;
+  }
+}
+
 __global__ void k_fill_f32(float* p, long long n, float v) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;

@@ -157,7 +157,9 @@ class GpuIndexFlat:
         _capi.check(self._lib.keds_index_set_eps_scale(self._h, float(scale)))
 
     # -- add
-    def add(self, x) -> None:
+    def add(self, x, normalize: bool = False) -> None:
+        """index.add(x). normalize=True L2-normalises the rows on the device as they are added."""
+        flags = 1 if normalize else 0
         if _is_tensor(x):
             if x.dim() != 2 or x.shape[1] != self.d:
                 raise AssertionError(f"add: shape {tuple(x.shape)} does not match d={self.d}")
@@ -166,10 +168,17 @@ class GpuIndexFlat:
             x = x.contiguous()
             if x.is_cuda:
                 torch.cuda.current_stream(x.device).synchronize()
-            _capi.check(self._lib.keds_index_add(self._h, x.data_ptr(), x.shape[0]))
+            _capi.check(self._lib.keds_index_add_ex(self._h, x.data_ptr(), x.shape[0], flags))
             return
         a = _as_f32_matrix(x, self.d, "add")
-        _capi.check(self._lib.keds_index_add(self._h, a.ctypes.data, a.shape[0]))
+        _capi.check(self._lib.keds_index_add_ex(self._h, a.ctypes.data, a.shape[0], flags))
+
+    def get_rows(self, first: int = 0, n: Optional[int] = None) -> np.ndarray:
+        """rows [first, first+n) of the resident fp32 master as a host array (e.g. to save a .pt)."""
+        n = self.ntotal - first if n is None else int(n)
+        out = np.empty((n, self.d), dtype=np.float32)
+        _capi.check(self._lib.keds_index_get_rows(self._h, int(first), n, out.ctypes.data))
+        return out
 
     # -- search
     def search(self, x, k: int, flags: int = 0, out=None):

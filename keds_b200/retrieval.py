@@ -72,19 +72,27 @@ class KnowledgeBase:
 
     def __init__(self, image_bases: torch.Tensor, text_bases: torch.Tensor, basenames: Sequence[str],
                  device: int = 0, metric: int = METRIC_L2) -> None:
+        self._init_indices(image_bases, text_bases, basenames, device, metric, normalize=False)
+
+    def _init_indices(self, image_bases, text_bases, basenames, device, metric, normalize) -> None:
         for t in (image_bases, text_bases):
             if not (isinstance(t, torch.Tensor) and t.dtype == torch.float32 and t.dim() == 2):
                 raise TypeError("knowledge bases must be 2-D float32 torch tensors (the .pt layout)")
         if image_bases.shape != text_bases.shape:
             raise ValueError("image and text bases must be aligned row for row")
-        self.image_bases = image_bases
-        self.text_bases = text_bases
+        if len(basenames) != image_bases.shape[0]:
+            raise ValueError("one basename per row")
         self.basenames = list(basenames)
         d = image_bases.shape[1]
         self.image_index = GpuIndexFlat(d, metric, device)
         self.text_index = GpuIndexFlat(d, metric, device)
-        self.image_index.add(image_bases)
-        self.text_index.add(text_bases)
+        self.image_index.add(image_bases, normalize=normalize)
+        self.text_index.add(text_bases, normalize=normalize)
+        if normalize:  # keep the host tensors bit-identical to what the device searches
+            image_bases = torch.from_numpy(self.image_index.get_rows())
+            text_bases = torch.from_numpy(self.text_index.get_rows())
+        self.image_bases = image_bases
+        self.text_bases = text_bases
 
     @classmethod
     def load(cls, image_pt: str, text_pt: str, names_txt: str, device: int = 0, metric: int = METRIC_L2):

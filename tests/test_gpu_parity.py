@@ -479,3 +479,28 @@ def test_training_step_shape_full_size_properties():
     il2.sync()
     assert (Il == Ii).all(dim=1).float().mean().item() >= 0.98
     assert (Dl - (2 - 2 * Di)).abs().max().item() < 1e-5
+
+
+def test_database_builder_normalises_on_the_device_and_round_trips(tmp_path):
+    """§8 f1: rows are L2-normalised while they are added; the saved artefacts keep the .pt layout
+    and reload into an identical database."""
+    from keds_b200 import database as kdb
+
+    g = torch.Generator().manual_seed(77)
+    img = torch.randn(3000, 768, generator=g) * 3.0
+    txt = torch.randn(3000, 768, generator=g) * 0.2
+    names = [f"{i:07d}" for i in range(3000)]
+    kb = kdb.build_knowledge_base(img, txt, names, device=0, normalize=True)
+    ref = img / img.norm(dim=1, keepdim=True)                     # src/main.py:465
+    assert (kb.image_bases - ref).abs().max().item() < 2e-7       # fp32 norm + divide, two roundings
+    assert (kb.image_bases.norm(dim=1) - 1).abs().max().item() < 1e-6
+    q = unit(40, 768, 78)
+    fi, ft = kr.get_retrieved_features(torch.from_numpy(q).cuda(), kb, None, topk=16, use_faiss=False)
+    want = orc.gather(kb.image_bases.numpy(), orc.search(kb.image_bases.numpy(), q, 16)[1])
+    assert np.array_equal(fi.cpu().numpy(), want)
+    paths = kdb.save_artefacts(kb, str(tmp_path))
+    kb2 = kr.KnowledgeBase.load(*paths, device=0)
+    assert torch.equal(kb2.image_bases, kb.image_bases) and kb2.basenames == names
+    D1, I1 = kb.text_index.search(q, 16)
+    D2, I2 = kb2.text_index.search(q, 16)
+    assert np.array_equal(I1, I2) and np.array_equal(D1, D2)

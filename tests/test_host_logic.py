@@ -57,3 +57,25 @@ def test_packed_layout_is_8_byte_aligned():
         total, off_i, d_bytes = packed_layout(nq, k)
         assert off_i % 8 == 0 and total % 8 == 0 and d_bytes == nq * k * 4
         assert total == off_i + nq * k * 8
+
+
+def test_database_sampling_and_pair_loading(tmp_path):
+    """database.py:14-36 + LoadDataBase (src/data.py:636-671): sample names, keep complete pairs."""
+    import torch
+    from keds_b200 import database as kdb
+
+    names = [f"{i:05d}.pt" for i in range(20)]
+    picked = kdb.sample_pairs(names, 8, seed=3)
+    assert len(picked) == 8 and len(set(picked)) == 8 and set(picked) <= set(names)
+    assert picked == kdb.sample_pairs(names, 8, seed=3)
+    assert len(kdb.sample_pairs(names, 100, seed=1)) == 20
+    img_dir, txt_dir = tmp_path / "image_feature_database", tmp_path / "text_feature_database"
+    img_dir.mkdir()
+    txt_dir.mkdir()
+    for i, n in enumerate(picked):
+        torch.save(torch.full((1, 6), float(i)), img_dir / n)          # [1, d] like a CLIP output
+        if i != 2:                                                      # one pair lacks its text half
+            torch.save(torch.full((6,), -float(i)), txt_dir / n)
+    img, txt, kept = kdb.load_pair_folders(str(tmp_path), picked)
+    assert img.shape == (7, 6) and txt.shape == (7, 6) and picked[2] not in kept
+    assert img.dtype == torch.float32 and float(img[0, 0]) == 0.0 and float(txt[1, 0]) == -1.0
