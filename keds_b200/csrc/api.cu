@@ -162,6 +162,7 @@ struct keds_index {
   keds_search_stats stats;
   bool attrs_set = false;
   bool use_pdl = true;
+  int rerank_threads_large = 128;  // block size of the throughput re-rank variant (KEDS_RERANK_THREADS)
   // in-kernel timing of the scoring kernel (bench.py's roofline leg): {min start, max end} ns
   bool timing_on = false;
   DevBuf timing;
@@ -185,6 +186,10 @@ int set_kernel_attrs(keds_index* ix) {
   CK(cudaFuncSetAttribute(k_exact_select, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   const char* no_pdl = getenv("KEDS_NO_PDL");
   ix->use_pdl = !(no_pdl && no_pdl[0] == '1');
+  if (const char* rt = getenv("KEDS_RERANK_THREADS")) {
+    const int v = atoi(rt);
+    if (v == 32 || v == 64 || v == 128 || v == 256) ix->rerank_threads_large = v;
+  }
   ix->attrs_set = true;
   return 0;
 }
@@ -461,7 +466,7 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
                    dim3(RERANK_THREADS), smem, st, rp));
     else
       CKS(launch_k(a->use_pdl, k_select_rerank<1, 4>, dim3(static_cast<unsigned>(nq), n_db),
-                   dim3(RERANK_THREADS), smem, st, rp));
+                   dim3(a->rerank_threads_large), smem, st, rp));
     CKS(prof_mark(a, st, 3));
     a->stats.launches++;
     CK(cudaGetLastError());

@@ -390,29 +390,33 @@ __device__ __forceinline__ float block_max_f(float v, float* red) {
 
 // Radix-select step: given a 256-bin histogram, find the bin b with
 //   count(bins > b) < need <= count(bins >= b)
-// and publish bcast[0] = b, bcast[1] = need - count(bins > b). Needs blockDim.x >= 256 and a
-// uniform call; ends with a __syncthreads so every thread may read bcast.
+// and publish bcast[0] = b, bcast[1] = need - count(bins > b). Warp 0 does the work (lane l owns
+// bins 8l .. 8l+7), so any block size works; uniform call; ends with a __syncthreads so every
+// thread may read bcast.
 __device__ __forceinline__ void block_find_bin(const unsigned int* hist, int need, unsigned int* bcast) {
-  __shared__ unsigned int wtot[8];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  unsigned int h = 0, suf = 0;
-  if (tid < 256) {
-    h = hist[tid];
-    suf = h;  // inclusive suffix sum inside the warp: bins tid .. warp end
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    unsigned int h[8], tot = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      h[i] = hist[lane * 8 + i];
+      tot += h[i];
+    }
+    unsigned int suf = tot;  // inclusive suffix sum over lanes: bins 8*lane .. 255
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const unsigned int up = __shfl_down_sync(0xffffffffu, suf, o);
       if (lane + o < 32) suf += up;
     }
-    if (lane == 0) wtot[warp] = suf;
-  }
-  __syncthreads();
-  if (tid < 256) {
-    for (int w = warp + 1; w < 8; ++w) suf += wtot[w];
-    const unsigned int excl = suf - h;
-    if (static_cast<int>(excl) < need && static_cast<int>(suf) >= need) {
-      bcast[0] = static_cast<unsigned int>(tid);
-      bcast[1] = static_cast<unsigned int>(need) - excl;
+    unsigned int above = suf - tot;  // count of bins owned by higher lanes
+#pragma unroll
+    for (int i = 7; i >= 0; --i) {
+      const unsigned int incl = above + h[i];
+      if (static_cast<int>(above) < need && static_cast<int>(incl) >= need) {
+        bcast[0] = static_cast<unsigned int>(lane * 8 + i);
+        bcast[1] = static_cast<unsigned int>(need) - above;
+      }
+      above = incl;
     }
   }
   __syncthreads();

@@ -150,12 +150,12 @@ k_select_rerank(const RerankParams p) {
   if (n >= p.k) {
     if (p.S >= p.k) {
       // t0 = k-th largest slice maximum (each of the k best slices holds a row at least that good)
-      if (tid < p.S) {
-        const unsigned int mine = smax[tid];
+      for (int s = tid; s < p.S; s += blockDim.x) {
+        const unsigned int mine = smax[s];
         int rank = 0;
         for (int u = 0; u < p.S; ++u) {
           const unsigned int o = smax[u];
-          rank += (o > mine) || (o == mine && u < tid);
+          rank += (o > mine) || (o == mine && u < s);
         }
         if (rank == p.k - 1) bcast[2] = mine;
       }
@@ -198,6 +198,32 @@ k_select_rerank(const RerankParams p) {
         }
       } else {
         radix = true;
+      }
+    } else if (slots <= 1024) {
+      // fewer slices than k: no slice-maximum bound, but the candidate set is small -- find a_(k)
+      // by rank counting over all of it (padding keys are 0 and never counted as >= a valid key
+      // unless k exceeds the valid count, which n >= k excludes)
+      for (int i = tid; i < slots; i += blockDim.x) {
+        if (ids[i] == PAD_ID) continue;
+        const unsigned int mine = keys[i];
+        int gt = 0, ge = 0;
+        for (int j = 0; j < slots; ++j) {
+          const unsigned int o = keys[j];
+          const bool valid = ids[j] != PAD_ID;
+          gt += valid && o > mine;
+          ge += valid && o >= mine;
+        }
+        if (gt < p.k && ge >= p.k) bcast[3] = mine;
+      }
+      __syncthreads();
+      kth = bcast[3];
+      tau = key_to_f32(kth) - 2.f * eps;
+      for (int i = tid; i < slots; i += blockDim.x) {
+        const unsigned int id = ids[i];
+        if (id != PAD_ID && key_to_f32(keys[i]) >= tau) {
+          const int pos = atomicAdd(&counters[1], 1);
+          if (pos < R_MAX) sel_id[pos] = id;
+        }
       }
     } else {
       radix = true;

@@ -80,6 +80,32 @@ def test_search_matches_oracle(n, b, d, k, metric):
     check(ix, db, q, k, metric, _capi.SEARCH_EXACT_ONLY)
 
 
+def test_random_shapes_property():
+    """Seeded sweep over ragged shapes: N around tile / slice boundaries, B around the 128-query
+    tile, d with and without 4- / 64-alignment, k from 1 to beyond the candidate capacity, both
+    metrics -- every selection path of the re-rank kernel (slice-maximum, direct, radix, n < k)
+    and the exact-only planner branch must agree with the oracle."""
+    rng = np.random.default_rng(2024)
+    dims = [8, 50, 64, 100, 128, 200, 768]
+    for trial in range(40):
+        n = int(rng.choice([1, 7, 255, 256, 257, 511, 1000, 1536, 4097, 9000, 30001]))
+        b = int(rng.choice([1, 2, 31, 127, 128, 129, 300]))
+        d = int(rng.choice(dims))
+        k = int(rng.choice([1, 2, 5, 16, 17, 33, 64, 100, 257, 300]))
+        metric = "l2" if trial % 2 else "ip"
+        db = unit(n, d, 5000 + trial)
+        if trial % 3 == 0:   # non-unit rows
+            db = db * rng.uniform(0.5, 2.0, size=(n, 1)).astype(np.float32)
+        q = unit(b, d, 6000 + trial) * np.float32(rng.uniform(0.5, 3.0))
+        ix = build(db, metric)
+        D, I = ix.search(q, k)
+        Dr, Ir = orc.search(db, q, k, metric)
+        # distances scale with |q|^2 |x|^2: scale the absolute tolerance accordingly
+        scale = float(np.abs(Dr[np.isfinite(Dr) & (np.abs(Dr) < 1e30)]).max()) if n else 1.0
+        c = orc.compare_topk(Dr, Ir, D, I, db, q, metric, TIE_GAP * max(1.0, scale), D_TOL * max(1.0, scale))
+        assert c["ok"], (trial, n, b, d, k, metric, c, ix.last_stats())
+
+
 def test_config1_4096_queries_vs_50k_rows():
     """BASELINE.json configs[0]: 4,096 unit-norm queries vs 50k x 768, k = 16."""
     db, q = unit(50000, 768, 1000), unit(4096, 768, 1001)
