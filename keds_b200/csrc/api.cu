@@ -140,7 +140,8 @@ constexpr size_t TIMING_PAIRS = 5;  // k_prep_rows, k_score_topk, k_select_reran
 
 struct Plan {
   int exact_only = 0;
-  int S = 1, n_qt = 1, n_items = 0, grid = 0;
+  bool pair = false;  // CTA-pair scoring kernel (two query tiles per work item)
+  int S = 1, n_qt = 1, n_qg = 1, n_items = 0, grid = 0;
 };
 
 }  // namespace
@@ -151,8 +152,10 @@ struct keds_index {
   int64_t id_offset = 0;
   float eps_scale = 1.f;
   DevBuf x_f32, x_bf16, bias, dbstat;
-  CUtensorMap tm_x;
+  CUtensorMap tm_x;   // {64 x 256}-row boxes (one CTA per tile)
+  CUtensorMap tm_xh;  // {64 x 128}-row boxes (CTA pair: half a tile each)
   bool tm_x_ok = false;
+  bool use_pair = true;
   // per-call scratch (one search in flight per handle)
   DevBuf q_f32, q_bf16, qstat, cand, cand_cnt, cand_theta, flagged[2], ctrl, exact_scratch;
   DevBuf D_stage[2], I_stage[2];
@@ -178,8 +181,12 @@ namespace {
 
 int set_kernel_attrs(keds_index* ix) {
   if (ix->attrs_set) return 0;
-  CK(cudaFuncSetAttribute(k_score_topk, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  CK(cudaFuncSetAttribute(k_score_topk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)SCORE_SMEM_BYTES));
+  CK(cudaFuncSetAttribute(k_score_topk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)SCORE_PAIR_SMEM_BYTES));
+  const char* no_pair = getenv("KEDS_NO_PAIR");
+  ix->use_pair = !(no_pair && no_pair[0] == '1');
   CK(cudaFuncSetAttribute(k_select_rerank<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaFuncSetAttribute(k_select_rerank<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaFuncSetAttribute(k_exact_scores, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
@@ -197,22 +204,40 @@ int set_kernel_attrs(keds_index* ix) {
 // Launch on `st`; with pdl the kernel may be scheduled while its predecessor in the stream is
 // still draining (programmatic dependent launch) -- every kernel of the search chain calls
 // griddep_wait() before it touches anything an earlier kernel wrote.
+// cluster > 1: thread-block cluster of that many CTAs along x (the CTA-pair scoring kernel).
 template <typename... KArgs, typename... Args>
-int launch_k(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
-             Args&&... args) {
+int launch_kc(bool pdl, int cluster, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+              cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
   cfg.gridDim = grid;
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (cluster > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = static_cast<unsigned>(cluster);
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 1 : 0;
+  cfg.numAttrs = na;
   CK(cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...));
   return 0;
+}
+
+template <typename... KArgs, typename... Args>
+int launch_k(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+             Args&&... args) {
+  return launch_kc(pdl, 1, kernel, grid, block, smem, st, std::forward<Args>(args)...);
 }
 
 // Pick the number of row slices: enough that no slice is expected to hold more than a third of
@@ -227,9 +252,14 @@ Plan make_plan(const keds_index* ix, int n_db, int64_t nq, int k, int64_t n_min,
   // the certificate to pass, theta must sit well below the k-th best score overall, i.e. the
   // top-k must be spread over many slices (expected share per slice <= LKEEP / 6)
   const int S_sel = std::max(1, (6 * k + LKEEP - 1) / LKEEP);
-  const int groups = n_db * pl.n_qt;
+  // more than one query tile: CTA pairs share each row tile (two query tiles per work item)
+  pl.pair = ix->use_pair && pl.n_qt >= 2 && ix->num_sms >= 2;
+  pl.n_qg = pl.pair ? (pl.n_qt + 1) / 2 : pl.n_qt;
+  const int units = pl.pair ? ix->num_sms / 2 : ix->num_sms;
+  const int groups = n_db * pl.n_qg;
   int S_hi = std::min(T_min, S_MAX);
-  const long long by_mem = static_cast<long long>(CAND_BUDGET / (size_t(LKEEP) * BM * 8)) / groups;
+  const long long by_mem =
+      static_cast<long long>(CAND_BUDGET / (size_t(LKEEP) * BM * 8)) / (static_cast<long long>(n_db) * pl.n_qt);
   S_hi = static_cast<int>(std::min<long long>(S_hi, by_mem));
   if ((flags & KEDS_SEARCH_EXACT_ONLY) || S_hi < S_sel || k > R_MAX / 2) {
     pl.exact_only = 1;
@@ -238,7 +268,7 @@ Plan make_plan(const keds_index* ix, int n_db, int64_t nq, int k, int64_t n_min,
   double best = 1e300;
   for (int S = S_sel; S <= S_hi; ++S) {
     const long long items = static_cast<long long>(groups) * S;
-    const long long G = std::min<long long>(items, ix->num_sms);
+    const long long G = std::min<long long>(items, units);
     const long long per_cta = (items + G - 1) / G;
     const double cost = static_cast<double>(per_cta) * ((T_max + S - 1) / S) + 0.35 * per_cta;
     if (cost < best - 1e-9) {
@@ -247,7 +277,7 @@ Plan make_plan(const keds_index* ix, int n_db, int64_t nq, int k, int64_t n_min,
     }
   }
   pl.n_items = groups * pl.S;
-  pl.grid = std::min(pl.n_items, ix->num_sms);
+  pl.grid = std::min(pl.n_items, units) * (pl.pair ? 2 : 1);
   return pl;
 }
 
@@ -394,7 +424,8 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
                    a->ctrl.as<unsigned int>(), CTRL_WORDS, tchain));
       a->stats.launches++;
     }
-    const size_t items = static_cast<size_t>(pl.n_items);
+    // candidate lines are indexed by (db, slice, query tile) whatever the work-item grouping
+    const size_t items = static_cast<size_t>(n_db) * pl.S * pl.n_qt;
     CKS(a->cand.ensure(items * LKEEP * BM * 8));
     CKS(a->cand_cnt.ensure(items * BM * 4));
     CKS(a->cand_theta.ensure(items * BM * 4));
@@ -403,6 +434,7 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
     memset(&sp, 0, sizeof sp);
     sp.n_db = n_db;
     sp.n_qt = pl.n_qt;
+    sp.n_qg = pl.n_qg;
     sp.S = pl.S;
     sp.n_items = pl.n_items;
     sp.kblocks = a->d_pad / BK;
@@ -420,8 +452,12 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
     sp.ld_dump = ld_dump;
     sp.timing = tchain ? tchain + 2 : nullptr;
     CKS(prof_mark(a, st, 1));
-    CKS(launch_k(a->use_pdl, k_score_topk, dim3(pl.grid), dim3(SCORE_THREADS), SCORE_SMEM_BYTES, st, a->tm_q,
-                 ix[0]->tm_x, n_db > 1 ? ix[1]->tm_x : ix[0]->tm_x, sp));
+    if (pl.pair)
+      CKS(launch_kc(a->use_pdl, 2, k_score_topk<true>, dim3(pl.grid), dim3(SCORE_THREADS), SCORE_PAIR_SMEM_BYTES,
+                    st, a->tm_q, ix[0]->tm_xh, n_db > 1 ? ix[1]->tm_xh : ix[0]->tm_xh, sp));
+    else
+      CKS(launch_k(a->use_pdl, k_score_topk<false>, dim3(pl.grid), dim3(SCORE_THREADS), SCORE_SMEM_BYTES, st,
+                   a->tm_q, ix[0]->tm_x, n_db > 1 ? ix[1]->tm_x : ix[0]->tm_x, sp));
     CKS(prof_mark(a, st, 2));
     a->stats.launches++;
     CK(cudaGetLastError());
@@ -702,6 +738,7 @@ int keds_index_add_ex(keds_index_t* ix, const float* x, int64_t n, uint32_t flag
   CK(cudaDeviceSynchronize());
   ix->n = n1;
   CKS(encode_rows_map(&ix->tm_x, ix->x_bf16.p, n1, ix->d_pad, BN));
+  CKS(encode_rows_map(&ix->tm_xh, ix->x_bf16.p, n1, ix->d_pad, BN / 2));
   ix->tm_x_ok = true;
   return 0;
 }

@@ -2,15 +2,23 @@
 //
 // Replaces the "SGEMM tile -> HBM -> k-select" pair inside the Faiss GPU flat index that KEDs
 // calls at src/trainer.py:213,221,271 and src/eval_utils.py:169,177. The [queries x rows] score
-// matrix lives only in TMEM; what reaches HBM is, per (row slice, query), a short list of
+// matrix lives only in TMEM; what reaches HBM is, per (row slice, query), one 128-byte line of
 // candidate (approx score, row id) pairs plus the slice's drop threshold.
 //
-//   warp 0        TMA producer: per k-block one {64 x 128} query box + one {64 x 256} row box
+//   warp 0        TMA producer: per k-block one {64 x 128} query box + one row box
 //   warp 1        tcgen05.mma issuer (one lane), owns the TMEM allocation
 //   warps 2..5    epilogue: TMEM lane == query, so one thread owns one query's scores
 //
 // Tile: M = 128 queries (TMEM lanes) x N = 256 DB rows (TMEM columns), K streamed in 64-wide
 // k-blocks (one 128-byte swizzle row). Two 256-column accumulators double-buffer MMA vs epilogue.
+//
+// Two variants of one kernel:
+//   kPair = false  one CTA per tile (cta_group::1). Used for batches of <= 128 queries, where the
+//                  kernel is HBM-bound and every SM streams its own row slice.
+//   kPair = true   a cluster of two CTAs shares every 256-row tile (cta_group::2, M = 256): each
+//                  CTA holds its own 128 queries and loads HALF of the row tile, the leader CTA
+//                  issues one MMA for both. Per CTA and k-block 32 KB cross L2->SM instead of 48 KB,
+//                  which is what bounds the single-CTA variant once the batch is compute-bound.
 #pragma once
 #include "ptx.cuh"
 
@@ -20,38 +28,43 @@ constexpr int BM = 128;
 constexpr int BN = 256;
 constexpr int BK = 64;
 constexpr int UK = 16;
-constexpr int NSTAGE = 3;
 constexpr int LKEEP = 16;   // a compaction keeps scores above the LKEEP-th best seen
 constexpr int CAP = 64;     // candidate slots per (item, query)
 constexpr int CHUNK = 32;   // TMEM columns per tcgen05.ld
 constexpr int SCORE_THREADS = 192;
 constexpr uint32_t Q_STAGE_BYTES = BM * BK * 2;
-constexpr uint32_t X_STAGE_BYTES = BN * BK * 2;
-constexpr uint32_t STAGE_BYTES = Q_STAGE_BYTES + X_STAGE_BYTES;
 constexpr uint32_t CAND_WARP_BYTES = CAP * 32 * 8;
 constexpr uint32_t TMEM_COLS = 512;
 
-// dynamic shared memory map (offsets from a 1024-aligned base)
-constexpr uint32_t SM_STAGES = 0;
-constexpr uint32_t SM_CAND = SM_STAGES + NSTAGE * STAGE_BYTES;
-constexpr uint32_t SM_BIAS = SM_CAND + 4 * CAND_WARP_BYTES;
-constexpr uint32_t SM_BARS = SM_BIAS + 2 * BN * 4;
-constexpr uint32_t SM_END = SM_BARS + 128;
-constexpr uint32_t SCORE_SMEM_BYTES = SM_END + 1024;  // + alignment slack
+template <bool kPair>
+struct ScoreCfg {
+  static constexpr int kStages = kPair ? 4 : 3;
+  static constexpr int kRowsPerCta = kPair ? BN / 2 : BN;           // row-tile rows this CTA loads
+  static constexpr uint32_t kXBytes = kRowsPerCta * BK * 2;
+  static constexpr uint32_t kStageBytes = Q_STAGE_BYTES + kXBytes;  // 48 KB / 32 KB
+  // dynamic shared memory map (offsets from a 1024-aligned base)
+  static constexpr uint32_t kOffCand = kStages * kStageBytes;
+  static constexpr uint32_t kOffBias = kOffCand + 4 * CAND_WARP_BYTES;
+  static constexpr uint32_t kOffBars = kOffBias + 2 * BN * 4;
+  static constexpr uint32_t kSmemBytes = kOffBars + 128 + 1024;     // + alignment slack
+};
+constexpr uint32_t SCORE_SMEM_BYTES = ScoreCfg<false>::kSmemBytes;
+constexpr uint32_t SCORE_PAIR_SMEM_BYTES = ScoreCfg<true>::kSmemBytes;
 
 struct ScoreParams {
   int n_db;          // 1 or 2 databases scored against the same queries
   int n_qt;          // query tiles of BM
+  int n_qg;          // query groups per (db, slice): n_qt (single CTA) or ceil(n_qt / 2) (pair)
   int S;             // row slices per (db, query tile)
-  int n_items;       // n_db * S * n_qt ; item = ((db * S) + s) * n_qt + qt
+  int n_items;       // n_db * S * n_qg ; item = ((db * S) + s) * n_qg + qg
   int kblocks;       // d_pad / BK
   int nq;            // live queries
   int n_rows[2];     // rows per database
   int n_tiles[2];    // ceil(n_rows / BN)
   const float* bias[2];  // nullable; additive per-row bias padded with -inf to n_tiles * BN
-  uint2* cand;       // [n_items][BM][LKEEP] {approx score bits, row id}, padded {-inf, ~0}
-  int* cand_cnt;     // [n_items][BM]
-  float* cand_theta; // [n_items][BM]  everything the slice dropped scored <= theta
+  uint2* cand;       // [n_db * S * n_qt][BM][LKEEP] {approx score bits, row id}, padded {-inf, ~0}
+  int* cand_cnt;     // [..][BM]
+  float* cand_theta; // [..][BM]  everything the slice dropped scored <= theta
   uint32_t* err;     // device error word (0 = ok)
   float* dump;       // debug: full approx scores [n_db][nq][ld_dump], or nullptr
   long long ld_dump;
@@ -59,13 +72,13 @@ struct ScoreParams {
 };
 
 struct ItemCoord {
-  int db, s, qt, t0, t1;
+  int db, s, qg, t0, t1;
 };
 
 __device__ __forceinline__ ItemCoord decode_item(const ScoreParams& p, int item) {
   ItemCoord c;
-  c.qt = item % p.n_qt;
-  const int t = item / p.n_qt;
+  c.qg = item % p.n_qg;
+  const int t = item / p.n_qg;
   c.s = t % p.S;
   c.db = t / p.S;
   const long long T = p.n_tiles[c.db];
@@ -132,23 +145,29 @@ __device__ __noinline__ CandState compact_candidates(uint32_t slot0, int cnt, fl
   return r;
 }
 
+template <bool kPair>
 __global__ void __launch_bounds__(SCORE_THREADS, 1)
 k_score_topk(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_x0,
              const __grid_constant__ CUtensorMap tm_x1, const ScoreParams p) {
+  using Cfg = ScoreCfg<kPair>;
+  constexpr int NSTAGE = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (sbase - smem_u32(smem_raw));
 
-  const uint32_t bars = sbase + SM_BARS;
+  const uint32_t bars = sbase + Cfg::kOffBars;
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (NSTAGE + s); };
   auto tfull_bar = [&](int a) { return bars + 8u * (2 * NSTAGE + a); };
   auto tempty_bar = [&](int a) { return bars + 8u * (2 * NSTAGE + 2 + a); };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + SM_BARS + 96);
-  volatile uint32_t* dead = reinterpret_cast<volatile uint32_t*>(gbase + SM_BARS + 100);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + Cfg::kOffBars + 104);
+  volatile uint32_t* dead = reinterpret_cast<volatile uint32_t*>(gbase + Cfg::kOffBars + 108);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t crank = kPair ? cluster_ctarank() : 0u;   // 0 = leader of the pair
+  const int unit = kPair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int n_units = kPair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
   if (threadIdx.x == 0) {
     prefetch_tensormap(&tm_q);
@@ -160,23 +179,28 @@ k_score_topk(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);
+      mbar_init(tempty_bar(a), kPair ? 8 : 4);  // pair: the leader collects both CTAs' epilogue warps
     }
     *dead = 0;
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (kPair) {
+      tmem_alloc_2sm(smem_u32(const_cast<uint32_t*>(tmem_slot)), TMEM_COLS);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kPair) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   // Programmatic dependent launch: everything above overlapped the tail of the previous kernel
   // (k_prep_rows); from here on its outputs (bf16 queries) are needed. Let the next kernel
-  // (k_select_rerank) start its own prologue as soon as SMs free up.
+  // (k_select_rerank) be scheduled as soon as SMs free up.
   griddep_wait();
   griddep_launch_dependents();
   const unsigned long long t_start = ktimer_begin(p.timing);
@@ -186,18 +210,27 @@ k_score_topk(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      for (int item = unit; item < p.n_items; item += n_units) {
         const ItemCoord c = decode_item(p, item);
         const CUtensorMap* tmx = c.db == 0 ? &tm_x0 : &tm_x1;
+        const int qt = kPair ? c.qg * 2 + static_cast<int>(crank) : c.qg;
         for (int tile = c.t0; tile < c.t1; ++tile) {
           for (int kb = 0; kb < p.kblocks; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1u, dead, p.err, 0x100u + stage);
-            const uint32_t sq = sbase + SM_STAGES + stage * STAGE_BYTES;
+            const uint32_t sq = sbase + stage * Cfg::kStageBytes;
             const uint32_t sx = sq + Q_STAGE_BYTES;
-            mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
-            tma_load_2d(sq, &tm_q, full_bar(stage), kb * BK, c.qt * BM, kEvictLast);
-            tma_load_2d(sx, tmx, full_bar(stage), kb * BK, tile * BN,
-                        p.n_qt > 1 ? kEvictNormal : kEvictFirst);
+            if constexpr (kPair) {
+              // the leader's barrier counts the bytes of both CTAs; only the leader arms it
+              if (crank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
+              tma_load_2d_2sm(sq, &tm_q, full_bar(stage), kb * BK, qt * BM, kEvictLast);
+              tma_load_2d_2sm(sx, tmx, full_bar(stage), kb * BK,
+                              tile * BN + static_cast<int>(crank) * Cfg::kRowsPerCta, kEvictNormal);
+            } else {
+              mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
+              tma_load_2d(sq, &tm_q, full_bar(stage), kb * BK, qt * BM, kEvictLast);
+              tma_load_2d(sx, tmx, full_bar(stage), kb * BK, tile * BN,
+                          p.n_qt > 1 ? kEvictNormal : kEvictFirst);
+            }
             if (++stage == NSTAGE) {
               stage = 0;
               phase ^= 1u;
@@ -207,14 +240,14 @@ k_score_topk(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = idesc_bf16_f32(BM, BN);
+    // ------------------------------------------------------------ MMA issuer (pair: leader only)
+    if (lane == 0 && crank == 0) {
+      constexpr uint32_t idesc = idesc_bf16_f32(kPair ? 2 * BM : BM, BN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      for (int item = unit; item < p.n_items; item += n_units) {
         const ItemCoord c = decode_item(p, item);
         for (int tile = c.t0; tile < c.t1; ++tile) {
           mbar_wait(tempty_bar(acc), acc_phase ^ 1u, dead, p.err, 0x200u + acc);
@@ -223,21 +256,24 @@ k_score_topk(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
           for (int kb = 0; kb < p.kblocks; ++kb) {
             mbar_wait(full_bar(stage), phase, dead, p.err, 0x300u + stage);
             tc_fence_after();
-            const uint32_t sq = sbase + SM_STAGES + stage * STAGE_BYTES;
+            const uint32_t sq = sbase + stage * Cfg::kStageBytes;
             const uint64_t adesc = smem_desc_sw128(sq);
             const uint64_t bdesc = smem_desc_sw128(sq + Q_STAGE_BYTES);
 #pragma unroll
             for (int k = 0; k < BK / UK; ++k) {
               // +32 bytes per K=16 step inside the 128-byte swizzle row: +2 in 16-byte units
-              umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              if constexpr (kPair)
+                umma_bf16_2sm(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              else
+                umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
             }
-            umma_commit(empty_bar(stage));
+            if constexpr (kPair) umma_commit_2sm(empty_bar(stage), 0x3); else umma_commit(empty_bar(stage));
             if (++stage == NSTAGE) {
               stage = 0;
               phase ^= 1u;
             }
           }
-          umma_commit(tfull_bar(acc));
+          if constexpr (kPair) umma_commit_2sm(tfull_bar(acc), 0x3); else umma_commit(tfull_bar(acc));
           acc ^= 1;
           if (acc == 0) acc_phase ^= 1u;
         }
@@ -247,15 +283,16 @@ k_score_topk(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
     // ------------------------------------------------------------ epilogue (lane == query)
     const int quad = warp & 3;                // TMEM lane quadrant this warp may read
     const int q_local = quad * 32 + lane;
-    const uint32_t wbuf = sbase + SM_CAND + static_cast<uint32_t>(warp - 2) * CAND_WARP_BYTES;
+    const uint32_t wbuf = sbase + Cfg::kOffCand + static_cast<uint32_t>(warp - 2) * CAND_WARP_BYTES;
     const uint32_t slot0 = wbuf + lane * 8;   // entry e of this lane lives at slot0 + e * 256
-    float* sbias = reinterpret_cast<float*>(gbase + SM_BIAS);
+    float* sbias = reinterpret_cast<float*>(gbase + Cfg::kOffBias);
     const int et = threadIdx.x - 64;          // 0..127 among epilogue threads
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+    for (int item = unit; item < p.n_items; item += n_units) {
       const ItemCoord c = decode_item(p, item);
-      const int q_glob = c.qt * BM + q_local;
+      const int qt = kPair ? c.qg * 2 + static_cast<int>(crank) : c.qg;
+      const int q_glob = qt * BM + q_local;
       const bool active = q_glob < p.nq;
       float theta = active ? -INFINITY : INFINITY;
       int cnt = 0;
@@ -315,43 +352,48 @@ k_score_topk(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
             theta = st.theta;
           }
         }
-        // accumulator drained: hand the TMEM buffer back to the MMA warp
+        // accumulator drained: hand the TMEM buffer back to the MMA warp (pair: of the leader CTA)
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        if (lane == 0) {
+          if constexpr (kPair) mbar_arrive_cluster(tempty_bar(acc), 0); else mbar_arrive(tempty_bar(acc));
+        }
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
       // Final compaction: at most LKEEP - 1 entries survive (those strictly above the slice's
-      // LKEEP-th best, which becomes theta). They leave as one 128-byte line per (item, query):
-      // [item][query][LKEEP] {score bits, row id}, padded with {-inf, ~0}; the re-rank kernel
-      // reads a slice with a single coalesced half-warp load.
+      // LKEEP-th best, which becomes theta). They leave as one 128-byte line per (slice, query):
+      // [(db, s, qt)][query][LKEEP] {score bits, row id}, padded with {-inf, ~0}; the re-rank
+      // kernel reads a slice with a single coalesced half-warp load.
       if (__any_sync(0xffffffffu, cnt >= LKEEP)) {
         const CandState st = compact_candidates(slot0, cnt, theta);
         cnt = st.cnt;
         theta = st.theta;
       }
-      uint2* cbase = p.cand + (static_cast<long long>(item) * BM + q_local) * LKEEP;
+      if (!kPair || qt < p.n_qt) {
+        const long long oitem = (static_cast<long long>(c.db) * p.S + c.s) * p.n_qt + qt;
+        uint2* cbase = p.cand + (oitem * BM + q_local) * LKEEP;
 #pragma unroll
-      for (int e = 0; e < LKEEP; e += 2) {
-        uint2 a = make_uint2(0xff800000u, 0xffffffffu), b = a;
-        if (e < cnt) a = lds64(slot0 + e * 256);
-        if (e + 1 < cnt) b = lds64(slot0 + (e + 1) * 256);
-        *reinterpret_cast<uint4*>(cbase + e) = make_uint4(a.x, a.y, b.x, b.y);
+        for (int e = 0; e < LKEEP; e += 2) {
+          uint2 a = make_uint2(0xff800000u, 0xffffffffu), b = a;
+          if (e < cnt) a = lds64(slot0 + e * 256);
+          if (e + 1 < cnt) b = lds64(slot0 + (e + 1) * 256);
+          *reinterpret_cast<uint4*>(cbase + e) = make_uint4(a.x, a.y, b.x, b.y);
+        }
+        p.cand_cnt[oitem * BM + q_local] = cnt;
+        p.cand_theta[oitem * BM + q_local] = theta;
       }
-      p.cand_cnt[static_cast<long long>(item) * BM + q_local] = cnt;
-      p.cand_theta[static_cast<long long>(item) * BM + q_local] = theta;
       __syncwarp();
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kPair) cluster_sync_all(); else __syncthreads();
   ktimer_end(p.timing, t_start);  // kernel duration without stream events
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if constexpr (kPair) tmem_dealloc_2sm(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 

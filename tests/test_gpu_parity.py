@@ -242,6 +242,10 @@ def test_fused_two_database_search_equals_two_searches():
     D2, I2 = ib.search(q, 16)
     assert np.array_equal(Ia, I1) and np.array_equal(Ib, I2)
     assert np.array_equal(Da, D1) and np.array_equal(Db, D2)
+    q3 = unit(300, 768, 55)     # three query tiles: the CTA-pair kernel with a dangling last tile
+    (Da3, Ia3), (Db3, Ib3) = search2(ia, ib, q3, 16)
+    assert orc.compare_topk(*orc.search(a, q3, 16), Da3, Ia3, a, q3)["ok"]
+    assert orc.compare_topk(*orc.search(b, q3, 16), Db3, Ib3, b, q3)["ok"]
     a2 = unit(12345, 768, 54)   # databases of different sizes
     ia2 = build(a2, "ip")
     (Da, Ia), (Db, Ib) = search2(ia2, ib, q, 16)
