@@ -1009,9 +1009,9 @@ int keds_gallery_rank(const float* Q, int64_t nq, const float* G, int64_t ng, in
   if (!Q || !G || !target || !rank_out || nq < 0 || ng <= 0 || d <= 0)
     return fail(KEDS_ERR_ARG, "gallery_rank: bad argument");
   if (nq == 0) return 0;
-  const size_t smem = static_cast<size_t>((d + 3) & ~3) * 4;
+  const size_t smem = static_cast<size_t>((d + 3) & ~3) * 4 * 8;  // 8 queries per block
   if (smem > 48 * 1024) return fail(KEDS_ERR_ARG, "gallery_rank: d too large");
-  k_gallery_rank<<<static_cast<unsigned>(nq), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+  k_gallery_rank<<<static_cast<unsigned>((nq + 7) / 8), 256, smem, static_cast<cudaStream_t>(stream)>>>(
       Q, nq, G, ng, d, reinterpret_cast<const long long*>(target),
       reinterpret_cast<const long long*>(exclude), reinterpret_cast<long long*>(rank_out));
   CK(cudaGetLastError());

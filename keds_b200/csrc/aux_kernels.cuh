@@ -570,26 +570,78 @@ __global__ void __launch_bounds__(256)
 k_gallery_rank(const float* __restrict__ Q, long long nq, const float* __restrict__ G, long long ng,
                int d, const long long* __restrict__ target, const long long* __restrict__ exclude,
                long long* __restrict__ rank_out) {
+  // GR_Q queries per block share every gallery row a warp reads (the row is fetched once for
+  // all of them); per (query,row) the arithmetic is that of warp_exact_score.
+  constexpr int GR_Q = 8;
   extern __shared__ uint8_t gr_smem[];
-  float* qv = reinterpret_cast<float*>(gr_smem);
-  __shared__ int total;
-  const long long q = blockIdx.x;
+  const int dq = (d + 3) & ~3;
+  float* qv = reinterpret_cast<float*>(gr_smem);  // [GR_Q][dq]
+  __shared__ int total[GR_Q];
+  __shared__ float s_target[GR_Q];
+  const long long q0 = static_cast<long long>(blockIdx.x) * GR_Q;
+  const int nqb = static_cast<int>(min(static_cast<long long>(GR_Q), nq - q0));
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int c = threadIdx.x; c < d; c += blockDim.x) qv[c] = Q[q * d + c];
-  if (threadIdx.x == 0) total = 0;
-  __syncthreads();
-  const long long t = target[q];
-  const long long ex = exclude ? exclude[q] : -1;
-  const float st = warp_exact_score(qv, G + t * d, d, METRIC_IP, lane);
-  int cnt = 0;
-  for (long long g = warp; g < ng; g += nw) {
-    if (g == t || g == ex) continue;
-    const float s = warp_exact_score(qv, G + g * d, d, METRIC_IP, lane);
-    cnt += (s > st) || (s == st && g < t);
+  for (int i = threadIdx.x; i < GR_Q * dq; i += blockDim.x) {
+    const int qi = i / dq, c = i % dq;
+    qv[i] = (qi < nqb && c < d) ? Q[(q0 + qi) * d + c] : 0.f;
   }
-  if (lane == 0) atomicAdd(&total, cnt);
+  if (threadIdx.x < GR_Q) total[threadIdx.x] = 0;
   __syncthreads();
-  if (threadIdx.x == 0) rank_out[q] = total;
+  for (int qi = warp; qi < nqb; qi += nw) {
+    const float st = warp_exact_score(qv + qi * dq, G + target[q0 + qi] * d, d, METRIC_IP, lane);
+    if (lane == 0) s_target[qi] = st;
+  }
+  __syncthreads();
+  long long tg[GR_Q], ex[GR_Q];
+  float st[GR_Q];
+  int cnt[GR_Q];
+#pragma unroll
+  for (int i = 0; i < GR_Q; ++i) {
+    tg[i] = i < nqb ? target[q0 + i] : -1;
+    ex[i] = (i < nqb && exclude) ? exclude[q0 + i] : -1;
+    st[i] = i < nqb ? s_target[i] : 0.f;
+    cnt[i] = 0;
+  }
+  const bool vec = (d & 3) == 0 && (reinterpret_cast<uintptr_t>(G) & 15) == 0;
+  for (long long g = warp; g < ng; g += nw) {
+    const float* xr = G + g * d;
+    float acc[GR_Q];
+#pragma unroll
+    for (int i = 0; i < GR_Q; ++i) acc[i] = 0.f;
+    if (vec) {
+      const float4* x4 = reinterpret_cast<const float4*>(xr);
+      const int d4 = d >> 2;
+      for (int c = lane; c < d4; c += 32) {
+        const float4 a = __ldg(x4 + c);
+#pragma unroll
+        for (int i = 0; i < GR_Q; ++i) {
+          const float4 b = reinterpret_cast<const float4*>(qv + i * dq)[c];
+          acc[i] = fmaf(a.x, b.x, acc[i]);
+          acc[i] = fmaf(a.y, b.y, acc[i]);
+          acc[i] = fmaf(a.z, b.z, acc[i]);
+          acc[i] = fmaf(a.w, b.w, acc[i]);
+        }
+      }
+    } else {
+      for (int c = lane; c < d; c += 32) {
+        const float a = __ldg(xr + c);
+#pragma unroll
+        for (int i = 0; i < GR_Q; ++i) acc[i] = fmaf(a, qv[i * dq + c], acc[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < GR_Q; ++i) {
+      const float s = warp_sum(acc[i]);
+      if (i < nqb && g != tg[i] && g != ex[i]) cnt[i] += (s > st[i]) || (s == st[i] && g < tg[i]);
+    }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < GR_Q; ++i)
+      if (i < nqb) atomicAdd(&total[i], cnt[i]);
+  }
+  __syncthreads();
+  if (threadIdx.x < nqb) rank_out[q0 + threadIdx.x] = total[threadIdx.x];
 }
 
 // hits[q][i] = #{ j < ks[i] : labels[I[q][j]] == qlabel[q] }   (ImageNet-domain R@k / P@k,
