@@ -163,6 +163,12 @@ def cpu_port_qps(db_img, db_txt, q, reps, threads=None):
 def run_reference(args, rank, world):
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 for multi-process launches: the CPU arm takes every core
+    # this process may run on
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except Exception:
+        torch.set_num_threads(max(1, os.cpu_count() or 1))
     n = args.rows
     torch.manual_seed(0)
     g = torch.Generator().manual_seed(SEED_IMG)
@@ -217,8 +223,9 @@ def run_ours(args, rank, world, local):
     ib = GpuIndexFlat(DIM, METRIC_INNER_PRODUCT, local)
     ia.add(img)
     ib.add(txt)
-    db_img_host = img.cpu().numpy() if (rank == 0 and not args.no_cpu_baseline) else None
-    db_txt_host = txt.cpu().numpy() if (rank == 0 and not args.no_cpu_baseline) else None
+    want_cpu = rank == 0 and world == 1 and not args.no_cpu_baseline  # CPU baseline: rank 0 at N = 1 only
+    db_img_host = img.cpu().numpy() if want_cpu else None
+    db_txt_host = txt.cpu().numpy() if want_cpu else None
     del img, txt
     torch.cuda.empty_cache()
 
@@ -393,6 +400,10 @@ def run_ours(args, rank, world, local):
     if sharded is not None:
         line["sharded"] = sharded
     if not args.no_cpu_baseline and db_img_host is not None:
+        try:
+            torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+        except Exception:
+            pass
         q = make_queries(BATCH, DIM, SEED_Q).numpy()
         cpu_port_qps(db_img_host[:50_000], db_txt_host[:50_000], q, 1)
         t0 = time.perf_counter()
