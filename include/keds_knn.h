@@ -145,6 +145,23 @@ int keds_topk_merge_strided(const float* D_parts, const int64_t* I_parts, int64_
                             int64_t stride_i, int parts, int64_t nq, int k, int metric, float* D,
                             int64_t* I, void* cuda_stream);
 
+/* Row-shard exchange over NVLink peer memory (no collective call in the step). The buffers are
+ * symmetric allocations mapped into every rank of the box; the library only sees raw pointers.
+ *   keds_p2p_push       copy this rank's block (src, bytes % 16 == 0) into peer_dst[r] for every
+ *                       r != my_rank with P2P stores, then publish `epoch` (system-scope release)
+ *                       to peer_flag[r]. peer_dst / peer_flag: host arrays of n_ranks device
+ *                       pointers (entry my_rank ignored). ticket: a zeroed device word owned by
+ *                       the caller. Ordered after earlier work on the stream.
+ *   keds_topk_merge_wait  keds_topk_merge_strided that first waits (system-scope acquire, bounded)
+ *                       until flags[r] >= epoch for every r != my_rank; flags: this rank's own
+ *                       flag array [parts]; a peer that never arrives sets *err_word. */
+int keds_p2p_push(const void* src, int64_t bytes, void* const* peer_dst, uint32_t* const* peer_flag,
+                  int n_ranks, int my_rank, uint32_t epoch, uint32_t* ticket, void* cuda_stream);
+int keds_topk_merge_wait(const float* D_parts, const int64_t* I_parts, int64_t stride_d, int64_t stride_i,
+                         int parts, int64_t nq, int k, int metric, float* D, int64_t* I,
+                         const uint32_t* flags, int my_rank, uint32_t epoch, uint32_t* err_word,
+                         void* cuda_stream);
+
 /* ---- gallery ranking --------------------------------------------------------------------------
  * rank_out[q] = #{ g != target[q], g != exclude[q] : (s(q,g), -g) > (s(q,target), -target) } with
  * s = fp32 inner product. Replaces the similarity matrix + full argsort + name matching of

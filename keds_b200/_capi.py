@@ -74,6 +74,15 @@ SIGNATURES = {
         C.c_int,
         [_vp, _vp, C.c_int64, C.c_int64, C.c_int, C.c_int64, C.c_int, C.c_int, _vp, _vp, _vp],
     ),
+    "keds_p2p_push": (
+        C.c_int,
+        [_vp, C.c_int64, C.POINTER(_vp), C.POINTER(_vp), C.c_int, C.c_int, C.c_uint32, _vp, _vp],
+    ),
+    "keds_topk_merge_wait": (
+        C.c_int,
+        [_vp, _vp, C.c_int64, C.c_int64, C.c_int, C.c_int64, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int,
+         C.c_uint32, _vp, _vp],
+    ),
     "keds_gallery_rank": (C.c_int, [_vp, C.c_int64, _vp, C.c_int64, C.c_int, _vp, _vp, _vp, _vp]),
     "keds_label_hits": (C.c_int, [_vp, C.c_int64, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp]),
     "keds_debug_scores": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp]),

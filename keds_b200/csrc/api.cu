@@ -983,9 +983,9 @@ int keds_topk_merge(const float* Dp, const int64_t* Ip, int parts, int64_t nq, i
   return keds_topk_merge_strided(Dp, Ip, nq * k, nq * k, parts, nq, k, metric, D, I, stream);
 }
 
-int keds_topk_merge_strided(const float* Dp, const int64_t* Ip, int64_t stride_d, int64_t stride_i,
-                            int parts, int64_t nq, int k, int metric, float* D, int64_t* I,
-                            void* stream) {
+static int merge_impl(const float* Dp, const int64_t* Ip, int64_t stride_d, int64_t stride_i, int parts,
+                      int64_t nq, int k, int metric, float* D, int64_t* I, const MergeWait& mw,
+                      void* stream) {
   if (!Dp || !Ip || !D || !I || parts <= 0 || nq < 0 || k <= 0)
     return fail(KEDS_ERR_ARG, "topk_merge: bad argument");
   if (nq == 0) return 0;
@@ -997,11 +997,58 @@ int keds_topk_merge_strided(const float* Dp, const int64_t* Ip, int64_t stride_d
     CK(cudaFuncSetAttribute(k_topk_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr = true;
   }
-  k_topk_merge<<<static_cast<unsigned>(nq), 128, smem, static_cast<cudaStream_t>(stream)>>>(
-      Dp, reinterpret_cast<const long long*>(Ip), stride_d, stride_i, parts, nq, k, metric, D,
-      reinterpret_cast<long long*>(I));
-  CK(cudaGetLastError());
+  // launched behind the local search / the push kernel with the programmatic attribute: its
+  // launch latency hides under their tails (it starts with griddepcontrol.wait)
+  CKS(launch_k(true, k_topk_merge, dim3(static_cast<unsigned>(nq)), dim3(128), smem,
+               static_cast<cudaStream_t>(stream), Dp, reinterpret_cast<const long long*>(Ip),
+               static_cast<long long>(stride_d), static_cast<long long>(stride_i), parts,
+               static_cast<long long>(nq), k, metric, D, reinterpret_cast<long long*>(I), mw));
   return 0;
+}
+
+int keds_topk_merge_strided(const float* Dp, const int64_t* Ip, int64_t stride_d, int64_t stride_i,
+                            int parts, int64_t nq, int k, int metric, float* D, int64_t* I,
+                            void* stream) {
+  MergeWait mw;
+  memset(&mw, 0, sizeof mw);
+  return merge_impl(Dp, Ip, stride_d, stride_i, parts, nq, k, metric, D, I, mw, stream);
+}
+
+int keds_p2p_push(const void* src, int64_t bytes, void* const* peer_dst, uint32_t* const* peer_flag,
+                  int n_ranks, int my_rank, uint32_t epoch, uint32_t* ticket, void* stream) {
+  if (!src || !peer_dst || !peer_flag || !ticket || bytes <= 0 || (bytes & 15) || n_ranks < 1 ||
+      n_ranks > P2P_MAX_RANKS || my_rank < 0 || my_rank >= n_ranks)
+    return fail(KEDS_ERR_ARG, "p2p_push: bad argument (bytes must be a positive multiple of 16, <= %d ranks)",
+                P2P_MAX_RANKS);
+  P2PPush p;
+  memset(&p, 0, sizeof p);
+  p.n_ranks = n_ranks;
+  p.my_rank = my_rank;
+  p.epoch = epoch;
+  p.n16 = bytes / 16;
+  p.src = static_cast<const uint4*>(src);
+  for (int r = 0; r < n_ranks; ++r) {
+    p.dst[r] = static_cast<uint4*>(peer_dst[r]);
+    p.flag[r] = peer_flag[r];
+    if (r != my_rank && (!p.dst[r] || !p.flag[r])) return fail(KEDS_ERR_ARG, "p2p_push: null peer pointer");
+  }
+  p.ticket = ticket;
+  const unsigned blocks = static_cast<unsigned>(std::min<long long>(64, (p.n16 + 255) / 256));
+  CKS(launch_k(true, k_p2p_push, dim3(std::max(1u, blocks)), dim3(256), 0, static_cast<cudaStream_t>(stream), p));
+  return 0;
+}
+
+int keds_topk_merge_wait(const float* Dp, const int64_t* Ip, int64_t stride_d, int64_t stride_i, int parts,
+                         int64_t nq, int k, int metric, float* D, int64_t* I, const uint32_t* flags,
+                         int my_rank, uint32_t epoch, uint32_t* err_word, void* stream) {
+  if (!flags || !err_word || my_rank < 0 || my_rank >= parts)
+    return fail(KEDS_ERR_ARG, "topk_merge_wait: bad argument");
+  MergeWait mw;
+  mw.flags = flags;
+  mw.my_rank = my_rank;
+  mw.epoch = epoch;
+  mw.err_word = err_word;
+  return merge_impl(Dp, Ip, stride_d, stride_i, parts, nq, k, metric, D, I, mw, stream);
 }
 
 int keds_gallery_rank(const float* Q, int64_t nq, const float* G, int64_t ng, int d,

@@ -459,21 +459,37 @@ __global__ void k_flag_all(int* flagged, int* n_flagged, int nq) {
 }  // namespace keds
 
 #include "exact_fallback.cuh"
+#include "p2p_exchange.cuh"
 
 namespace keds {
 
 // ---------------------------------------------------------------------------------------------
 // Merge `parts` per-shard results (part p at Dp + p*stride_d, Ip + p*stride_i, each [nq][k]) into the global top-k (same total order; ids are
 // already global). One block per query. Used after the all-gather of a row-sharded search.
-__global__ void k_topk_merge(const float* __restrict__ Dp, const long long* __restrict__ Ip,
+// With `flags` set (peer-memory exchange, p2p_exchange.cuh) each block first waits until every
+// peer has delivered its part for this `epoch`; Dp/Ip must not be __restrict__/read-only cached.
+struct MergeWait {
+  const unsigned int* flags;  // nullptr: parts are already complete (NCCL path)
+  int my_rank;
+  unsigned int epoch;
+  unsigned int* err_word;
+};
+
+__global__ void k_topk_merge(const float* Dp, const long long* Ip,
                              long long stride_d, long long stride_i, int parts, long long nq, int k,
-                             int metric, float* __restrict__ D, long long* __restrict__ I) {
+                             int metric, float* __restrict__ D, long long* __restrict__ I,
+                             const MergeWait mw) {
   extern __shared__ uint8_t mg_smem[];
   unsigned long long* key = reinterpret_cast<unsigned long long*>(mg_smem);   // parts*k
   float* val = reinterpret_cast<float*>(key + parts * k);                     // parts*k
   long long* idv = reinterpret_cast<long long*>(val + ((parts * k + 1) & ~1)); // parts*k
   const long long q = blockIdx.x;
   const int tot = parts * k;
+  griddep_wait();
+  if (mw.flags != nullptr) {
+    if (threadIdx.x == 0) p2p_wait_flags(mw.flags, parts, mw.my_rank, mw.epoch, mw.err_word);
+    __syncthreads();
+  }
   for (int i = threadIdx.x; i < tot; i += blockDim.x) {
     const int pt = i / k, j = i % k;
     const long long src = q * k + j;
