@@ -13,6 +13,11 @@ DEPS = [
     os.path.join(HERE, "csrc", "ptx.cuh"),
     os.path.join(HERE, "csrc", "score_topk_sm100.cuh"),
     os.path.join(HERE, "csrc", "aux_kernels.cuh"),
+    os.path.join(HERE, "csrc", "score_topk_resident_sm100.cuh"),
+    os.path.join(HERE, "csrc", "score_topk_mcast_sm100.cuh"),
+    os.path.join(HERE, "csrc", "rerank.cuh"),
+    os.path.join(HERE, "csrc", "exact_fallback.cuh"),
+    os.path.join(HERE, "csrc", "p2p_exchange.cuh"),
     os.path.join(os.path.dirname(HERE), "include", "keds_knn.h"),
 ]
 LIB = os.path.join(HERE, "libkeds_knn.so")
