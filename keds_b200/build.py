@@ -8,18 +8,9 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "api.cu")
-DEPS = [
-    SRC,
-    os.path.join(HERE, "csrc", "ptx.cuh"),
-    os.path.join(HERE, "csrc", "score_topk_sm100.cuh"),
-    os.path.join(HERE, "csrc", "aux_kernels.cuh"),
-    os.path.join(HERE, "csrc", "score_topk_resident_sm100.cuh"),
-    os.path.join(HERE, "csrc", "score_topk_mcast_sm100.cuh"),
-    os.path.join(HERE, "csrc", "rerank.cuh"),
-    os.path.join(HERE, "csrc", "exact_fallback.cuh"),
-    os.path.join(HERE, "csrc", "p2p_exchange.cuh"),
-    os.path.join(os.path.dirname(HERE), "include", "keds_knn.h"),
-]
+DEPS = [SRC, os.path.join(os.path.dirname(HERE), "include", "keds_knn.h")] + sorted(
+    os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HERE, "csrc")) if f.endswith(".cuh")
+)
 LIB = os.path.join(HERE, "libkeds_knn.so")
 
 NVCC_FLAGS = [

@@ -11,8 +11,6 @@
 #include <vector>
 
 #include "aux_kernels.cuh"
-#include "score_topk_resident_sm100.cuh"
-#include "score_topk_mcast_sm100.cuh"
 
 using namespace keds;
 
@@ -142,10 +140,8 @@ constexpr size_t TIMING_PAIRS = 5;  // k_prep_rows, k_score_topk, k_select_reran
 
 struct Plan {
   int exact_only = 0;
-  bool pair = false;      // CTA-pair scoring kernel (two query tiles per work item)
-  bool resident = false;  // CTA-pair kernel with resident queries (one query tile)
-  bool mcast = false;     // cluster of two CTAs sharing multicast query boxes (one query tile)
-  int S = 1, S_out = 1, n_qt = 1, n_qg = 1, n_items = 0, grid = 0;
+  bool pair = false;  // CTA-pair scoring kernel (two query tiles per work item)
+  int S = 1, n_qt = 1, n_qg = 1, n_items = 0, grid = 0;
 };
 
 }  // namespace
@@ -163,9 +159,7 @@ struct keds_index {
   // per-call scratch (one search in flight per handle)
   DevBuf q_f32, q_bf16, qstat, cand, cand_cnt, cand_theta, flagged[2], ctrl, exact_scratch;
   DevBuf D_stage[2], I_stage[2];
-  CUtensorMap tm_q;    // {64 x 128}-query boxes
-  CUtensorMap tm_q64;  // {64 x 64}-query boxes (resident-query pair kernel)
-  int one_tile_variant = 0;  // kernel for <= 128 queries: 0 single CTA, 1 resident pair, 2 multicast pair
+  CUtensorMap tm_q;
   const void* tm_q_base = nullptr;
   int64_t tm_q_rows = 0;
   keds_search_stats stats;
@@ -193,15 +187,6 @@ int set_kernel_attrs(keds_index* ix) {
                           (int)SCORE_PAIR_SMEM_BYTES));
   const char* no_pair = getenv("KEDS_NO_PAIR");
   ix->use_pair = !(no_pair && no_pair[0] == '1');
-  CK(cudaFuncSetAttribute(k_score_topk_resident, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                          (int)SCORE_RES_SMEM_BYTES));
-  CK(cudaFuncSetAttribute(k_score_topk_mcast, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                          (int)SCORE_SMEM_BYTES));
-  if (const char* v = getenv("KEDS_ONE_TILE")) {
-    if (!strcmp(v, "single")) ix->one_tile_variant = 0;
-    else if (!strcmp(v, "resident")) ix->one_tile_variant = 1;
-    else if (!strcmp(v, "mcast")) ix->one_tile_variant = 2;
-  }
   CK(cudaFuncSetAttribute(k_select_rerank<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaFuncSetAttribute(k_select_rerank<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaFuncSetAttribute(k_exact_scores, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
@@ -269,41 +254,30 @@ Plan make_plan(const keds_index* ix, int n_db, int64_t nq, int k, int64_t n_min,
   const int S_sel = std::max(1, (6 * k + LKEEP - 1) / LKEEP);
   // more than one query tile: CTA pairs share each row tile (two query tiles per work item)
   pl.pair = ix->use_pair && pl.n_qt >= 2 && ix->num_sms >= 2;
-  // one query tile: CTA pairs with the queries resident in shared memory (64 per CTA)
-  pl.resident = ix->one_tile_variant == 1 && pl.n_qt == 1 && ix->num_sms >= 2 && ix->d_pad / BK <= R_MAX_KBLOCKS;
-  // ... or pairs that walk one slice together and multicast the query boxes to each other
-  pl.mcast = ix->one_tile_variant == 2 && pl.n_qt == 1 && ix->num_sms >= 2;
-  const bool two_cta = pl.pair || pl.resident || pl.mcast;
-  const bool sub2 = pl.resident || pl.mcast;  // two candidate sub-slices per planner slice
   pl.n_qg = pl.pair ? (pl.n_qt + 1) / 2 : pl.n_qt;
-  const int units = two_cta ? ix->num_sms / 2 : ix->num_sms;
+  const int units = pl.pair ? ix->num_sms / 2 : ix->num_sms;
   const int groups = n_db * pl.n_qg;
   int S_hi = std::min(T_min, S_MAX);
   const long long by_mem =
       static_cast<long long>(CAND_BUDGET / (size_t(LKEEP) * BM * 8)) / (static_cast<long long>(n_db) * pl.n_qt);
-  S_hi = static_cast<int>(std::min<long long>(S_hi, sub2 ? by_mem / 2 : by_mem));
-  const int S_lo = sub2 ? (S_sel + 1) / 2 : S_sel;
-  if ((flags & KEDS_SEARCH_EXACT_ONLY) || S_hi < S_lo || k > R_MAX / 2) {
+  S_hi = static_cast<int>(std::min<long long>(S_hi, by_mem));
+  if ((flags & KEDS_SEARCH_EXACT_ONLY) || S_hi < S_sel || k > R_MAX / 2) {
     pl.exact_only = 1;
     return pl;
   }
   double best = 1e300;
-  for (int S = S_lo; S <= S_hi; ++S) {
+  for (int S = S_sel; S <= S_hi; ++S) {
     const long long items = static_cast<long long>(groups) * S;
     const long long G = std::min<long long>(items, units);
     const long long per_cta = (items + G - 1) / G;
-    int tiles = (T_max + S - 1) / S;           // tiles one CTA walks per item
-    if (pl.mcast) tiles = (tiles + 1) / 2;     // the two CTAs of a pair interleave a slice's tiles
-    const double cost = static_cast<double>(per_cta) * tiles + 0.35 * per_cta;
+    const double cost = static_cast<double>(per_cta) * ((T_max + S - 1) / S) + 0.35 * per_cta;
     if (cost < best - 1e-9) {
       best = cost;
       pl.S = S;
     }
   }
   pl.n_items = groups * pl.S;
-  pl.grid = std::min(pl.n_items, units) * (two_cta ? 2 : 1);
-  // the one-query-tile pair kernels hand the re-rank two sub-slices per planner slice
-  pl.S_out = sub2 ? 2 * pl.S : pl.S;
+  pl.grid = std::min(pl.n_items, units) * (pl.pair ? 2 : 1);
   return pl;
 }
 
@@ -319,7 +293,6 @@ int ensure_q_map(keds_index* ix, int64_t rows_needed) {
   if (ix->tm_q_base != ix->q_bf16.p) {
     const int64_t rows = static_cast<int64_t>(ix->q_bf16.cap / (static_cast<size_t>(ix->d_pad) * 2));
     CKS(encode_rows_map(&ix->tm_q, ix->q_bf16.p, rows, ix->d_pad, BM));
-    CKS(encode_rows_map(&ix->tm_q64, ix->q_bf16.p, rows, ix->d_pad, RQ));
     ix->tm_q_base = ix->q_bf16.p;
     ix->tm_q_rows = rows;
   }
@@ -452,7 +425,7 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
       a->stats.launches++;
     }
     // candidate lines are indexed by (db, slice, query tile) whatever the work-item grouping
-    const size_t items = static_cast<size_t>(n_db) * pl.S_out * pl.n_qt;
+    const size_t items = static_cast<size_t>(n_db) * pl.S * pl.n_qt;
     CKS(a->cand.ensure(items * LKEEP * BM * 8));
     CKS(a->cand_cnt.ensure(items * BM * 4));
     CKS(a->cand_theta.ensure(items * BM * 4));
@@ -479,13 +452,7 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
     sp.ld_dump = ld_dump;
     sp.timing = tchain ? tchain + 2 : nullptr;
     CKS(prof_mark(a, st, 1));
-    if (pl.mcast)
-      CKS(launch_kc(a->use_pdl, 2, k_score_topk_mcast, dim3(pl.grid), dim3(SCORE_THREADS),
-                    SCORE_SMEM_BYTES, st, a->tm_q64, ix[0]->tm_x, n_db > 1 ? ix[1]->tm_x : ix[0]->tm_x, sp));
-    else if (pl.resident)
-      CKS(launch_kc(a->use_pdl, 2, k_score_topk_resident, dim3(pl.grid), dim3(SCORE_THREADS),
-                    SCORE_RES_SMEM_BYTES, st, a->tm_q64, ix[0]->tm_xh, n_db > 1 ? ix[1]->tm_xh : ix[0]->tm_xh, sp));
-    else if (pl.pair)
+    if (pl.pair)
       CKS(launch_kc(a->use_pdl, 2, k_score_topk<true>, dim3(pl.grid), dim3(SCORE_THREADS), SCORE_PAIR_SMEM_BYTES,
                     st, a->tm_q, ix[0]->tm_xh, n_db > 1 ? ix[1]->tm_xh : ix[0]->tm_xh, sp));
     else
@@ -500,7 +467,7 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
     memset(&rp, 0, sizeof rp);
     rp.n_db = n_db;
     rp.n_qt = pl.n_qt;
-    rp.S = pl.S_out;
+    rp.S = pl.S;
     rp.nq = static_cast<int>(nq);
     rp.k = k;
     rp.d = a->d;
@@ -522,10 +489,10 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
     rp.eps_scale = a->eps_scale;
     rp.cons = cons;
     rp.timing = tchain ? tchain + 4 : nullptr;
-    const size_t slots = static_cast<size_t>(pl.S_out) * LKEEP;
+    const size_t slots = static_cast<size_t>(pl.S) * LKEEP;
     // qvec | part | keys, ids | smax | a_key, a_id, sel_id, sel_sc | hist | red | bcast | counters | top_*
     const size_t smem = static_cast<size_t>((a->d + 3) & ~3) * 4 + static_cast<size_t>(cons.part4) * 16 +
-                        slots * 8 + pl.S_out * 4 + R_MAX * 16 + 256 * 4 + 32 * 4 + 16 + 16 +
+                        slots * 8 + pl.S * 4 + R_MAX * 16 + 256 * 4 + 32 * 4 + 16 + 16 +
                         static_cast<size_t>(k) * 12;
     if (smem > 200 * 1024) return fail(KEDS_ERR_ARG, "re-rank shared memory %zu too large", smem);
     // one wave of blocks (two per SM): the latency variant; more: the four-per-SM throughput variant

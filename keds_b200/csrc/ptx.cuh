@@ -216,24 +216,6 @@ __device__ __forceinline__ void umma_commit_2sm(uint32_t bar, uint16_t cta_mask)
       "h"(cta_mask)
       : "memory");
 }
-// TMA load delivered to the same shared-memory offset of every CTA in `cta_mask`; each destination
-// CTA's mbarrier at offset `bar` counts the bytes it received
-__device__ __forceinline__ void tma_load_2d_mcast(uint32_t dst, const CUtensorMap* map, uint32_t bar,
-                                                  int32_t c_inner, int32_t c_outer, uint16_t cta_mask,
-                                                  uint64_t policy) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint "
-      "[%0], [%1, {%4, %5}], [%2], %3, %6;" ::"r"(dst),
-      "l"(map), "r"(bar), "h"(cta_mask), "r"(c_inner), "r"(c_outer), "l"(policy)
-      : "memory");
-}
-// single-CTA MMAs, but the completion arrives on the mbarrier at this offset in every CTA of `cta_mask`
-__device__ __forceinline__ void umma_commit_mcast(uint32_t bar, uint16_t cta_mask) {
-  asm volatile(
-      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-      "h"(cta_mask)
-      : "memory");
-}
 // arrive on the mbarrier at the same offset in CTA `cta` of the cluster
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
   asm volatile(
@@ -276,26 +258,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr)
       : "memory");
-}
-
-// 32 lanes x 16 columns
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
-        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
-        "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait16(uint32_t (&v)[16]) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]),
-                 "+r"(v[7]), "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]),
-                 "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
-               :
-               : "memory");
 }
 
 // Wait for outstanding tcgen05.ld of this thread. The registers are passed through as "+r" so

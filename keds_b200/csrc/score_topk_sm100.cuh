@@ -109,12 +109,10 @@ struct CandState {
 // Per-thread compaction of one query's candidate slots (all 32 lanes of a warp run it in lock
 // step on their own columns of the warp's interleaved buffer): find the LKEEP-th best score with
 // a register sorting network, raise theta to it, keep only strictly better entries.
-// CAPX = slots the caller's buffer really has (<= CAP; the network always sorts CAP values).
-template <int CAPX>
 __device__ __noinline__ CandState compact_candidates(uint32_t slot0, int cnt, float theta) {
   float s[CAP];
 #pragma unroll
-  for (int e = 0; e < CAP; ++e) s[e] = (e < CAPX && e < cnt) ? lds32f(slot0 + e * 256) : -INFINITY;
+  for (int e = 0; e < CAP; ++e) s[e] = (e < cnt) ? lds32f(slot0 + e * 256) : -INFINITY;
 #pragma unroll
   for (int k = 2; k <= CAP; k <<= 1) {
 #pragma unroll
@@ -349,7 +347,7 @@ k_score_topk(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
           }
           cnt = static_cast<int>((wptr - slot0) >> 8);
           if (__any_sync(0xffffffffu, cnt > CAP - CHUNK)) {
-            const CandState st = compact_candidates<CAP>(slot0, cnt, theta);
+            const CandState st = compact_candidates(slot0, cnt, theta);
             cnt = st.cnt;
             theta = st.theta;
           }
@@ -368,7 +366,7 @@ k_score_topk(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
       // [(db, s, qt)][query][LKEEP] {score bits, row id}, padded with {-inf, ~0}; the re-rank
       // kernel reads a slice with a single coalesced half-warp load.
       if (__any_sync(0xffffffffu, cnt >= LKEEP)) {
-        const CandState st = compact_candidates<CAP>(slot0, cnt, theta);
+        const CandState st = compact_candidates(slot0, cnt, theta);
         cnt = st.cnt;
         theta = st.theta;
       }
