@@ -176,6 +176,55 @@ int keds_label_hits(const int64_t* I, int64_t nq, int kmax, const int64_t* label
                     const int64_t* qlabel, const int32_t* ks, int nks, int32_t* hits,
                     void* cuda_stream);
 
+/* ---- neighbour consumer (forward only) ----------------------------------------
+ * The modules that consume the retrieved neighbours, evaluated in one launch sequence:
+ *   mapped = img2text(feat); nb_img = img2text(base_img[I_img]); nb_txt = img2text(base_txt[I_txt])
+ *   tokens[:,0,:] = retrieval_fuse(mapped[:,None], nb_img, nb_img)   (CrossFormer, image stack = 0)
+ *   tokens[:,1,:] = text_condition(mapped[:,None], nb_txt, nb_txt)   (CrossFormer, text stack = 1)
+ *   tokens[:,2,:] = mapped
+ * i.e. src/trainer.py:59-69 and src/eval_utils.py:378-383,515-519,661-668,806-810,943-947 with
+ * IM2TEXT / CrossFormer / CrossAttention of src/model/model.py:37-123 in eval mode (dropout off).
+ * Arithmetic: tf32 tensor-core products with fp32 accumulation, fp32 everywhere else. No backward
+ * pass: training keeps the PyTorch modules.
+ *
+ * create: d_in = feature width (768), d_mid = IM2TEXT middle_dim (512), d_tok = IM2TEXT output_dim =
+ *   CrossFormer q/k/v_dim (768), n_hidden = IM2TEXT n_layer (2), n_layers = CrossFormer num_layers
+ *   (3), heads (8), dim_head (64). All widths multiples of 4.
+ * set_linear: one nn.Linear, W [out][in] float32 row-major (torch layout), b [out] or NULL; host or
+ *   device pointers; copied. kind MLP: layer 0..n_hidden-1 = layers[i][0], layer n_hidden = fc_out
+ *   (stack ignored). Other kinds: to_q / to_k / to_v / to_out[0] of cross_layers[layer] of `stack`.
+ * finalize: after every slot is set; forward fails before it. */
+typedef struct keds_consumer keds_consumer_t;
+enum keds_consumer_kind {
+  KEDS_CONSUMER_MLP = 0,
+  KEDS_CONSUMER_TO_Q = 1,
+  KEDS_CONSUMER_TO_K = 2,
+  KEDS_CONSUMER_TO_V = 3,
+  KEDS_CONSUMER_TO_OUT = 4
+};
+int keds_consumer_create(int d_in, int d_mid, int d_tok, int n_hidden, int n_layers, int heads,
+                         int dim_head, int device, keds_consumer_t** out);
+void keds_consumer_free(keds_consumer_t* c);
+int keds_consumer_set_linear(keds_consumer_t* c, int kind, int stack, int layer, const float* W,
+                             const float* b, int out_features, int in_features);
+int keds_consumer_finalize(keds_consumer_t* c);
+/* feat [B][d_in], base_* [n_*][d_in] (keds_index_rows), I_* [B][k] int64 (ids < 0 read as zero rows),
+ * perm int32[k] or NULL (the shared randperm of src/trainer.py:218-219, image neighbours only),
+ * tokens [B][3][d_tok]: all device memory. Asynchronous on cuda_stream. */
+int keds_consumer_forward(keds_consumer_t* c, const float* feat, const float* base_img, int64_t n_img,
+                          const float* base_txt, int64_t n_txt, const int64_t* I_img,
+                          const int64_t* I_txt, const int32_t* perm, int64_t B, int k, float* tokens,
+                          void* cuda_stream);
+/* synchronise the stream and report a device-side pipeline error, if any; launches (nullable) =
+ * kernels launched by this handle so far */
+int keds_consumer_check(keds_consumer_t* c, void* cuda_stream, int64_t* launches);
+/* Diagnostics: with debug on, every k_linear_tf32 launch of a forward records per CTA
+ * {start, prologue done, dependency met, accumulator ready, end} (%globaltimer ns).
+ * debug_timeline copies launch `launch` (index within the last forward) of n_ctas CTAs to
+ * out[n_ctas][5] (host). Synchronises the device. */
+int keds_consumer_set_debug(keds_consumer_t* c, int enable);
+int keds_consumer_debug_timeline(keds_consumer_t* c, int launch, uint64_t* out, int64_t n_ctas);
+
 /* ---- diagnostics ------------------------------------------------------------------------------
  * Approximate (bf16 tensor-core) scores of q against every row: out [nq][ntotal] device float32.
  * Test hook for the GEMM alone; not a product path. */

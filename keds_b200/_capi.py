@@ -85,6 +85,20 @@ SIGNATURES = {
     ),
     "keds_gallery_rank": (C.c_int, [_vp, C.c_int64, _vp, C.c_int64, C.c_int, _vp, _vp, _vp, _vp]),
     "keds_label_hits": (C.c_int, [_vp, C.c_int64, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp]),
+    "keds_consumer_create": (
+        C.c_int,
+        [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)],
+    ),
+    "keds_consumer_free": (None, [_vp]),
+    "keds_consumer_set_linear": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_int, C.c_int]),
+    "keds_consumer_finalize": (C.c_int, [_vp]),
+    "keds_consumer_forward": (
+        C.c_int,
+        [_vp, _vp, _vp, C.c_int64, _vp, C.c_int64, _vp, _vp, _vp, C.c_int64, C.c_int, _vp, _vp],
+    ),
+    "keds_consumer_check": (C.c_int, [_vp, _vp, C.POINTER(C.c_int64)]),
+    "keds_consumer_set_debug": (C.c_int, [_vp, C.c_int]),
+    "keds_consumer_debug_timeline": (C.c_int, [_vp, C.c_int, _vp, C.c_int64]),
     "keds_debug_scores": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp]),
     "keds_index_set_eps_scale": (C.c_int, [_vp, C.c_float]),
     "keds_index_set_pdl": (C.c_int, [_vp, C.c_int]),

@@ -1078,3 +1078,6 @@ int keds_label_hits(const int64_t* I, int64_t nq, int kmax, const int64_t* label
 }
 
 }  // extern "C"
+
+// keds_consumer_*: the neighbour consumer (uses the helpers above)
+#include "consumer_host.cuh"

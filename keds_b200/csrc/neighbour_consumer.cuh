@@ -1,0 +1,290 @@
+// Forward pass of the consumer of the retrieved neighbours: the IM2TEXT MLP
+// applied to the query and to every neighbour, then two 3-layer single-query cross-attention
+// stacks (image neighbours / text neighbours) -- src/model/model.py:37-123, called at
+// src/trainer.py:59-69 and src/eval_utils.py:378-383,515-519,661-668,806-810,943-947.
+//
+// Two kernels:
+//   k_linear_tf32   C = act(A W^T + bias), nn.Linear layout (W: [out][in]), fp32 in / fp32 out,
+//                   tcgen05.mma kind::tf32 with TMA-staged operands (the TMA unit rounds fp32 to
+//                   tf32 on the way in), accumulators in TMEM, bias (+ReLU) fused in the epilogue.
+//                   blockIdx.z selects one of two independent problems of the same shape (the two
+//                   attention stacks), so both run in one launch.
+//   k_cross_attend  softmax(q K^T / sqrt(dh)) V for ONE query token per batch row over its k
+//                   neighbours, one warp per head (src/model/model.py:69-73 with n_q = 1).
+#pragma once
+#include "ptx.cuh"
+
+namespace keds {
+
+constexpr int LIN_M = 128;       // rows of A per tile (TMEM lanes)
+constexpr int LIN_K = 32;        // fp32 words per k-block = one 128-byte swizzle row
+constexpr int LIN_UK = 8;        // K per tcgen05.mma kind::tf32
+constexpr int LIN_THREADS = 192;
+constexpr uint32_t LIN_A_BYTES = LIN_M * LIN_K * 4;
+constexpr int LIN_WBOX = 128;    // rows of W per TMA box (the descriptor's box height)
+
+// BN = output features per tile (TMEM columns): 128 for the small products (more CTAs), 256 where
+// there are enough tiles anyway (half the A re-reads per flop).
+template <int BN>
+struct LinCfg {
+  static constexpr int kStages = BN == 128 ? 6 : 4;
+  static constexpr uint32_t kBBytes = BN * LIN_K * 4;
+  static constexpr uint32_t kStageBytes = LIN_A_BYTES + kBBytes;
+  static constexpr uint32_t kOffBars = kStages * kStageBytes;
+  static constexpr uint32_t kSmemBytes = kOffBars + 128 + BN * 4 + 1024;  // barriers, bias, alignment slack
+};
+
+struct LinearParams {
+  int M, N, K;            // C[M][N] = act(A[M][K] W[N][K]^T + bias[N])
+  int relu;
+  const float* bias[2];   // per problem (blockIdx.z); nullable
+  float* C[2];
+  long long ldc;          // floats between rows of C
+  uint32_t* err;          // device error word (0 = ok)
+  unsigned long long* tdump;  // diagnostics: per CTA {start, prologue done, dependency met, accumulator ready, end} ns
+};
+
+template <int BN>
+__global__ void __launch_bounds__(LIN_THREADS, 1)
+k_linear_tf32(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_a1,
+              const __grid_constant__ CUtensorMap tm_w0, const __grid_constant__ CUtensorMap tm_w1,
+              const LinearParams p) {
+  using Cfg = LinCfg<BN>;
+  constexpr int LIN_STAGES = Cfg::kStages;
+  constexpr uint32_t LIN_STAGE_BYTES = Cfg::kStageBytes;
+  constexpr int LIN_N = BN;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (sbase - smem_u32(smem_raw));
+  const uint32_t bars = sbase + Cfg::kOffBars;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (LIN_STAGES + s); };
+  const uint32_t tfull_bar = bars + 8u * (2 * LIN_STAGES);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + Cfg::kOffBars + 112);
+  volatile uint32_t* dead = reinterpret_cast<volatile uint32_t*>(gbase + Cfg::kOffBars + 116);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int z = blockIdx.z;
+  const int n0 = blockIdx.x * LIN_N;
+  const int m0 = blockIdx.y * LIN_M;
+  const CUtensorMap* tm_a = z == 0 ? &tm_a0 : &tm_a1;
+  const CUtensorMap* tm_w = z == 0 ? &tm_w0 : &tm_w1;
+  const int kblocks = (p.K + LIN_K - 1) / LIN_K;  // a ragged tail reads zeros from both operands
+  unsigned long long* td = p.tdump ? p.tdump + 5ull * (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) : nullptr;
+  if (td && threadIdx.x == 0) td[0] = global_timer_ns();
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(tm_a);
+    prefetch_tensormap(tm_w);
+    for (int s = 0; s < LIN_STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tfull_bar, 1);
+    *dead = 0;
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), LIN_N);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (td && threadIdx.x == 0) td[1] = global_timer_ns();
+
+  griddep_wait();  // A is the previous kernel's output
+  if (td && threadIdx.x == 0) td[2] = global_timer_ns();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1u, dead, p.err, 0x700u + stage);
+        const uint32_t sa = sbase + stage * LIN_STAGE_BYTES;
+        mbar_arrive_expect_tx(full_bar(stage), LIN_STAGE_BYTES);
+        tma_load_2d(sa, tm_a, full_bar(stage), kb * LIN_K, m0, kEvictNormal);
+#pragma unroll
+        for (int wb = 0; wb < BN / LIN_WBOX; ++wb)
+          tma_load_2d(sa + LIN_A_BYTES + wb * (LIN_WBOX * LIN_K * 4), tm_w, full_bar(stage), kb * LIN_K,
+                      n0 + wb * LIN_WBOX, kEvictLast);
+        if (++stage == LIN_STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = idesc_tf32_f32(LIN_M, LIN_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        mbar_wait(full_bar(stage), phase, dead, p.err, 0x710u + stage);
+        tc_fence_after();
+        const uint32_t sa = sbase + stage * LIN_STAGE_BYTES;
+        const uint64_t adesc = smem_desc_sw128(sa);
+        const uint64_t bdesc = smem_desc_sw128(sa + LIN_A_BYTES);
+#pragma unroll
+        for (int k = 0; k < LIN_K / LIN_UK; ++k)  // +32 bytes per K = 8 step: +2 in 16-byte units
+          umma_tf32(tmem_base, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+        umma_commit(empty_bar(stage));
+        if (++stage == LIN_STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+      umma_commit(tfull_bar);
+    }
+  } else {
+    // epilogue: TMEM lane == row of C. A thread holds 32 consecutive columns of ONE row; written
+    // as such, a warp's store touches 32 rows (one 16-byte piece of 32 different lines). So each
+    // warp turns its 32 x 32 block through shared memory (the pipeline stages are idle by now) and
+    // writes whole 128-byte row segments.
+    const int quad = warp & 3;
+    const int row0 = m0 + quad * 32;
+    const float* bias = p.bias[z];
+    float* cbase = p.C[z] + n0;
+    float* tr = reinterpret_cast<float*>(gbase) + quad * (32 * 33);  // [32 rows][33] per warp
+    // this tile's bias -> shared memory while the main loop runs (weights: no dependency on the
+    // previous kernel); the column loop below then never waits on global memory
+    float* sbias = reinterpret_cast<float*>(gbase + Cfg::kOffBars + 128);
+    for (int j = threadIdx.x - 64; j < LIN_N; j += 128)
+      sbias[j] = (bias != nullptr && n0 + j < p.N) ? __ldg(bias + n0 + j) : 0.f;
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    mbar_wait(tfull_bar, 0u, dead, p.err, 0x720u);
+    tc_fence_after();
+    if (td && threadIdx.x == 64) td[3] = global_timer_ns();
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const bool vec_ok = (p.ldc & 3) == 0 && (p.N & 3) == 0 && (reinterpret_cast<uintptr_t>(p.C[z]) & 15) == 0;
+#pragma unroll 1
+    for (int ch = 0; ch < LIN_N / 32; ++ch) {
+      uint32_t v[32];
+      tmem_ld32(taddr + ch * 32, v);
+      tmem_ld_wait(v);
+      const int c0 = n0 + ch * 32;
+      if (c0 >= p.N) break;
+      // bias first, into registers: interleaved with the stores below the compiler must assume
+      // the two shared-memory arrays alias and serialises 32 load -> store round trips
+      float4 bv[8];
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4) bv[j4] = reinterpret_cast<const float4*>(sbias + ch * 32)[j4];
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4) {
+        const float x0 = __uint_as_float(v[4 * j4 + 0]) + bv[j4].x, x1 = __uint_as_float(v[4 * j4 + 1]) + bv[j4].y;
+        const float x2 = __uint_as_float(v[4 * j4 + 2]) + bv[j4].z, x3 = __uint_as_float(v[4 * j4 + 3]) + bv[j4].w;
+        tr[lane * 33 + 4 * j4 + 0] = p.relu ? fmaxf(x0, 0.f) : x0;
+        tr[lane * 33 + 4 * j4 + 1] = p.relu ? fmaxf(x1, 0.f) : x1;
+        tr[lane * 33 + 4 * j4 + 2] = p.relu ? fmaxf(x2, 0.f) : x2;
+        tr[lane * 33 + 4 * j4 + 3] = p.relu ? fmaxf(x3, 0.f) : x3;
+      }
+      __syncwarp();
+      if (vec_ok) {
+        // 8 lanes cover one row's 32 columns (128 bytes), 4 rows per store instruction
+        const int cc = (lane & 7) * 4;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int rr = it * 4 + (lane >> 3);
+          const float* s = tr + rr * 33 + cc;
+          if (row0 + rr < p.M && c0 + cc < p.N)
+            *reinterpret_cast<float4*>(cbase + static_cast<long long>(row0 + rr) * p.ldc + ch * 32 + cc) =
+                make_float4(s[0], s[1], s[2], s[3]);
+        }
+      } else {
+        for (int rr = 0; rr < 32; ++rr)
+          if (row0 + rr < p.M && c0 + lane < p.N)
+            cbase[static_cast<long long>(row0 + rr) * p.ldc + ch * 32 + lane] = tr[rr * 33 + lane];
+      }
+      __syncwarp();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (td && threadIdx.x == 0) td[4] = global_timer_ns();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, LIN_N);
+  }
+}
+
+struct AttendParams {
+  int B, k, heads, dim_head;
+  const float* Q[2];    // [B][heads * dim_head]
+  const float* KV[2];   // [B * k][ld_kv]; keys at column k_off + h * dim_head, values at v_off + ...
+  float* O[2];          // [B][heads * dim_head]
+  long long ld_kv;
+  int k_off, v_off;
+  float scale;          // dim_head ** -0.5
+};
+
+// grid (B, problems), block = 32 * heads threads (one warp per head), dynamic smem =
+// heads * (dim_head + k) floats. Scores: one LANE per neighbour (its key row is read with
+// independent 16-byte loads against the query staged in shared memory); the weighted sum of the
+// value rows: one lane per output column, coalesced over the row.
+__global__ void k_cross_attend(const AttendParams p) {
+  extern __shared__ float att_sm[];
+  griddep_wait();
+  const int b = blockIdx.x;
+  const int z = blockIdx.y;
+  const int h = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int dh = p.dim_head;
+  const int inner = p.heads * dh;
+  const float* q = p.Q[z] + static_cast<long long>(b) * inner + h * dh;
+  const float* kv = p.KV[z] + static_cast<long long>(b) * p.k * p.ld_kv + h * dh;
+  float* qs = att_sm + h * dh;
+  float* w = att_sm + p.heads * dh + h * p.k;
+  for (int d = lane; d < dh; d += 32) qs[d] = q[d];
+  __syncwarp();
+  const bool vec = (dh & 3) == 0 && (p.ld_kv & 3) == 0 && (p.k_off & 3) == 0 &&
+                   (reinterpret_cast<uintptr_t>(p.KV[z]) & 15) == 0;
+  float mx = -INFINITY;
+  for (int j = lane; j < p.k; j += 32) {
+    const float* kr = kv + j * p.ld_kv + p.k_off;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    if (vec) {
+      const float4* k4 = reinterpret_cast<const float4*>(kr);
+      const float4* q4 = reinterpret_cast<const float4*>(qs);
+#pragma unroll 8
+      for (int d = 0; d < (dh >> 2); ++d) {
+        const float4 a = __ldg(k4 + d);
+        const float4 c = q4[d];
+        s0 = fmaf(a.x, c.x, s0);
+        s1 = fmaf(a.y, c.y, s1);
+        s2 = fmaf(a.z, c.z, s2);
+        s3 = fmaf(a.w, c.w, s3);
+      }
+    } else {
+      for (int d = 0; d < dh; ++d) s0 = fmaf(kr[d], qs[d], s0);
+    }
+    const float s = ((s0 + s1) + (s2 + s3)) * p.scale;
+    w[j] = s;
+    mx = fmaxf(mx, s);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float den = 0.f;
+  for (int j = lane; j < p.k; j += 32) {
+    const float e = expf(w[j] - mx);
+    w[j] = e;
+    den += e;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) den += __shfl_xor_sync(0xffffffffu, den, o);
+  __syncwarp();
+  const float inv = 1.f / den;
+  float* o = p.O[z] + static_cast<long long>(b) * inner + h * dh;
+  for (int d = lane; d < dh; d += 32) {
+    const float* vr = kv + p.v_off + d;
+    float acc = 0.f;
+#pragma unroll 8
+    for (int j = 0; j < p.k; ++j) acc = fmaf(w[j], __ldg(vr + j * p.ld_kv), acc);
+    o[d] = acc * inv;
+  }
+}
+
+}  // namespace keds

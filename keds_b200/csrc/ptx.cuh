@@ -41,7 +41,9 @@ __device__ __forceinline__ void griddep_launch_dependents() {
 }
 __device__ __forceinline__ unsigned long long global_timer_ns() {
   unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  // "memory": the read must stay on its side of barriers (without it the compiler hoists it above
+  // a __syncthreads and an "end" stamp is taken when the thread ARRIVES at the barrier)
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)::"memory");
   return t;
 }
 
@@ -243,6 +245,22 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
 // Instruction descriptor, kind::f16: A=B=bf16, D=fp32, both operands K-major, dense.
 __host__ __device__ constexpr uint32_t idesc_bf16_f32(uint32_t M, uint32_t N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+// kind::tf32: A=B=tf32 (fp32 words in shared memory, 8 per K step), D=fp32, K-major, dense.
+__host__ __device__ constexpr uint32_t idesc_tf32_f32(uint32_t M, uint32_t N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 
 // 32 lanes x 32 columns of fp32 accumulators -> 32 registers per thread (thread i owns lane base+i).

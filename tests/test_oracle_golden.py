@@ -103,3 +103,20 @@ def test_metrics_coco(met):
 def test_metrics_imgnet(met):
     z, e = met
     _close(orc.metrics_imgnet(z["in_q"], z["in_gal"], z["in_qlab"], z["in_glab"]), e["metrics"]["imgnet"])
+
+
+# ------------------------------------------------------------------ neighbour consumer (§8 f2)
+def test_consumer_oracle_matches_the_reference_modules(golden_dir):
+    # tests/golden/consumer.npz: IM2TEXT / CrossFormer of src/model/model.py run unchanged
+    # (oracle/make_golden_consumer.py), call sequence of src/trainer.py:59-69
+    from oracle import consumer_oracle as corc
+
+    g = np.load(os.path.join(golden_dir, "consumer.npz"))
+    heads = int(g["dims"][5])
+    sds = [{k.split("/", 1)[1]: g[k] for k in g.files if k.startswith(p + "/")}
+           for p in ("img2text", "retrieval_fuse", "text_condition")]
+    tokens = corc.consumer_tokens(sds[0], sds[1], sds[2], heads, g["feat"], g["base_img"], g["base_txt"],
+                                  g["I_img"], g["I_txt"])
+    assert tokens.shape == g["tokens"].shape == (5, 3, 40)
+    # the reference computed in float32, the oracle in float64
+    assert np.abs(tokens - g["tokens"]).max() < 2e-6 * max(1.0, np.abs(g["tokens"]).max())
