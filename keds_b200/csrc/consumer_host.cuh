@@ -13,17 +13,19 @@ struct LinearW {
   DevBuf w, b;
   int out = 0, in = 0;
   bool set = false;
-  CUtensorMap tm;
+  CUtensorMap tm;     // boxes of 128 weight rows (k_linear_tf32)
+  CUtensorMap tm32;   // boxes of 32 weight rows (k_linear_tf32_splitk)
 };
 
 // fp32 [rows][cols] with `ld` floats between rows -> boxes of {32 columns x 128 rows}, 128-byte
 // swizzle; the TMA unit rounds to tf32 and zero-fills out-of-range rows / columns.
-int encode_f32_map(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int64_t ld) {
+int encode_f32_map(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int64_t ld,
+                   int box_rows = LIN_M) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail(KEDS_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
   cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ld) * 4};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(LIN_K), static_cast<cuuint32_t>(LIN_M)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(LIN_K), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, const_cast<void*>(base), gdim, gstr, box,
                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -132,6 +134,24 @@ int consumer_linear(keds_consumer* c, const float* A0, const float* A1, int64_t 
   const long long c128 = mt * ((p.N + 127) / 128) * nz, c256 = mt * ((p.N + 255) / 256) * nz;
   const long long sms = std::max(1, c->num_sms);
   const bool wide = ((c256 + sms - 1) / sms) * 48 < ((c128 + sms - 1) / sms) * 32;
+  // a handful of tiles only: 32-column tiles with the K range split over a cluster of SK_SPLIT CTAs
+  if (c128 * 6 <= sms && c->num_sms >= SK_MAX_SPLIT) {
+    const long long tiles = mt * ((p.N + SK_BN - 1) / SK_BN) * nz;
+    const int split = tiles * 4 <= sms ? 4 : 2;  // keep it to one wave
+    const dim3 gs(static_cast<unsigned>(split * ((p.N + SK_BN - 1) / SK_BN)), static_cast<unsigned>(mt),
+                  static_cast<unsigned>(nz));
+    if (c->debug && c->dbg_launch < CONS_DBG_LAUNCHES && gs.x * gs.y * gs.z <= (unsigned)CONS_DBG_CTAS)
+      p.tdump = c->tdump.as<unsigned long long>() + static_cast<size_t>(c->dbg_launch) * CONS_DBG_CTAS * 5;
+    c->dbg_launch++;
+    if (split == 4)
+      CKS(launch_kc(true, 4, k_linear_tf32_splitk<4>, gs, dim3(SK_THREADS), SK_SMEM_BYTES, st, ta0, ta1, W0->tm32,
+                    nz > 1 ? W1->tm32 : W0->tm32, p));
+    else
+      CKS(launch_kc(true, 2, k_linear_tf32_splitk<2>, gs, dim3(SK_THREADS), SK_SMEM_BYTES, st, ta0, ta1, W0->tm32,
+                    nz > 1 ? W1->tm32 : W0->tm32, p));
+    c->launches++;
+    return 0;
+  }
   const int bn = wide ? 256 : 128;
   const dim3 grid(static_cast<unsigned>((p.N + bn - 1) / bn), static_cast<unsigned>(mt), static_cast<unsigned>(nz));
   if (c->debug && c->dbg_launch < CONS_DBG_LAUNCHES && grid.x * grid.y * grid.z <= (unsigned)CONS_DBG_CTAS)
@@ -236,6 +256,10 @@ int keds_consumer_finalize(keds_consumer_t* c) {
                             (int)LinCfg<128>::kSmemBytes));
     CK(cudaFuncSetAttribute(k_linear_tf32<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)LinCfg<256>::kSmemBytes));
+    CK(cudaFuncSetAttribute(k_linear_tf32_splitk<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)SK_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(k_linear_tf32_splitk<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)SK_SMEM_BYTES));
     CK(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, c->device));
     c->attrs_set = true;
   }
@@ -256,13 +280,18 @@ int keds_consumer_finalize(keds_consumer_t* c) {
     }
     kv.set = true;
     CKS(encode_f32_map(&kv.tm, kv.w.p, kv.out, kv.in, kv.in));
+    CKS(encode_f32_map(&kv.tm32, kv.w.p, kv.out, kv.in, kv.in, SK_BN));
     for (int l = 0; l < c->n_layers; ++l) {
       CKS(encode_f32_map(&c->wq[z][l].tm, c->wq[z][l].w.p, c->inner, c->d_tok, c->d_tok));
       CKS(encode_f32_map(&c->wo[z][l].tm, c->wo[z][l].w.p, c->d_tok, c->inner, c->inner));
+      CKS(encode_f32_map(&c->wq[z][l].tm32, c->wq[z][l].w.p, c->inner, c->d_tok, c->d_tok, SK_BN));
+      CKS(encode_f32_map(&c->wo[z][l].tm32, c->wo[z][l].w.p, c->d_tok, c->inner, c->inner, SK_BN));
     }
   }
-  for (int i = 0; i <= c->n_hidden; ++i)
+  for (int i = 0; i <= c->n_hidden; ++i) {
     CKS(encode_f32_map(&c->mlp[i].tm, c->mlp[i].w.p, c->mlp[i].out, c->mlp[i].in, c->mlp[i].in));
+    CKS(encode_f32_map(&c->mlp[i].tm32, c->mlp[i].w.p, c->mlp[i].out, c->mlp[i].in, c->mlp[i].in, SK_BN));
+  }
   CK(cudaDeviceSynchronize());
   c->finalized = true;
   return 0;
@@ -358,8 +387,10 @@ int keds_consumer_forward(keds_consumer_t* c, const float* q, const float* base_
     ap.k_off = (2 * l) * inner;
     ap.v_off = (2 * l + 1) * inner;
     ap.scale = 1.0f / sqrtf(static_cast<float>(c->dim_head));
-    CKS(launch_k(true, k_cross_attend, dim3(static_cast<unsigned>(B), 2), dim3(32 * c->heads),
-                 static_cast<size_t>(c->heads) * (c->dim_head + k) * 4, st, ap));
+    // fast path: the reference's dim_head = 64 with 16-byte aligned key / value rows
+    const bool dh64 = c->dim_head == 64 && (kvw & 3) == 0;
+    CKS(launch_k(true, dh64 ? k_cross_attend<64> : k_cross_attend<0>, dim3(static_cast<unsigned>(B), 2),
+                 dim3(32 * c->heads), static_cast<size_t>(c->heads) * (c->dim_head + k) * 4, st, ap));
     c->launches++;
     float *o0, *o1;
     int64_t ldo;

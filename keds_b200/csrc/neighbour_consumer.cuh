@@ -19,7 +19,8 @@ namespace keds {
 constexpr int LIN_M = 128;       // rows of A per tile (TMEM lanes)
 constexpr int LIN_K = 32;        // fp32 words per k-block = one 128-byte swizzle row
 constexpr int LIN_UK = 8;        // K per tcgen05.mma kind::tf32
-constexpr int LIN_THREADS = 192;
+constexpr int LIN_THREADS = 320;    // k_linear_tf32: TMA warp, MMA warp, 8 epilogue warps (2 per TMEM lane quadrant)
+constexpr int SK_THREADS = 192;     // k_linear_tf32_splitk: TMA warp, MMA warp, 4 epilogue warps
 constexpr uint32_t LIN_A_BYTES = LIN_M * LIN_K * 4;
 constexpr int LIN_WBOX = 128;    // rows of W per TMA box (the descriptor's box height)
 
@@ -148,20 +149,21 @@ k_linear_tf32(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__
     const int row0 = m0 + quad * 32;
     const float* bias = p.bias[z];
     float* cbase = p.C[z] + n0;
-    float* tr = reinterpret_cast<float*>(gbase) + quad * (32 * 33);  // [32 rows][33] per warp
+    const int half = (warp - 2) >> 2;  // the two warps of a quadrant take alternate 32-column chunks
+    float* tr = reinterpret_cast<float*>(gbase) + (warp - 2) * (32 * 33);  // [32 rows][33] per warp
     // this tile's bias -> shared memory while the main loop runs (weights: no dependency on the
     // previous kernel); the column loop below then never waits on global memory
     float* sbias = reinterpret_cast<float*>(gbase + Cfg::kOffBars + 128);
-    for (int j = threadIdx.x - 64; j < LIN_N; j += 128)
+    for (int j = threadIdx.x - 64; j < LIN_N; j += 256)
       sbias[j] = (bias != nullptr && n0 + j < p.N) ? __ldg(bias + n0 + j) : 0.f;
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    asm volatile("bar.sync 1, 256;" ::: "memory");
     mbar_wait(tfull_bar, 0u, dead, p.err, 0x720u);
     tc_fence_after();
     if (td && threadIdx.x == 64) td[3] = global_timer_ns();
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     const bool vec_ok = (p.ldc & 3) == 0 && (p.N & 3) == 0 && (reinterpret_cast<uintptr_t>(p.C[z]) & 15) == 0;
 #pragma unroll 1
-    for (int ch = 0; ch < LIN_N / 32; ++ch) {
+    for (int ch = half; ch < LIN_N / 32; ch += 2) {
       uint32_t v[32];
       tmem_ld32(taddr + ch * 32, v);
       tmem_ld_wait(v);
@@ -204,10 +206,192 @@ k_linear_tf32(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__
 
   tc_fence_before();
   __syncthreads();
-  if (td && threadIdx.x == 0) td[4] = global_timer_ns();
+  if (td && lane == 0) atomicMax(&td[4], global_timer_ns());  // every warp: see ktimer_end
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, LIN_N);
+  }
+}
+
+// The same product for SMALL problems (the single-query-token chain: M = batch rows, a handful of
+// 128 x 128 tiles). One tile per CTA leaves most SMs idle and each busy SM limited by its 64 B/clk
+// ingress port, so here the work is cut finer in both directions: 32-column tiles, and the K range
+// of a tile split over a CLUSTER of SK_SPLIT CTAs. Each CTA accumulates its K slice in TMEM, parks
+// the 128 x 32 partial in its shared memory, and after a cluster barrier CTA r sums columns
+// [8r, 8r + 8) of all partials through distributed shared memory (fixed order: deterministic),
+// adds the bias and stores. grid = (SK_SPLIT * n_tiles, m_tiles, problems), cluster (SK_SPLIT,1,1).
+constexpr int SK_BN = 32;
+constexpr int SK_MAX_SPLIT = 4;      // cluster size: 2 or 4 (template parameter)
+constexpr int SK_STAGES = 6;
+constexpr uint32_t SK_B_BYTES = SK_BN * LIN_K * 4;                 // 4 KB
+constexpr uint32_t SK_STAGE_BYTES = LIN_A_BYTES + SK_B_BYTES;      // 20 KB
+constexpr uint32_t SK_OFF_PART = SK_STAGES * SK_STAGE_BYTES;       // [32 columns][128 rows] fp32
+constexpr uint32_t SK_OFF_BARS = SK_OFF_PART + SK_BN * LIN_M * 4;
+constexpr uint32_t SK_SMEM_BYTES = SK_OFF_BARS + 128 + 1024;
+
+template <int SK_SPLIT>
+__global__ void __launch_bounds__(SK_THREADS, 1)
+k_linear_tf32_splitk(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_a1,
+                     const __grid_constant__ CUtensorMap tm_w0, const __grid_constant__ CUtensorMap tm_w1,
+                     const LinearParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (sbase - smem_u32(smem_raw));
+  const uint32_t bars = sbase + SK_OFF_BARS;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (SK_STAGES + s); };
+  const uint32_t tfull_bar = bars + 8u * (2 * SK_STAGES);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + SK_OFF_BARS + 112);
+  volatile uint32_t* dead = reinterpret_cast<volatile uint32_t*>(gbase + SK_OFF_BARS + 116);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int z = blockIdx.z;
+  const int split = static_cast<int>(cluster_ctarank());   // == blockIdx.x % SK_SPLIT
+  const int n0 = (blockIdx.x / SK_SPLIT) * SK_BN;
+  const int m0 = blockIdx.y * LIN_M;
+  const CUtensorMap* tm_a = z == 0 ? &tm_a0 : &tm_a1;
+  const CUtensorMap* tm_w = z == 0 ? &tm_w0 : &tm_w1;
+  const int kblocks = (p.K + LIN_K - 1) / LIN_K;
+  const int kb0 = kblocks * split / SK_SPLIT, kb1 = kblocks * (split + 1) / SK_SPLIT;
+  unsigned long long* td = p.tdump ? p.tdump + 5ull * (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) : nullptr;
+  if (td && threadIdx.x == 0) td[0] = global_timer_ns();
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(tm_a);
+    prefetch_tensormap(tm_w);
+    for (int s = 0; s < SK_STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tfull_bar, 1);
+    *dead = 0;
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), SK_BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (td && threadIdx.x == 0) td[1] = global_timer_ns();
+
+  griddep_wait();
+  if (td && threadIdx.x == 0) td[2] = global_timer_ns();
+
+  float* part = reinterpret_cast<float*>(gbase + SK_OFF_PART);
+  float bv[SK_BN / SK_SPLIT];  // bias of the columns this CTA reduces (epilogue warps)
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1u, dead, p.err, 0x800u + stage);
+        const uint32_t sa = sbase + stage * SK_STAGE_BYTES;
+        mbar_arrive_expect_tx(full_bar(stage), SK_STAGE_BYTES);
+        tma_load_2d(sa, tm_a, full_bar(stage), kb * LIN_K, m0, kEvictNormal);
+        tma_load_2d(sa + LIN_A_BYTES, tm_w, full_bar(stage), kb * LIN_K, n0, kEvictLast);
+        if (++stage == SK_STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = idesc_tf32_f32(LIN_M, SK_BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(full_bar(stage), phase, dead, p.err, 0x810u + stage);
+        tc_fence_after();
+        const uint32_t sa = sbase + stage * SK_STAGE_BYTES;
+        const uint64_t adesc = smem_desc_sw128(sa);
+        const uint64_t bdesc = smem_desc_sw128(sa + LIN_A_BYTES);
+#pragma unroll
+        for (int k = 0; k < LIN_K / LIN_UK; ++k)
+          umma_tf32(tmem_base, adesc + 2u * k, bdesc + 2u * k, idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
+        umma_commit(empty_bar(stage));
+        if (++stage == SK_STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+      umma_commit(tfull_bar);
+    }
+  } else {
+    // this CTA's partial tile -> shared memory, column-major (thread == row: conflict-free)
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;
+#pragma unroll
+    for (int c = 0; c < SK_BN / SK_SPLIT; ++c) {
+      const int col = n0 + split * (SK_BN / SK_SPLIT) + c;
+      bv[c] = (p.bias[z] != nullptr && col < p.N) ? __ldg(p.bias[z] + col) : 0.f;
+    }
+    uint32_t v[32];
+    if (kb1 > kb0) {
+      mbar_wait(tfull_bar, 0u, dead, p.err, 0x820u);
+      tc_fence_after();
+      tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16), v);
+      tmem_ld_wait(v);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = 0u;  // more splits than k-blocks: this slice is empty
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) part[j * LIN_M + r] = __uint_as_float(v[j]);
+  }
+  if (td && threadIdx.x == 64) td[3] = global_timer_ns();
+
+  tc_fence_before();
+  __syncwarp();
+  cluster_sync_all();  // every CTA's partial is parked
+
+  if (warp >= 2) {
+    // CTA `split` owns columns [8 split, 8 split + 8) of the tile: sum the SK_SPLIT partials in rank
+    // order through distributed shared memory, add the bias, store 32 bytes per row
+    const int r = (warp & 3) * 32 + lane;
+    const int row = m0 + r;
+    const int c0 = split * (SK_BN / SK_SPLIT);
+    float acc[SK_BN / SK_SPLIT];
+#pragma unroll
+    for (int c = 0; c < SK_BN / SK_SPLIT; ++c) acc[c] = 0.f;
+    const uint32_t pbase = sbase + SK_OFF_PART;
+#pragma unroll
+    for (int s = 0; s < SK_SPLIT; ++s) {
+#pragma unroll
+      for (int c = 0; c < SK_BN / SK_SPLIT; ++c)
+        acc[c] += ld_dsmem_f32(pbase + static_cast<uint32_t>(((c0 + c) * LIN_M + r) * 4), static_cast<uint32_t>(s));
+    }
+#pragma unroll
+    for (int c = 0; c < SK_BN / SK_SPLIT; ++c) {
+      const float x = acc[c] + bv[c];
+      acc[c] = p.relu ? fmaxf(x, 0.f) : x;
+    }
+    if (row < p.M) {
+      float* crow = p.C[z] + static_cast<long long>(row) * p.ldc + n0 + c0;
+      const bool vec_ok = (p.ldc & 3) == 0 && (p.N & 3) == 0 && (reinterpret_cast<uintptr_t>(p.C[z]) & 15) == 0;
+      if (vec_ok) {
+#pragma unroll
+        for (int c = 0; c < SK_BN / SK_SPLIT; c += 4)
+          if (n0 + c0 + c < p.N)
+            *reinterpret_cast<float4*>(crow + c) = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
+      } else {
+#pragma unroll
+        for (int c = 0; c < SK_BN / SK_SPLIT; ++c)
+          if (n0 + c0 + c < p.N) crow[c] = acc[c];
+      }
+    }
+  }
+
+  __syncwarp();
+  cluster_sync_all();  // nobody leaves while a peer may still read its partial
+  if (td && lane == 0) atomicMax(&td[4], global_timer_ns());
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, SK_BN);
   }
 }
 
@@ -225,6 +409,10 @@ struct AttendParams {
 // heads * (dim_head + k) floats. Scores: one LANE per neighbour (its key row is read with
 // independent 16-byte loads against the query staged in shared memory); the weighted sum of the
 // value rows: one lane per output column, coalesced over the row.
+// DH = 64 (the reference's dim_head): every global load of a phase is issued before its first
+// use (explicit register arrays -- left to itself the compiler keeps two loads in flight and the
+// kernel is a chain of ~24 memory round trips). DH = 0: any dim_head, plain loops.
+template <int DH>
 __global__ void k_cross_attend(const AttendParams p) {
   extern __shared__ float att_sm[];
   griddep_wait();
@@ -232,7 +420,7 @@ __global__ void k_cross_attend(const AttendParams p) {
   const int z = blockIdx.y;
   const int h = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int dh = p.dim_head;
+  const int dh = DH > 0 ? DH : p.dim_head;
   const int inner = p.heads * dh;
   const float* q = p.Q[z] + static_cast<long long>(b) * inner + h * dh;
   const float* kv = p.KV[z] + static_cast<long long>(b) * p.k * p.ld_kv + h * dh;
@@ -240,28 +428,29 @@ __global__ void k_cross_attend(const AttendParams p) {
   float* w = att_sm + p.heads * dh + h * p.k;
   for (int d = lane; d < dh; d += 32) qs[d] = q[d];
   __syncwarp();
-  const bool vec = (dh & 3) == 0 && (p.ld_kv & 3) == 0 && (p.k_off & 3) == 0 &&
-                   (reinterpret_cast<uintptr_t>(p.KV[z]) & 15) == 0;
   float mx = -INFINITY;
   for (int j = lane; j < p.k; j += 32) {
     const float* kr = kv + j * p.ld_kv + p.k_off;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    if (vec) {
-      const float4* k4 = reinterpret_cast<const float4*>(kr);
-      const float4* q4 = reinterpret_cast<const float4*>(qs);
-#pragma unroll 8
-      for (int d = 0; d < (dh >> 2); ++d) {
-        const float4 a = __ldg(k4 + d);
-        const float4 c = q4[d];
-        s0 = fmaf(a.x, c.x, s0);
-        s1 = fmaf(a.y, c.y, s1);
-        s2 = fmaf(a.z, c.z, s2);
-        s3 = fmaf(a.w, c.w, s3);
+    float s;
+    if constexpr (DH > 0) {
+      float4 a[DH / 4];
+#pragma unroll
+      for (int d = 0; d < DH / 4; ++d) a[d] = __ldg(reinterpret_cast<const float4*>(kr) + d);
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+      for (int d = 0; d < DH / 4; ++d) {
+        const float4 c = reinterpret_cast<const float4*>(qs)[d];
+        s0 = fmaf(a[d].x, c.x, s0);
+        s1 = fmaf(a[d].y, c.y, s1);
+        s2 = fmaf(a[d].z, c.z, s2);
+        s3 = fmaf(a[d].w, c.w, s3);
       }
+      s = (s0 + s1) + (s2 + s3);
     } else {
-      for (int d = 0; d < dh; ++d) s0 = fmaf(kr[d], qs[d], s0);
+      s = 0.f;
+      for (int d = 0; d < dh; ++d) s = fmaf(kr[d], qs[d], s);
     }
-    const float s = ((s0 + s1) + (s2 + s3)) * p.scale;
+    s *= p.scale;
     w[j] = s;
     mx = fmaxf(mx, s);
   }
@@ -278,12 +467,34 @@ __global__ void k_cross_attend(const AttendParams p) {
   __syncwarp();
   const float inv = 1.f / den;
   float* o = p.O[z] + static_cast<long long>(b) * inner + h * dh;
-  for (int d = lane; d < dh; d += 32) {
-    const float* vr = kv + p.v_off + d;
-    float acc = 0.f;
-#pragma unroll 8
-    for (int j = 0; j < p.k; ++j) acc = fmaf(w[j], __ldg(vr + j * p.ld_kv), acc);
-    o[d] = acc * inv;
+  if constexpr (DH > 0) {
+    // lane owns columns lane and lane + 32; 16 value rows (2 x 16 loads) in flight per step
+    float acc0 = 0.f, acc1 = 0.f;
+    for (int j0 = 0; j0 < p.k; j0 += 16) {
+      float t0[16], t1[16];
+#pragma unroll
+      for (int jj = 0; jj < 16; ++jj) {
+        const bool live = j0 + jj < p.k;
+        const float* vr = kv + (j0 + jj) * p.ld_kv + p.v_off;
+        t0[jj] = live ? __ldg(vr + lane) : 0.f;
+        t1[jj] = (live && DH > 32) ? __ldg(vr + 32 + lane) : 0.f;
+      }
+#pragma unroll
+      for (int jj = 0; jj < 16; ++jj) {
+        const float wj = j0 + jj < p.k ? w[j0 + jj] : 0.f;
+        acc0 = fmaf(wj, t0[jj], acc0);
+        acc1 = fmaf(wj, t1[jj], acc1);
+      }
+    }
+    o[lane] = acc0 * inv;
+    if (DH > 32) o[32 + lane] = acc1 * inv;
+  } else {
+    for (int d = lane; d < dh; d += 32) {
+      const float* vr = kv + p.v_off + d;
+      float acc = 0.f;
+      for (int j = 0; j < p.k; ++j) acc = fmaf(w[j], __ldg(vr + j * p.ld_kv), acc);
+      o[d] = acc * inv;
+    }
   }
 }
 

@@ -114,6 +114,9 @@ def main() -> None:
 
     def ctas(m, n, nz):  # the host's tile-width rule (consumer_host.cuh: consumer_linear)
         c128, c256 = mt(m) * ((n + 127) // 128) * nz, mt(m) * ((n + 255) // 256) * nz
+        if c128 * 6 <= sms:  # split-K clusters: 4 CTAs per 32-column tile
+            tiles = mt(m) * ((n + 31) // 32) * nz
+            return (4 if tiles * 4 <= sms else 2) * tiles
         return c256 if -(-c256 // sms) * 48 < -(-c128 // sms) * 32 else c128
 
     grids = [ctas(M33, 512, 1), ctas(M33, 512, 1), ctas(M33, 768, 1), ctas(Bk, 3072, 2)] \
