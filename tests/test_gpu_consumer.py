@@ -116,3 +116,27 @@ def test_consumer_argument_errors():
         NeighbourConsumer(to_torch(sds[0]), bad, to_torch(sds[2]), heads=4, device=0)
     with pytest.raises(ValueError):
         NeighbourConsumer(to_torch(sds[0]), to_torch(sds[1]), to_torch(sds[2]), heads=5, device=0)
+
+
+def test_retrieve_and_consume_in_one_call_matches_the_oracle_pipeline():
+    # src/trainer.py:53-69: normalise a copy for the search, gather, img2text, two CrossFormers
+    from keds_b200 import retrieval as kr
+    from oracle import knn_oracle as orc
+
+    sds = corc.random_state_dicts(768, 512, 768, 2, 3, 8, 64, seed=21)
+    rng = np.random.default_rng(77)
+    n, B, k = 20000, 48, 16
+    base_img = rng.standard_normal((n, 768)).astype(np.float32)
+    base_img /= np.linalg.norm(base_img, axis=1, keepdims=True)
+    base_txt = (0.6 * base_img + 0.4 * rng.standard_normal((n, 768)).astype(np.float32) / np.sqrt(768)).astype(np.float32)
+    base_txt /= np.linalg.norm(base_txt, axis=1, keepdims=True)
+    feat = (2.5 * rng.standard_normal((B, 768))).astype(np.float32)      # un-normalised on purpose
+    kb = kr.KnowledgeBase(torch.from_numpy(base_img), torch.from_numpy(base_txt), [str(i) for i in range(n)], device=0)
+    cons = NeighbourConsumer(to_torch(sds[0]), to_torch(sds[1]), to_torch(sds[2]), heads=8, device=0)
+    got = cons.from_features(torch.from_numpy(feat).cuda(), kb, topk=k).cpu().numpy()
+    assert cons.check() > 0
+    qn = feat / np.linalg.norm(feat, axis=1, keepdims=True)
+    _, I_img = orc.search(base_img, qn, k, "l2")
+    _, I_txt = orc.search(base_txt, qn, k, "l2")
+    want = corc.consumer_tokens(sds[0], sds[1], sds[2], 8, feat, base_img, base_txt, I_img, I_txt)
+    assert np.abs(got - want).max() / np.abs(want).max() < REL_TOL
