@@ -29,24 +29,30 @@ constexpr int BN = 256;
 constexpr int BK = 64;
 constexpr int UK = 16;
 constexpr int LKEEP = 16;   // a compaction keeps scores above the LKEEP-th best seen
-constexpr int CAP = 64;     // candidate slots per (item, query)
+constexpr int CAP_MAX = 64;  // candidate slots per (item, query): 64 (CTA pair) or 32 (single CTA), see ScoreCfg
 constexpr int CHUNK = 32;   // TMEM columns per tcgen05.ld
 constexpr int SCORE_THREADS = 192;
 constexpr uint32_t Q_STAGE_BYTES = BM * BK * 2;
-constexpr uint32_t CAND_WARP_BYTES = CAP * 32 * 8;
 constexpr uint32_t TMEM_COLS = 512;
 
 template <bool kPair>
 struct ScoreCfg {
-  static constexpr int kStages = kPair ? 4 : 3;
+  // Single CTA (HBM-bound, one query tile): the kernel lives on bytes in flight, so the candidate
+  // slots are cut to 32 per query (32 KB) to make room for a fourth 48-KB stage; the slot count
+  // is then checked every 8 scores. CTA pair (compute-bound): 64 slots, checked every 32 scores --
+  // compactions are what its epilogue can least afford.
+  static constexpr int kStages = 4;
+  static constexpr int kCap = kPair ? 64 : 32;
+  static constexpr int kAppend = kPair ? 32 : 8;
+  static constexpr uint32_t kCandWarpBytes = kCap * 32 * 8;
   static constexpr int kRowsPerCta = kPair ? BN / 2 : BN;           // row-tile rows this CTA loads
   static constexpr uint32_t kXBytes = kRowsPerCta * BK * 2;
   static constexpr uint32_t kStageBytes = Q_STAGE_BYTES + kXBytes;  // 48 KB / 32 KB
   // dynamic shared memory map (offsets from a 1024-aligned base)
   static constexpr uint32_t kOffCand = kStages * kStageBytes;
-  static constexpr uint32_t kOffBias = kOffCand + 4 * CAND_WARP_BYTES;
+  static constexpr uint32_t kOffBias = kOffCand + 4 * kCandWarpBytes;
   static constexpr uint32_t kOffBars = kOffBias + 2 * BN * 4;
-  static constexpr uint32_t kSmemBytes = kOffBars + 128 + 1024;     // + alignment slack
+  static constexpr uint32_t kSmemBytes = kOffBars + 256 + 768;      // barriers + alignment slack (227 KB exactly for the single-CTA variant)
 };
 constexpr uint32_t SCORE_SMEM_BYTES = ScoreCfg<false>::kSmemBytes;
 constexpr uint32_t SCORE_PAIR_SMEM_BYTES = ScoreCfg<true>::kSmemBytes;
@@ -109,6 +115,7 @@ struct CandState {
 // Per-thread compaction of one query's candidate slots (all 32 lanes of a warp run it in lock
 // step on their own columns of the warp's interleaved buffer): find the LKEEP-th best score with
 // a register sorting network, raise theta to it, keep only strictly better entries.
+template <int CAP>
 __device__ __noinline__ CandState compact_candidates(uint32_t slot0, int cnt, float theta) {
   float s[CAP];
 #pragma unroll
@@ -155,13 +162,23 @@ k_score_topk(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (sbase - smem_u32(smem_raw));
 
+  {
+    // the layout fills the 227 KB exactly up to the alignment slack: refuse to run rather than
+    // overrun if the dynamic window starts less aligned than assumed
+    uint32_t dyn;
+    asm volatile("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
+    if (sbase - smem_u32(smem_raw) + (Cfg::kSmemBytes - 768u) > dyn) {
+      if (threadIdx.x == 0) atomicCAS(p.err, 0u, 0x900u);
+      return;
+    }
+  }
   const uint32_t bars = sbase + Cfg::kOffBars;
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (NSTAGE + s); };
   auto tfull_bar = [&](int a) { return bars + 8u * (2 * NSTAGE + a); };
   auto tempty_bar = [&](int a) { return bars + 8u * (2 * NSTAGE + 2 + a); };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + Cfg::kOffBars + 104);
-  volatile uint32_t* dead = reinterpret_cast<volatile uint32_t*>(gbase + Cfg::kOffBars + 108);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + Cfg::kOffBars + 200);
+  volatile uint32_t* dead = reinterpret_cast<volatile uint32_t*>(gbase + Cfg::kOffBars + 204);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -283,7 +300,9 @@ k_score_topk(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
     // ------------------------------------------------------------ epilogue (lane == query)
     const int quad = warp & 3;                // TMEM lane quadrant this warp may read
     const int q_local = quad * 32 + lane;
-    const uint32_t wbuf = sbase + Cfg::kOffCand + static_cast<uint32_t>(warp - 2) * CAND_WARP_BYTES;
+    constexpr int CAP = Cfg::kCap;
+    constexpr int APPEND = Cfg::kAppend;
+    const uint32_t wbuf = sbase + Cfg::kOffCand + static_cast<uint32_t>(warp - 2) * Cfg::kCandWarpBytes;
     const uint32_t slot0 = wbuf + lane * 8;   // entry e of this lane lives at slot0 + e * 256
     float* sbias = reinterpret_cast<float*>(gbase + Cfg::kOffBias);
     const int et = threadIdx.x - 64;          // 0..127 among epilogue threads
@@ -337,19 +356,25 @@ k_score_topk(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
             for (int j = 0; j < CHUNK; ++j)
               if (static_cast<int>(idx0) + j < n_rows) drow[idx0 + j] = __uint_as_float(v[j]);
           }
-          uint32_t wptr = slot0 + static_cast<uint32_t>(cnt) * 256u;
+          // APPEND scores at a time, then make sure the next APPEND still fit. (The slot buffers
+          // are small on purpose: 32 KB instead of 64 KB buys a fourth TMA stage, and the kernel
+          // lives on bytes in flight.)
 #pragma unroll
-          for (int j = 0; j < CHUNK; ++j) {
-            if (__uint_as_float(v[j]) > theta) {
-              sts64(wptr, v[j], idx0 + j);
-              wptr += 256u;
+          for (int g = 0; g < CHUNK; g += APPEND) {
+            uint32_t wptr = slot0 + static_cast<uint32_t>(cnt) * 256u;
+#pragma unroll
+            for (int j = g; j < g + APPEND; ++j) {
+              if (__uint_as_float(v[j]) > theta) {
+                sts64(wptr, v[j], idx0 + j);
+                wptr += 256u;
+              }
             }
-          }
-          cnt = static_cast<int>((wptr - slot0) >> 8);
-          if (__any_sync(0xffffffffu, cnt > CAP - CHUNK)) {
-            const CandState st = compact_candidates(slot0, cnt, theta);
-            cnt = st.cnt;
-            theta = st.theta;
+            cnt = static_cast<int>((wptr - slot0) >> 8);
+            if (__any_sync(0xffffffffu, cnt > CAP - APPEND)) {
+              const CandState st = compact_candidates<CAP>(slot0, cnt, theta);
+              cnt = st.cnt;
+              theta = st.theta;
+            }
           }
         }
         // accumulator drained: hand the TMEM buffer back to the MMA warp (pair: of the leader CTA)
@@ -366,7 +391,7 @@ k_score_topk(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
       // [(db, s, qt)][query][LKEEP] {score bits, row id}, padded with {-inf, ~0}; the re-rank
       // kernel reads a slice with a single coalesced half-warp load.
       if (__any_sync(0xffffffffu, cnt >= LKEEP)) {
-        const CandState st = compact_candidates(slot0, cnt, theta);
+        const CandState st = compact_candidates<CAP>(slot0, cnt, theta);
         cnt = st.cnt;
         theta = st.theta;
       }
