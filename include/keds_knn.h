@@ -225,6 +225,25 @@ int keds_consumer_check(keds_consumer_t* c, void* cuda_stream, int64_t* launches
 int keds_consumer_set_debug(keds_consumer_t* c, int enable);
 int keds_consumer_debug_timeline(keds_consumer_t* c, int launch, uint64_t* out, int64_t n_ctas);
 
+/* ---- contrastive loss over the gathered features (forward + backward) ---------
+ * The step that follows the retrieval path in the training loop (src/trainer.py:85-135,164):
+ *   logits = logit_scale * I_all @ T_all.t()
+ *   loss   = (CrossEntropy(logits, arange(N)) + CrossEntropy(logits.t(), arange(N))) / 2
+ * I_all, T_all: [N][d] float32 device, the image / text features of ALL ranks after the all-gather
+ * (rows [row0, row0 + n_local) are this rank's own); logit_scale: 1 float, device (no host sync).
+ * Outputs (device): loss (1 float), and -- both
+ * or neither -- dI_local, dT_local [n_local][d] = d loss / d (this rank's rows), plus dscale
+ * (1 float, nullable) = d loss / d logit_scale. Products run on tf32 tensor cores with a hi/lo
+ * operand split (fp32-class accuracy). N and d multiples of 4. Asynchronous on cuda_stream. */
+typedef struct keds_clip_loss keds_clip_loss_t;
+int keds_clip_loss_create(int device, keds_clip_loss_t** out);
+void keds_clip_loss_free(keds_clip_loss_t* h);
+int keds_clip_loss_forward_backward(keds_clip_loss_t* h, const float* I_all, const float* T_all, int64_t N,
+                                    int d, int64_t row0, int64_t n_local, const float* logit_scale, float* loss,
+                                    float* dI_local, float* dT_local, float* dscale, void* cuda_stream);
+/* synchronise the stream and report a device-side pipeline error, if any */
+int keds_clip_loss_check(keds_clip_loss_t* h, void* cuda_stream);
+
 /* ---- diagnostics ------------------------------------------------------------------------------
  * Approximate (bf16 tensor-core) scores of q against every row: out [nq][ntotal] device float32.
  * Test hook for the GEMM alone; not a product path. */

@@ -99,6 +99,13 @@ SIGNATURES = {
     "keds_consumer_check": (C.c_int, [_vp, _vp, C.POINTER(C.c_int64)]),
     "keds_consumer_set_debug": (C.c_int, [_vp, C.c_int]),
     "keds_consumer_debug_timeline": (C.c_int, [_vp, C.c_int, _vp, C.c_int64]),
+    "keds_clip_loss_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
+    "keds_clip_loss_free": (None, [_vp]),
+    "keds_clip_loss_forward_backward": (
+        C.c_int,
+        [_vp, _vp, _vp, C.c_int64, C.c_int, C.c_int64, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp],
+    ),
+    "keds_clip_loss_check": (C.c_int, [_vp, _vp]),
     "keds_debug_scores": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp]),
     "keds_index_set_eps_scale": (C.c_int, [_vp, C.c_float]),
     "keds_index_set_pdl": (C.c_int, [_vp, C.c_int]),

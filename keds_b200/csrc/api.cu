@@ -1081,3 +1081,5 @@ int keds_label_hits(const int64_t* I, int64_t nq, int kmax, const int64_t* label
 
 // keds_consumer_*: the neighbour consumer (uses the helpers above)
 #include "consumer_host.cuh"
+// keds_clip_loss_*: the contrastive loss over the gathered features
+#include "clip_loss_host.cuh"

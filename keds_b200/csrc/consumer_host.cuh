@@ -49,7 +49,7 @@ struct keds_consumer {
   struct AMap {  // TMA descriptor of an activation operand: a pure function of (base, rows, K, ld)
     const float* base;
     int64_t rows, ld;
-    int K;
+    int K, box_rows;
     CUtensorMap tm;
   };
   std::vector<AMap> amaps;
@@ -89,33 +89,36 @@ void consumer_slot_dims(const keds_consumer* c, int kind, int layer, int* out, i
   }
 }
 
+// Descriptors of operands that live in scratch buffers are cached: a descriptor is a pure function
+// of (base, rows, K, ld, box rows), so after the first call of a given shape every lookup hits
+// (encoding costs ~5 us of host time per descriptor, more than the kernels they feed).
+int consumer_cached_map(keds_consumer* c, const float* A, int64_t rows, int K, int64_t ld, int box_rows,
+                        CUtensorMap* out) {
+  for (const auto& e : c->amaps)
+    if (e.base == A && e.rows == rows && e.K == K && e.ld == ld && e.box_rows == box_rows) {
+      *out = e.tm;
+      return 0;
+    }
+  keds_consumer::AMap e;
+  e.base = A;
+  e.rows = rows;
+  e.K = K;
+  e.ld = ld;
+  e.box_rows = box_rows;
+  CKS(encode_f32_map(&e.tm, A, rows, K, ld, box_rows));
+  if (c->amaps.size() >= 256) c->amaps.clear();
+  c->amaps.push_back(e);
+  *out = e.tm;
+  return 0;
+}
+
 // C[z] = act(A[z] W[z]^T + b[z]) for z < nz; A[z]: [M][K] with lda floats between rows
 int consumer_linear(keds_consumer* c, const float* A0, const float* A1, int64_t lda, int64_t M,
                     const LinearW* W0, const LinearW* W1, int relu, float* C0, float* C1, int64_t ldc,
                     int nz, cudaStream_t st) {
-  // descriptors of the activation operands are cached: the operands are this handle's scratch
-  // buffers, so after the first call of a given (B, k) every lookup hits (encoding costs ~5 us of
-  // host time per descriptor, more than the kernels they feed)
-  auto cached_map = [&](const float* A, int64_t rows, int K, CUtensorMap* out) -> int {
-    for (const auto& e : c->amaps)
-      if (e.base == A && e.rows == rows && e.K == K && e.ld == lda) {
-        *out = e.tm;
-        return 0;
-      }
-    keds_consumer::AMap e;
-    e.base = A;
-    e.rows = rows;
-    e.K = K;
-    e.ld = lda;
-    CKS(encode_f32_map(&e.tm, A, rows, K, lda));
-    if (c->amaps.size() >= 256) c->amaps.clear();
-    c->amaps.push_back(e);
-    *out = e.tm;
-    return 0;
-  };
   CUtensorMap ta0, ta1;
-  CKS(cached_map(A0, M, W0->in, &ta0));
-  if (nz > 1) CKS(cached_map(A1, M, W1->in, &ta1)); else ta1 = ta0;
+  CKS(consumer_cached_map(c, A0, M, W0->in, lda, LIN_M, &ta0));
+  if (nz > 1) CKS(consumer_cached_map(c, A1, M, W1->in, lda, LIN_M, &ta1)); else ta1 = ta0;
   LinearParams p;
   memset(&p, 0, sizeof p);
   p.M = static_cast<int>(M);

@@ -120,3 +120,19 @@ def test_consumer_oracle_matches_the_reference_modules(golden_dir):
     assert tokens.shape == g["tokens"].shape == (5, 3, 40)
     # the reference computed in float32, the oracle in float64
     assert np.abs(tokens - g["tokens"]).max() < 2e-6 * max(1.0, np.abs(g["tokens"]).max())
+
+
+# ------------------------------------------------------------------ gathered contrastive loss (§8 f3)
+def test_clip_loss_oracle_matches_torch_autograd_of_the_reference_statements(golden_dir):
+    from oracle import clip_loss_oracle as lorc
+
+    g = np.load(os.path.join(golden_dir, "clip_loss.npz"))
+    world, scale = int(g["world"]), float(g["scale"])
+    I_all = np.concatenate([g[f"I{r}"] for r in range(world)])      # rank order (the reference: local first)
+    T_all = np.concatenate([g[f"T{r}"] for r in range(world)])
+    B = g["I0"].shape[0]
+    for r in range(world):
+        loss, dI, dT, ds = lorc.clip_loss(I_all, T_all, scale, row0=r * B, n_local=B)
+        assert abs(loss - float(g[f"loss{r}"])) < 1e-12
+        assert np.abs(dI - g[f"dI{r}"]).max() < 1e-12 and np.abs(dT - g[f"dT{r}"]).max() < 1e-12
+        assert abs(ds - float(g[f"dscale{r}"])) < 1e-12
