@@ -49,6 +49,7 @@ int keds_clip_loss_create(int device, keds_clip_loss_t** out) {
                             (int)LinCfg<128>::kSmemBytes));
     CK(cudaFuncSetAttribute(k_linear_tf32<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)LinCfg<256>::kSmemBytes));
+    CK(cudaFuncSetAttribute(k_linear_tf32_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PL_SMEM_BYTES));
     CK(cudaFuncSetAttribute(k_linear_tf32_splitk<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SK_SMEM_BYTES));
     CK(cudaFuncSetAttribute(k_linear_tf32_splitk<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SK_SMEM_BYTES));
     CK(cudaDeviceGetAttribute(&h->lin.num_sms, cudaDevAttrMultiProcessorCount, device));

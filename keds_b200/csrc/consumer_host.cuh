@@ -131,6 +131,7 @@ int consumer_linear(keds_consumer* c, const float* A0, const float* A1, int64_t 
   p.C[1] = C1;
   p.ldc = ldc;
   p.err = c->err.as<uint32_t>();
+  p.nz = nz;
   // tile width: fewer, wider tiles re-read A half as often but fill the SMs worse; pick by waves x
   // bytes per k-block (32 KB for 128 columns, 48 KB for 256)
   const long long mt = (M + LIN_M - 1) / LIN_M;
@@ -160,6 +161,15 @@ int consumer_linear(keds_consumer* c, const float* A0, const float* A1, int64_t 
   if (c->debug && c->dbg_launch < CONS_DBG_LAUNCHES && grid.x * grid.y * grid.z <= (unsigned)CONS_DBG_CTAS)
     p.tdump = c->tdump.as<unsigned long long>() + static_cast<size_t>(c->dbg_launch) * CONS_DBG_CTAS * 5;
   c->dbg_launch++;
+  // more than two waves of wide tiles: one persistent CTA per SM with the epilogue of a tile
+  // hidden under the main loop of the next
+  if (wide && c256 > 2 * sms) {
+    p.tdump = nullptr;  // (no per-CTA stamps: one CTA walks many tiles)
+    CKS(launch_k(true, k_linear_tf32_persistent, dim3(static_cast<unsigned>(sms)), dim3(PL_THREADS), PL_SMEM_BYTES,
+                 st, ta0, ta1, W0->tm, nz > 1 ? W1->tm : W0->tm, p));
+    c->launches++;
+    return 0;
+  }
   if (wide)
     CKS(launch_k(true, k_linear_tf32<256>, grid, dim3(LIN_THREADS), LinCfg<256>::kSmemBytes, st, ta0, ta1,
                  W0->tm, nz > 1 ? W1->tm : W0->tm, p));
@@ -259,6 +269,8 @@ int keds_consumer_finalize(keds_consumer_t* c) {
                             (int)LinCfg<128>::kSmemBytes));
     CK(cudaFuncSetAttribute(k_linear_tf32<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)LinCfg<256>::kSmemBytes));
+    CK(cudaFuncSetAttribute(k_linear_tf32_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)PL_SMEM_BYTES));
     CK(cudaFuncSetAttribute(k_linear_tf32_splitk<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)SK_SMEM_BYTES));
     CK(cudaFuncSetAttribute(k_linear_tf32_splitk<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,

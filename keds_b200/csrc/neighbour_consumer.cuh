@@ -43,6 +43,7 @@ struct LinearParams {
   long long ldc;          // floats between rows of C
   uint32_t* err;          // device error word (0 = ok)
   unsigned long long* tdump;  // diagnostics: per CTA {start, prologue done, dependency met, accumulator ready, end} ns
+  int nz;                 // problems (k_linear_tf32_persistent walks a flat tile list)
 };
 
 template <int BN>
@@ -210,6 +211,197 @@ k_linear_tf32(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, LIN_N);
+  }
+}
+
+// The same product for MANY tiles (more than two waves of CTAs: the key/value projection of the
+// neighbour consumer). One CTA per SM walks a flat list of 128 x 256 tiles; two 256-column TMEM
+// accumulators let the epilogue of tile t run under the main loop of tile t + 1, and CTA launch /
+// retire costs are paid once. Tile order: the N index runs fastest, so concurrently running CTAs
+// share their A rows in L2.
+constexpr int PL_BN = 256;
+constexpr int PL_STAGES = 4;
+constexpr int PL_THREADS = 192;  // TMA warp, MMA warp, 4 epilogue warps (hidden under the next main loop)
+constexpr uint32_t PL_STAGE_BYTES = LIN_A_BYTES + PL_BN * LIN_K * 4;   // 48 KB
+constexpr uint32_t PL_OFF_TR = PL_STAGES * PL_STAGE_BYTES;             // 4 warps x [32][33] fp32
+constexpr uint32_t PL_OFF_BIAS = PL_OFF_TR + 4 * 32 * 33 * 4;
+constexpr uint32_t PL_OFF_BARS = PL_OFF_BIAS + 2 * PL_BN * 4;
+constexpr uint32_t PL_SMEM_BYTES = PL_OFF_BARS + 256 + 1024;
+
+__global__ void __launch_bounds__(PL_THREADS, 1)
+k_linear_tf32_persistent(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_a1,
+                         const __grid_constant__ CUtensorMap tm_w0, const __grid_constant__ CUtensorMap tm_w1,
+                         const LinearParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (sbase - smem_u32(smem_raw));
+  const uint32_t bars = sbase + PL_OFF_BARS;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (PL_STAGES + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * PL_STAGES + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * PL_STAGES + 2 + a); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + PL_OFF_BARS + 200);
+  volatile uint32_t* dead = reinterpret_cast<volatile uint32_t*>(gbase + PL_OFF_BARS + 204);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nt = (p.N + PL_BN - 1) / PL_BN;
+  const int mt = (p.M + LIN_M - 1) / LIN_M;
+  const int tiles = nt * mt * p.nz;
+  const int kblocks = (p.K + LIN_K - 1) / LIN_K;
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&tm_a0);
+    prefetch_tensormap(&tm_w0);
+    if (p.nz > 1) {
+      prefetch_tensormap(&tm_a1);
+      prefetch_tensormap(&tm_w1);
+    }
+    for (int s = 0; s < PL_STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);
+    }
+    *dead = 0;
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), 2 * PL_BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  griddep_wait();  // A is the previous kernel's output
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const int n0 = (t % nt) * PL_BN, m0 = ((t / nt) % mt) * LIN_M, z = t / (nt * mt);
+        const CUtensorMap* tm_a = z == 0 ? &tm_a0 : &tm_a1;
+        const CUtensorMap* tm_w = z == 0 ? &tm_w0 : &tm_w1;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u, dead, p.err, 0x900u + stage);
+          const uint32_t sa = sbase + stage * PL_STAGE_BYTES;
+          mbar_arrive_expect_tx(full_bar(stage), PL_STAGE_BYTES);
+          tma_load_2d(sa, tm_a, full_bar(stage), kb * LIN_K, m0, kEvictNormal);
+#pragma unroll
+          for (int wb = 0; wb < PL_BN / LIN_WBOX; ++wb)
+            tma_load_2d(sa + LIN_A_BYTES + wb * (LIN_WBOX * LIN_K * 4), tm_w, full_bar(stage), kb * LIN_K,
+                        n0 + wb * LIN_WBOX, kEvictLast);
+          if (++stage == PL_STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = idesc_tf32_f32(LIN_M, PL_BN);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u, dead, p.err, 0x910u + acc);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * PL_BN);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(full_bar(stage), phase, dead, p.err, 0x920u + stage);
+          tc_fence_after();
+          const uint32_t sa = sbase + stage * PL_STAGE_BYTES;
+          const uint64_t adesc = smem_desc_sw128(sa);
+          const uint64_t bdesc = smem_desc_sw128(sa + LIN_A_BYTES);
+#pragma unroll
+          for (int k = 0; k < LIN_K / LIN_UK; ++k)
+            umma_tf32(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(empty_bar(stage));
+          if (++stage == PL_STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(tfull_bar(acc));
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    float* tr = reinterpret_cast<float*>(gbase + PL_OFF_TR) + (warp - 2) * (32 * 33);
+    float* sbias_all = reinterpret_cast<float*>(gbase + PL_OFF_BIAS);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+      const int n0 = (t % nt) * PL_BN, m0 = ((t / nt) % mt) * LIN_M, z = t / (nt * mt);
+      const int row0 = m0 + quad * 32;
+      const float* bias = p.bias[z];
+      float* cbase = p.C[z] + n0;
+      float* sbias = sbias_all + acc * PL_BN;
+      for (int j = threadIdx.x - 64; j < PL_BN; j += 128)
+        sbias[j] = (bias != nullptr && n0 + j < p.N) ? __ldg(bias + n0 + j) : 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(tfull_bar(acc), acc_phase, dead, p.err, 0x930u + acc);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * PL_BN);
+      const bool vec_ok = (p.ldc & 3) == 0 && (p.N & 3) == 0 && (reinterpret_cast<uintptr_t>(p.C[z]) & 15) == 0;
+#pragma unroll 1
+      for (int ch = 0; ch < PL_BN / 32; ++ch) {
+        uint32_t v[32];
+        tmem_ld32(taddr + ch * 32, v);
+        tmem_ld_wait(v);
+        const int c0 = n0 + ch * 32;
+        if (c0 >= p.N) break;
+        float4 bv[8];
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) bv[j4] = reinterpret_cast<const float4*>(sbias + ch * 32)[j4];
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float x0 = __uint_as_float(v[4 * j4 + 0]) + bv[j4].x, x1 = __uint_as_float(v[4 * j4 + 1]) + bv[j4].y;
+          const float x2 = __uint_as_float(v[4 * j4 + 2]) + bv[j4].z, x3 = __uint_as_float(v[4 * j4 + 3]) + bv[j4].w;
+          tr[lane * 33 + 4 * j4 + 0] = p.relu ? fmaxf(x0, 0.f) : x0;
+          tr[lane * 33 + 4 * j4 + 1] = p.relu ? fmaxf(x1, 0.f) : x1;
+          tr[lane * 33 + 4 * j4 + 2] = p.relu ? fmaxf(x2, 0.f) : x2;
+          tr[lane * 33 + 4 * j4 + 3] = p.relu ? fmaxf(x3, 0.f) : x3;
+        }
+        __syncwarp();
+        if (vec_ok) {
+          const int cc = (lane & 7) * 4;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + (lane >> 3);
+            const float* s = tr + rr * 33 + cc;
+            if (row0 + rr < p.M && c0 + cc < p.N)
+              *reinterpret_cast<float4*>(cbase + static_cast<long long>(row0 + rr) * p.ldc + ch * 32 + cc) =
+                  make_float4(s[0], s[1], s[2], s[3]);
+          }
+        } else {
+          for (int rr = 0; rr < 32; ++rr)
+            if (row0 + rr < p.M && c0 + lane < p.N)
+              cbase[static_cast<long long>(row0 + rr) * p.ldc + ch * 32 + lane] = tr[rr * 33 + lane];
+        }
+        __syncwarp();
+      }
+      // accumulator drained: the MMA warp may reuse it two tiles from now
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * PL_BN);
   }
 }
 

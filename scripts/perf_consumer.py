@@ -128,6 +128,9 @@ def main() -> None:
             tl.append({"launch": i, "ctas": gsz, "skipped": "more CTAs than the debug buffer holds"})
             continue
         t = cons.debug_timeline(i, gsz).astype(np.int64)
+        if not t[:, 0].any():
+            tl.append({"launch": i, "ctas": gsz, "skipped": "persistent kernel: no per-CTA stamps"})
+            continue
         t_first = int(t[:, 0].min()) if t_first is None else t_first
         if i == 3:  # the key/value projection: per-CTA (start, end) relative to the launch's first CTA
             res["kv_cta_us"] = ((t[:, [0, 4]] - t[:, 0].min()) / 1e3).round(2).tolist()
