@@ -116,6 +116,55 @@ def test_config1_4096_queries_vs_50k_rows():
     assert st["exact_only"] == 0 and st["n_flagged"][0] < 64   # the tensor-core path answered
 
 
+def test_more_queries_than_one_pass_holds():
+    """Batches above 16,384 queries (config 3 has 65,536) are cut into passes inside one call: the
+    seams must not show, for one database and for the fused two-database search."""
+    db, db2 = unit(6000, 64, 301), unit(6000, 64, 302)
+    q = unit(16384 + 700, 64, 303)
+    ix, ix2 = build(db, "l2"), build(db2, "l2")
+    check(ix, db, q, 8, "l2")
+    (Da, Ia), (Db, Ib) = search2(ix, ix2, torch.from_numpy(q).cuda(), 8)
+    for D, I, base in ((Da, Ia, db), (Db, Ib, db2)):
+        Dr, Ir = orc.search(base, q, 8, "l2")
+        c = orc.compare_topk(Dr, Ir, D.cpu().numpy(), I.cpu().numpy(), base, q, "l2", TIE_GAP, D_TOL)
+        assert c["ok"], c
+
+
+def test_two_indices_searched_from_two_threads_on_their_own_streams():
+    """One search in flight per handle, but handles are independent: two host threads, two CUDA
+    streams, two indices at once (the ctypes calls release the GIL)."""
+    import threading
+
+    dbs = [unit(30000, 256, 400 + i) for i in range(2)]
+    qs = [unit(200, 256, 410 + i) for i in range(2)]
+    ixs = [build(db, "ip") for db in dbs]
+    res, errs = [None, None], []
+
+    def work(i):
+        try:
+            s = torch.cuda.Stream()
+            with torch.cuda.stream(s):
+                qd = torch.from_numpy(qs[i]).cuda()
+                for _ in range(8):
+                    D, I = ixs[i].search(qd, 16)
+                s.synchronize()
+            res[i] = (D.cpu().numpy(), I.cpu().numpy())
+        except Exception as e:  # pragma: no cover
+            errs.append(e)
+
+    ths = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    assert not errs, errs
+    for i in range(2):
+        Dr, Ir = orc.search(dbs[i], qs[i], 16, "ip")
+        c = orc.compare_topk(Dr, Ir, res[i][0], res[i][1], dbs[i], qs[i], "ip", TIE_GAP, D_TOL)
+        assert c["ok"], c
+        assert ixs[i].last_stats()["err_word"] == 0
+
+
 def test_odd_dimension_and_unaligned_rows():
     db, q = unit(700, 50, 3), unit(33, 50, 4)   # d = 50: scalar fp32 path, padded k-block
     check(build(db, "ip"), db, q, 10, "ip")
