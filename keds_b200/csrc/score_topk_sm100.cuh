@@ -29,7 +29,6 @@ constexpr int BN = 256;
 constexpr int BK = 64;
 constexpr int UK = 16;
 constexpr int LKEEP = 16;   // a compaction keeps scores above the LKEEP-th best seen
-constexpr int CAP_MAX = 64;  // candidate slots per (item, query): 64 (CTA pair) or 32 (single CTA), see ScoreCfg
 constexpr int CHUNK = 32;   // TMEM columns per tcgen05.ld
 constexpr int SCORE_THREADS = 192;
 constexpr uint32_t Q_STAGE_BYTES = BM * BK * 2;
