@@ -137,13 +137,22 @@ __device__ __noinline__ CandState compact_candidates(uint32_t slot0, int cnt, fl
     }
   }
   theta = fmaxf(theta, s[LKEEP - 1]);
+  // keep the entries above theta, in place and in order: every entry is in registers before the
+  // first store; positions come from the keep mask (see the append loop for why)
   int w = 0;
-  for (int e = 0; e < cnt; ++e) {
-    const uint2 en = lds64(slot0 + e * 256);
-    if (__uint_as_float(en.x) > theta) {
-      sts64(slot0 + w * 256, en.x, en.y);
-      ++w;
+#pragma unroll
+  for (int e0 = 0; e0 < CAP; e0 += 16) {
+    uint2 en[16];
+    uint32_t m = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      en[i] = lds64(slot0 + (e0 + i) * 256);
+      m |= (e0 + i < cnt && __uint_as_float(en[i].x) > theta) ? (1u << i) : 0u;
     }
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (m & (1u << i)) sts64(slot0 + (w + __popc(m & ((1u << i) - 1u))) * 256, en[i].x, en[i].y);
+    w += __popc(m);
   }
   CandState r;
   r.cnt = w;
@@ -360,13 +369,21 @@ k_score_topk(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
           // lives on bytes in flight.)
 #pragma unroll
           for (int g = 0; g < CHUNK; g += APPEND) {
+            // Eight slot addresses first (a chain of selects in eight DIFFERENT registers), then the
+            // eight predicated stores. Written the obvious way -- store, bump one pointer, store --
+            // every bump waits ~20 cycles for the store in front of it to have read that register
+            // (a write-after-read hazard on a memory instruction), 25 cycles per score in all.
             uint32_t wptr = slot0 + static_cast<uint32_t>(cnt) * 256u;
 #pragma unroll
-            for (int j = g; j < g + APPEND; ++j) {
-              if (__uint_as_float(v[j]) > theta) {
-                sts64(wptr, v[j], idx0 + j);
-                wptr += 256u;
-              }
+            for (int j0 = g; j0 < g + APPEND; j0 += 8) {
+              uint32_t a[9];
+              a[0] = wptr;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) a[i + 1] = a[i] + (__uint_as_float(v[j0 + i]) > theta ? 256u : 0u);
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (__uint_as_float(v[j0 + i]) > theta) sts64(a[i], v[j0 + i], idx0 + j0 + i);
+              wptr = a[8];
             }
             cnt = static_cast<int>((wptr - slot0) >> 8);
             if (__any_sync(0xffffffffu, cnt > CAP - APPEND)) {
