@@ -126,11 +126,12 @@ k_exact_select(const ExactParams p) {
     for (int r = tid; r < p.k; r += blockDim.x) top_id[r] = 0xFFFFFFFFu;
     // k-th largest rank score: 4 x 8-bit radix passes over the score row (global / L2)
     unsigned int prefix = 0, mask = 0;
-    int need = keff;
+    int need = keff, n_eq = 0;
     for (int shift = 24; shift >= 0; shift -= 8) {
       for (int i = tid; i < 256; i += blockDim.x) hist[i] = 0;
       __syncthreads();
-      for (long long i = tid; i < n; i += blockDim.x) {
+#pragma unroll 8
+      for (long long i = tid; i < n; i += blockDim.x) {  // unrolled: eight loads in flight per thread
         float v = sc[i];
         if (v == 0.f) v = 0.f;
         const unsigned int key = f32_to_key(v);
@@ -141,11 +142,27 @@ k_exact_select(const ExactParams p) {
       prefix |= bcast[0] << shift;
       mask |= 255u << shift;
       need = static_cast<int>(bcast[1]);
+      if (shift == 0) n_eq = static_cast<int>(hist[bcast[0]]);  // rows scoring exactly the k-th value
       __syncthreads();
     }
     const unsigned int kth = prefix;  // `need` rows equal to kth are wanted, lowest ids first
     if (tid < 4) counters[tid] = 0;
     __syncthreads();
+    if (n_eq == need) {
+      // the usual case: every row that ties with the k-th value is wanted, so nothing has to be
+      // taken in id order -- one pass, no block barriers (the rank sort below orders the output)
+#pragma unroll 4
+      for (long long i = tid; i < n; i += blockDim.x) {
+        float v = sc[i];
+        if (v == 0.f) v = 0.f;
+        const unsigned int key = f32_to_key(v);
+        if (key >= kth) {
+          const int pos = key > kth ? atomicAdd(&counters[0], 1) : (keff - need) + atomicAdd(&counters[1], 1);
+          sel_key[pos] = key;
+          sel_id[pos] = static_cast<unsigned int>(i);
+        }
+      }
+    } else
     // rows strictly better than kth: any order; rows equal to kth: in id order until `need`
     for (long long base = 0; base < n; base += blockDim.x) {
       const long long i = base + tid;
