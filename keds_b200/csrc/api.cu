@@ -76,6 +76,27 @@ struct DevBuf {
   T* as() const { return static_cast<T*>(p); }
 };
 
+// page-locked host staging (the numpy-in / numpy-out path: one DMA each way instead of the driver's
+// pageable-memory staging, and no extra blocking copy for the status words)
+struct HostBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    CK(cudaHostAlloc(&p, bytes, cudaHostAllocDefault));
+    cap = bytes;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
 struct DeviceGuard {
   int prev = -1;
   bool ok = false;
@@ -159,6 +180,7 @@ struct keds_index {
   // per-call scratch (one search in flight per handle)
   DevBuf q_f32, q_bf16, qstat, cand, cand_cnt, cand_theta, flagged[2], ctrl, exact_scratch;
   DevBuf D_stage[2], I_stage[2];
+  HostBuf h_q, h_out;  // pinned staging for host-pointer calls
   CUtensorMap tm_q;
   const void* tm_q_base = nullptr;
   int64_t tm_q_rows = 0;
@@ -563,8 +585,17 @@ int search_impl(keds_index* ix[2], int n_db, const float* q, int64_t nq, int k, 
   }
   const float* qd = q;
   if (!q_dev) {
-    CKS(a->q_f32.ensure(static_cast<size_t>(nq) * a->d * 4));
-    CK(cudaMemcpyAsync(a->q_f32.p, q, static_cast<size_t>(nq) * a->d * 4, cudaMemcpyHostToDevice, st));
+    const size_t qb = static_cast<size_t>(nq) * a->d * 4;
+    CKS(a->q_f32.ensure(qb));
+    const void* src = q;
+    if (!out_dev && qb <= (size_t(64) << 20)) {
+      // host in, host out: the call synchronises before it returns, so a pinned staging buffer can
+      // be reused call after call (one real DMA instead of the driver's chunked pageable copy)
+      CKS(a->h_q.ensure(qb));
+      memcpy(a->h_q.p, q, qb);
+      src = a->h_q.p;
+    }
+    CK(cudaMemcpyAsync(a->q_f32.p, src, qb, cudaMemcpyHostToDevice, st));
     qd = a->q_f32.as<float>();
   }
   float* Dd[2] = {nullptr, nullptr};
@@ -623,11 +654,29 @@ int search_impl(keds_index* ix[2], int n_db, const float* q, int64_t nq, int k, 
     }
   }
   if (!out_dev) {
+    // results and status words into pinned memory with asynchronous copies, ONE synchronisation,
+    // then plain memcpy into the caller's arrays
+    const size_t db_ = static_cast<size_t>(nq) * k * 4, ib_ = static_cast<size_t>(nq) * k * 8;
+    const size_t per = db_ + ib_;
+    CKS(a->h_out.ensure(per * n_db + CTRL_WORDS * 4));
+    uint8_t* h = static_cast<uint8_t*>(a->h_out.p);
     for (int i = 0; i < n_db; ++i) {
-      CK(cudaMemcpyAsync(D[i], Dd[i], static_cast<size_t>(nq) * k * 4, cudaMemcpyDeviceToHost, st));
-      CK(cudaMemcpyAsync(I[i], Id[i], static_cast<size_t>(nq) * k * 8, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(h + per * i, Dd[i], db_, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(h + per * i + db_, Id[i], ib_, cudaMemcpyDeviceToHost, st));
     }
-    return finish_sync(a, st);
+    uint32_t* hc = reinterpret_cast<uint32_t*>(h + per * n_db);
+    memset(hc, 0, CTRL_WORDS * 4);
+    if (a->ctrl.p) CK(cudaMemcpyAsync(hc, a->ctrl.p, CTRL_WORDS * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (int i = 0; i < n_db; ++i) {
+      memcpy(D[i], h + per * i, db_);
+      memcpy(I[i], h + per * i + db_, ib_);
+    }
+    a->stats.n_flagged[0] = static_cast<int32_t>(hc[0]);
+    a->stats.n_flagged[1] = static_cast<int32_t>(hc[1]);
+    a->stats.err_word = hc[2];
+    if (hc[2] != 0) return fail(KEDS_ERR_KERNEL, "scoring kernel watchdog fired: error word 0x%x", hc[2]);
+    return 0;
   }
   return 0;
 }
@@ -692,6 +741,8 @@ void keds_index_free(keds_index_t* ix) {
                     &ix->flagged[1], &ix->ctrl, &ix->exact_scratch, &ix->D_stage[0], &ix->D_stage[1],
                     &ix->I_stage[0], &ix->I_stage[1], &ix->timing};
   for (DevBuf* b : bufs) b->release();
+  ix->h_q.release();
+  ix->h_out.release();
   for (cudaEvent_t e : ix->prof_ev) cudaEventDestroy(e);
   delete ix;
 }
