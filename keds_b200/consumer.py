@@ -95,6 +95,8 @@ class NeighbourConsumer:
         if b is not None:
             b = b.detach().to(dtype=torch.float32).contiguous()
             bp = b.data_ptr()
+        if W.is_cuda:  # the native copy runs on the legacy stream: finish whatever produced W / b first
+            torch.cuda.current_stream(W.device).synchronize()
         _capi.check(self._lib.keds_consumer_set_linear(self._h, kind, stack, layer, W.data_ptr(), bp,
                                                        int(W.shape[0]), int(W.shape[1])))
 

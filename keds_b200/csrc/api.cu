@@ -152,6 +152,17 @@ bool is_device_ptr(const void* p) {
   return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
+// device that owns a device pointer (-1: not device memory)
+int device_of(const void* p) {
+  if (!p) return -1;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return -1;
+  }
+  return (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) ? a.device : -1;
+}
+
 constexpr int CTRL_WORDS = 8;  // [0],[1] n_flagged per db, [2] err word, [3],[4] grid barriers
 constexpr int S_MAX = 192;
 constexpr size_t CAND_BUDGET = size_t(1) << 30;
@@ -303,13 +314,14 @@ Plan make_plan(const keds_index* ix, int n_db, int64_t nq, int k, int64_t n_min,
   return pl;
 }
 
-int ensure_q_map(keds_index* ix, int64_t rows_needed) {
+int ensure_q_map(keds_index* ix, int64_t rows_needed, cudaStream_t st) {
   const size_t bytes = static_cast<size_t>(rows_needed) * ix->d_pad * 2;
   if (bytes > ix->q_bf16.cap) {
     // round up so repeated slightly larger batches do not re-encode every call
     const int64_t rows = (rows_needed + 1023) / 1024 * 1024;
     CKS(ix->q_bf16.ensure(static_cast<size_t>(rows) * ix->d_pad * 2));
-    CK(cudaMemset(ix->q_bf16.p, 0, ix->q_bf16.cap));
+    // on the caller's stream: a legacy-stream memset is not ordered against a non-blocking stream
+    CK(cudaMemsetAsync(ix->q_bf16.p, 0, ix->q_bf16.cap, st));
     ix->tm_q_base = nullptr;
   }
   if (ix->tm_q_base != ix->q_bf16.p) {
@@ -432,7 +444,7 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
   } else {
     // operands: bf16 queries + per-query residual norms
     const int64_t q_rows = static_cast<int64_t>(pl.n_qt) * BM;
-    CKS(ensure_q_map(a, q_rows));
+    CKS(ensure_q_map(a, q_rows, st));
     CKS(a->qstat.ensure(static_cast<size_t>(nq) * sizeof(float4)));
     {
       CKS(prof_mark(a, st, 0));
@@ -1013,6 +1025,9 @@ int keds_gather_pool(const float* base, int64_t n_base, const int64_t* I, const 
   if (!base || !I || !out || B < 0 || k <= 0 || d <= 0 || n_base < 0)
     return fail(KEDS_ERR_ARG, "gather_pool: bad argument");
   if (B == 0) return 0;
+  const int dev = device_of(out);
+  if (dev < 0 || device_of(base) != dev) return fail(KEDS_ERR_ARG, "gather_pool: base and out must be memory of one device");
+  DeviceGuard g(dev);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (!W) {
     const long long warps = static_cast<long long>(B) * k;
@@ -1043,10 +1058,13 @@ static int merge_impl(const float* Dp, const int64_t* Ip, int64_t stride_d, int6
   const size_t tot = static_cast<size_t>(parts) * k;
   const size_t smem = tot * 8 + ((tot + 1) & ~size_t(1)) * 4 + tot * 8;
   if (smem > 200 * 1024) return fail(KEDS_ERR_ARG, "topk_merge: parts*k too large");
-  static bool attr = false;
-  if (!attr) {
+  const int dev = device_of(D);
+  if (dev < 0) return fail(KEDS_ERR_ARG, "topk_merge: device pointers only");
+  DeviceGuard g(dev);
+  static bool attr[64] = {false};  // the attribute is per device
+  if (dev >= 64 || !attr[dev]) {
     CK(cudaFuncSetAttribute(k_topk_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr = true;
+    if (dev < 64) attr[dev] = true;
   }
   // launched behind the local search / the push kernel with the programmatic attribute: its
   // launch latency hides under their tails (it starts with griddepcontrol.wait)
@@ -1084,6 +1102,9 @@ int keds_p2p_push(const void* src, int64_t bytes, void* const* peer_dst, uint32_
     if (r != my_rank && (!p.dst[r] || !p.flag[r])) return fail(KEDS_ERR_ARG, "p2p_push: null peer pointer");
   }
   p.ticket = ticket;
+  const int dev = device_of(src);
+  if (dev < 0) return fail(KEDS_ERR_ARG, "p2p_push: src must be device memory");
+  DeviceGuard g(dev);
   const unsigned blocks = static_cast<unsigned>(std::min<long long>(64, (p.n16 + 255) / 256));
   CKS(launch_k(true, k_p2p_push, dim3(std::max(1u, blocks)), dim3(256), 0, static_cast<cudaStream_t>(stream), p));
   return 0;
@@ -1109,6 +1130,10 @@ int keds_gallery_rank(const float* Q, int64_t nq, const float* G, int64_t ng, in
   if (nq == 0) return 0;
   const size_t smem = static_cast<size_t>((d + 3) & ~3) * 4 * 8;  // 8 queries per block
   if (smem > 48 * 1024) return fail(KEDS_ERR_ARG, "gallery_rank: d too large");
+  const int dev = device_of(rank_out);
+  if (dev < 0 || device_of(Q) != dev || device_of(G) != dev)
+    return fail(KEDS_ERR_ARG, "gallery_rank: Q, G and rank_out must be memory of one device");
+  DeviceGuard g(dev);
   k_gallery_rank<<<static_cast<unsigned>((nq + 7) / 8), 256, smem, static_cast<cudaStream_t>(stream)>>>(
       Q, nq, G, ng, d, reinterpret_cast<const long long*>(target),
       reinterpret_cast<const long long*>(exclude), reinterpret_cast<long long*>(rank_out));
@@ -1121,6 +1146,9 @@ int keds_label_hits(const int64_t* I, int64_t nq, int kmax, const int64_t* label
   if (!I || !labels || !qlabel || !ks || !hits || nq < 0 || kmax <= 0 || nks <= 0)
     return fail(KEDS_ERR_ARG, "label_hits: bad argument");
   if (nq == 0) return 0;
+  const int dev = device_of(hits);
+  if (dev < 0 || device_of(I) != dev) return fail(KEDS_ERR_ARG, "label_hits: I and hits must be memory of one device");
+  DeviceGuard g(dev);
   k_label_hits<<<static_cast<unsigned>((nq + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const long long*>(I), nq, kmax, reinterpret_cast<const long long*>(labels),
       reinterpret_cast<const long long*>(qlabel), ks, nks, hits);

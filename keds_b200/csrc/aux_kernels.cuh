@@ -270,27 +270,39 @@ __device__ __forceinline__ void consume_query(const ConsumeParams& c, const floa
   float* pool = c.mode != 0 ? c.pool[s] : nullptr;
   float* feat = c.feat[s] ? c.feat[s] + b * k * d : nullptr;
   if (pool == nullptr && feat == nullptr) return;
-  if (tid == 0) {
-    // k is small (16 in KEDs): a serial pass beats a block reduction
+  // the permutation entries of this warp's first neighbours: fetched before the weights so that
+  // the global load overlaps them
+  const int* perm = c.perm[s];
+  int jr_first[NIF];
+#pragma unroll
+  for (int t = 0; t < NIF; ++t) {
+    const int jo = (tid >> 5) * NIF + t;
+    jr_first[t] = jo < k ? (perm ? perm[jo] : jo) : 0;
+  }
+  if (tid < 32) {
+    // weights by one warp (k is small: 16 in KEDs)
     if (pool != nullptr && c.mode == 2) {
       const float sign = metric == METRIC_L2 ? -1.f : 1.f;
       float mx = -INFINITY;
-      for (int j = 0; j < k; ++j)
+      for (int j = tid; j < k; j += 32)
         if (top_id[j] != 0xFFFFFFFFu) mx = fmaxf(mx, sign * c.tau * top_d[j]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
       float sum = 0.f;
-      for (int j = 0; j < k; ++j) {
+      for (int j = tid; j < k; j += 32) {
         const float e = top_id[j] != 0xFFFFFFFFu ? __expf(sign * c.tau * top_d[j] - mx) : 0.f;
         w[j] = e;
         sum += e;
       }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
       const float inv = sum > 0.f ? 1.f / sum : 0.f;
-      for (int j = 0; j < k; ++j) w[j] *= inv;
+      for (int j = tid; j < k; j += 32) w[j] *= inv;
     } else {
-      for (int j = 0; j < k; ++j) w[j] = 1.f / static_cast<float>(k);
+      for (int j = tid; j < k; j += 32) w[j] = 1.f / static_cast<float>(k);
     }
   }
   __syncthreads();
-  const int* perm = c.perm[s];
   const bool vec = c.part4 > 0 && ((reinterpret_cast<uintptr_t>(rows) | reinterpret_cast<uintptr_t>(c.feat[s]) |
                                     reinterpret_cast<uintptr_t>(c.pool[s])) & 15) == 0;
   if (vec) {
@@ -312,7 +324,8 @@ __device__ __forceinline__ void consume_query(const ConsumeParams& c, const floa
 #pragma unroll
         for (int t = 0; t < NIF; ++t) {
           const int jo = jo0 + t;
-          jr[t] = jo < k ? (perm ? perm[jo] : jo) : 0;  // output slot jo shows rank jr
+          // output slot jo shows rank jr
+          jr[t] = jo0 == warp * NIF ? jr_first[t] : (jo < k ? (perm ? perm[jo] : jo) : 0);
           idv[t] = jo < k ? top_id[jr[t]] : 0xFFFFFFFFu;
 #pragma unroll
           for (int u = 0; u < U; ++u) {
@@ -352,6 +365,7 @@ __device__ __forceinline__ void consume_query(const ConsumeParams& c, const floa
       __syncthreads();
       for (int col = tid; col < d4; col += blockDim.x) {
         float4 acc = part[col];
+#pragma unroll 8
         for (int gg = 1; gg < nwarps; ++gg) {
           const float4 o = part[gg * d4 + col];
           acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;

@@ -56,6 +56,7 @@ int keds_clip_loss_create(int device, keds_clip_loss_t** out) {
     CKS(h->lin.err.ensure(16));
     CK(cudaMemset(h->lin.err.p, 0, 16));
     CKS(h->accum.ensure(16));
+    CK(cudaDeviceSynchronize());  // the memset above is on the legacy stream; callers may use any stream
     return 0;
   };
   const int rc = init();

@@ -153,6 +153,7 @@ k_select_rerank(const RerankParams p) {
       for (int s = tid; s < p.S; s += blockDim.x) {
         const unsigned int mine = smax[s];
         int rank = 0;
+#pragma unroll 8
         for (int u = 0; u < p.S; ++u) {
           const unsigned int o = smax[u];
           rank += (o > mine) || (o == mine && u < s);
@@ -162,12 +163,23 @@ k_select_rerank(const RerankParams p) {
       __syncthreads();  // (2)
       const float t0 = bcast[2] != 0u ? key_to_f32(bcast[2]) : -INFINITY;
       const float thr = t0 - 2.f * eps;
-      for (int i = tid; i < slots; i += blockDim.x) {
-        const unsigned int id = ids[i];
-        if (id != PAD_ID && key_to_f32(keys[i]) >= thr) {
-          const int pos = atomicAdd(&counters[2], 1);
-          if (pos < R_MAX) {
-            a_key[pos] = keys[i];
+      // few slots survive: one shared-memory atomic per warp and pass, none for most warps
+      for (int i0 = 0; i0 < slots; i0 += blockDim.x) {
+        const int i = i0 + tid;
+        unsigned int id = PAD_ID, key = 0u;
+        if (i < slots) {
+          id = ids[i];
+          key = keys[i];
+        }
+        const bool hit = id != PAD_ID && key_to_f32(key) >= thr;
+        const unsigned int bal = __ballot_sync(0xffffffffu, hit);
+        if (bal != 0u) {
+          int base = 0;
+          if (lane == 0) base = atomicAdd(&counters[2], __popc(bal));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          const int pos = base + __popc(bal & ((1u << lane) - 1u));
+          if (hit && pos < R_MAX) {
+            a_key[pos] = key;
             a_id[pos] = id;
           }
         }
@@ -179,6 +191,7 @@ k_select_rerank(const RerankParams p) {
         for (int c = tid; c < na; c += blockDim.x) {
           const unsigned int mine = a_key[c];
           int gt = 0, ge = 0;
+#pragma unroll 8
           for (int j = 0; j < na; ++j) {
             const unsigned int o = a_key[j];
             gt += o > mine;
@@ -284,6 +297,7 @@ k_select_rerank(const RerankParams p) {
     const float sc = sel_sc[c];
     const unsigned long long mine = order_key(p.metric == METRIC_L2 ? -sc : sc, sel_id[c]);
     int rank = 0;
+#pragma unroll 8
     for (int j = 0; j < m; ++j) {
       const float sj = sel_sc[j];
       rank += order_key(p.metric == METRIC_L2 ? -sj : sj, sel_id[j]) > mine;
