@@ -244,8 +244,8 @@ def run_ours(args, rank, world, local):
                          out=bufs)
         return o["I_img"], o["I_txt"], o["feat_img"], o["feat_txt"], o["pool_img"], o["pool_txt"]
 
-    # k_prep_rows, k_score_topk, k_select_rerank (+ neighbour consumer), k_exact_scores, k_exact_select
-    LAUNCHES_PER_STEP = 5
+    # k_prep_rows, k_score_topk, k_select_rerank (+ neighbour consumer), k_exact_fallback
+    LAUNCHES_PER_STEP = 4
 
     def barrier():
         if world > 1:

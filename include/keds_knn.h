@@ -115,7 +115,7 @@ int keds_index_last_stats(const keds_index_t* idx, keds_search_stats* out);
 int keds_index_set_profiling(keds_index_t* idx, int enable);
 int keds_index_profile(keds_index_t* idx, double* score_ms_total, int64_t* score_launches);
 /* Mode 1, whole chain: average in-loop duration of each kernel of a search (0 k_prep_rows,
- * 1 k_score_topk, 2 k_select_rerank, 3 k_exact_scores, 4 k_exact_select) and the average idle gap
+ * 1 k_score_topk, 2 k_select_rerank, 3 k_exact_fallback, 4 reserved = 0) and the average idle gap
  * in front of it (end of the previous kernel to its first CTA), in ms. n >= 5. Does not clear. */
 int keds_index_profile_chain(keds_index_t* idx, double* dur_ms, double* gap_ms, int64_t* searches, int n);
 /* Stage marks (mode 2): index 1 prep_rows, 2 score_topk, 3 select_rerank (+ neighbour consumer),

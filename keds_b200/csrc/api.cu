@@ -163,12 +163,12 @@ int device_of(const void* p) {
   return (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) ? a.device : -1;
 }
 
-constexpr int CTRL_WORDS = 8;  // [0],[1] n_flagged per db, [2] err word, [3],[4] grid barriers
+constexpr int CTRL_WORDS = 8;  // [0],[1] n_flagged per db, [2] err word, [3..5] work counters of the exact fallback
 constexpr int S_MAX = 192;
 constexpr size_t CAND_BUDGET = size_t(1) << 30;
 constexpr int64_t Q_PASS_MAX = 16384;
 constexpr size_t TIMING_RING = 8192;
-constexpr size_t TIMING_PAIRS = 5;  // k_prep_rows, k_score_topk, k_select_rerank, k_exact_scores, k_exact_select
+constexpr size_t TIMING_PAIRS = 5;  // k_prep_rows, k_score_topk, k_select_rerank, k_exact_fallback, (reserved)
 
 struct Plan {
   int exact_only = 0;
@@ -222,8 +222,7 @@ int set_kernel_attrs(keds_index* ix) {
   ix->use_pair = !(no_pair && no_pair[0] == '1');
   CK(cudaFuncSetAttribute(k_select_rerank<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaFuncSetAttribute(k_select_rerank<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  CK(cudaFuncSetAttribute(k_exact_scores, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-  CK(cudaFuncSetAttribute(k_exact_select, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  CK(cudaFuncSetAttribute(k_exact_fallback, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   const char* no_pdl = getenv("KEDS_NO_PDL");
   ix->use_pdl = !(no_pdl && no_pdl[0] == '1');
   if (const char* rt = getenv("KEDS_RERANK_THREADS")) {
@@ -387,16 +386,20 @@ int launch_exact(keds_index* ix, keds_index* dbs[2], int n_db, const float* q_de
   const int dq = (ix->d + 3) & ~3;
   const size_t smem_sc = static_cast<size_t>(EXACT_QG) * dq * 4;
   const size_t smem_sel = static_cast<size_t>(cons.part4) * 16 + static_cast<size_t>(k) * 20 + 256 * 4 + 16 + 16 + 32;
-  if (smem_sc > 160 * 1024 || smem_sel > 160 * 1024)
-    return fail(KEDS_ERR_ARG, "d=%d / k=%d too large for the exact fallback", ix->d, k);
+  const size_t smem = std::max(smem_sc, smem_sel);
+  if (smem > 160 * 1024) return fail(KEDS_ERR_ARG, "d=%d / k=%d too large for the exact fallback", ix->d, k);
+  const unsigned blocks = static_cast<unsigned>(ix->num_sms * 2);
+  // status words [3..5]: work counters of the fallback, zero at the start of every search
+  ep.work = ix->ctrl.as<unsigned int>() + 3;
+  ep.done = ix->ctrl.as<unsigned int>() + 5;
+  ep.err = ix->ctrl.as<unsigned int>() + 2;
   const int passes = static_cast<int>((nq + fc - 1) / fc);
-  const unsigned sel_blocks = static_cast<unsigned>(std::min<long long>(fc, 4 * ix->num_sms));
   for (int pass = 0; pass < passes; ++pass) {
     ep.pass = pass;
     ep.timing = pass == 0 ? timing : nullptr;
-    CKS(launch_k(ix->use_pdl, k_exact_scores, dim3(ix->num_sms * 2), dim3(EXACT_THREADS), smem_sc, st, ep));
-    CKS(launch_k(ix->use_pdl, k_exact_select, dim3(sel_blocks, n_db), dim3(EXACT_THREADS), smem_sel, st, ep));
-    ix->stats.launches += 2;
+    if (pass > 0) CK(cudaMemsetAsync(ix->ctrl.as<unsigned int>() + 3, 0, 12, st));
+    CKS(launch_k(ix->use_pdl, k_exact_fallback, dim3(blocks), dim3(EXACT_THREADS), smem, st, ep));
+    ix->stats.launches += 1;
   }
   return 0;
 }
@@ -565,7 +568,7 @@ int finish_sync(keds_index* a, cudaStream_t st) {
   a->stats.n_flagged[1] = static_cast<int32_t>(h[1]);
   a->stats.err_word = h[2];
   if (h[2] != 0)
-    return fail(KEDS_ERR_KERNEL, "scoring kernel watchdog fired: error word 0x%x", h[2]);
+    return fail(KEDS_ERR_KERNEL, "device watchdog fired (scoring pipeline or fallback barrier): error word 0x%x", h[2]);
   return 0;
 }
 
@@ -687,7 +690,7 @@ int search_impl(keds_index* ix[2], int n_db, const float* q, int64_t nq, int k, 
     a->stats.n_flagged[0] = static_cast<int32_t>(hc[0]);
     a->stats.n_flagged[1] = static_cast<int32_t>(hc[1]);
     a->stats.err_word = hc[2];
-    if (hc[2] != 0) return fail(KEDS_ERR_KERNEL, "scoring kernel watchdog fired: error word 0x%x", hc[2]);
+    if (hc[2] != 0) return fail(KEDS_ERR_KERNEL, "device watchdog fired (scoring pipeline or fallback barrier): error word 0x%x", hc[2]);
     return 0;
   }
   return 0;

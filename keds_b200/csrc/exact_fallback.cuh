@@ -1,13 +1,15 @@
 // Exact fp32 fallback for the queries whose certificate failed (and the whole batch in exact-only
-// mode): two ordinary kernels per pass, both of which return at once when nothing is flagged, so
-// they can sit in every search's launch chain (programmatic dependent launch hides their launch
-// latency) without a host round trip.
+// mode): ONE kernel per pass, k_exact_fallback, which returns at once when nothing is flagged, so it
+// can sit in every search's launch chain (programmatic dependent launch hides its launch latency)
+// without a host round trip. Two phases; work units are claimed through counters and the second
+// phase starts once every unit of the first is finished (no dependence on how many blocks are
+// resident); every block skips both alike when nothing is flagged:
 //
-//   k_exact_scores   rank scores (IP, or -squared-L2) of up to f_cap flagged queries per database
-//                    against every row -> scratch[db][f][row]
-//   k_exact_select   one block per (flagged query, database): radix-select the k-th best, take ties
-//                    in id order, order by (score desc, id asc), write D/I, then run the neighbour
-//                    consumer for that query (the re-rank kernel skipped it)
+//   exact_scores   rank scores (IP, or -squared-L2) of up to f_cap flagged queries per database
+//                  against every row -> scratch[db][f][row]
+//   exact_select   one block per (flagged query, database): radix-select the k-th best, take ties
+//                  in id order, order by (score desc, id asc), write D/I, then run the neighbour
+//                  consumer for that query (the re-rank kernel skipped it)
 //
 // Pass p handles flagged[p * f_cap ... (p+1) * f_cap); the host launches ceil(nq / f_cap) passes.
 // Included by aux_kernels.cuh (uses warp_exact_score, block_find_bin, consume_query).
@@ -31,79 +33,142 @@ struct ExactParams {
   ExactDb db[2];
   int n_db, d, metric, k, f_cap, pass;
   const float* q_f32;
-  unsigned long long* timing;  // nullable: pair 0 = k_exact_scores, pair 1 = k_exact_select
+  unsigned int* work;          // [0] phase-1 units handed out, [1] phase-2 items handed out (zero at launch)
+  unsigned int* done;          // phase-1 units finished (zero at launch)
+  unsigned int* err;           // status word: EXACT_ERR_BARRIER if the barrier watchdog fired
+  unsigned long long* timing;  // nullable in-kernel launch timer
 };
 
-__global__ void __launch_bounds__(EXACT_THREADS)
-k_exact_scores(const ExactParams p) {
-  griddep_wait();  // no early trigger: when this kernel has real work its successor must not take its SM slots
-  const unsigned long long t_start = ktimer_begin(p.timing);
-  extern __shared__ uint8_t ex_smem[];
+constexpr unsigned int EXACT_ERR_BARRIER = 0xEB000000u;
+
+// Work is handed out through counters, never by block index: the blocks that are resident drain
+// all of it, so the wait between the phases cannot depend on a block that has not started yet
+// (two handles searching at once may share the SMs between their grids).
+__device__ __forceinline__ unsigned int exact_claim(unsigned int* counter, unsigned int* slot) {
+  __syncthreads();  // the previous value of *slot has been read by everyone
+  if (threadIdx.x == 0) *slot = atomicAdd(counter, 1u);
+  __syncthreads();
+  return *slot;
+}
+
+struct ExactShape {
+  int F[2];          // flagged queries of this pass per database
+  int qgroups[2];    // groups of EXACT_QG queries
+  int chunks[2];     // row chunks per query group
+  long long cg[2];   // 32-row groups per chunk
+  unsigned int units[2];
+};
+
+__device__ __forceinline__ ExactShape exact_shape(const ExactParams& p) {
+  ExactShape sh;
+  const int r0 = p.pass * p.f_cap;
+#pragma unroll
+  for (int dbi = 0; dbi < 2; ++dbi) {
+    sh.F[dbi] = 0;
+    sh.qgroups[dbi] = 0;
+    sh.chunks[dbi] = 0;
+    sh.cg[dbi] = 1;
+    sh.units[dbi] = 0;
+    if (dbi < p.n_db) {
+      const int nfl = *p.db[dbi].n_flagged;
+      if (nfl > r0) {
+        sh.F[dbi] = min(p.f_cap, nfl - r0);
+        sh.qgroups[dbi] = (sh.F[dbi] + EXACT_QG - 1) / EXACT_QG;
+        const long long groups = (p.db[dbi].n_rows + 31) / 32;
+        // about four chunks per block of the grid, at least one 32-row group per warp
+        const long long want = 4ll * gridDim.x;
+        sh.cg[dbi] = max(static_cast<long long>(blockDim.x >> 5), (groups + want - 1) / want);
+        sh.chunks[dbi] = static_cast<int>((groups + sh.cg[dbi] - 1) / sh.cg[dbi]);
+        sh.units[dbi] = static_cast<unsigned int>(sh.qgroups[dbi]) * static_cast<unsigned int>(sh.chunks[dbi]);
+      }
+    }
+  }
+  return sh;
+}
+
+// phase 1: unit = (database, query group, row chunk); the finished-unit count is the barrier
+__device__ __forceinline__ void exact_scores(const ExactParams& p, const ExactShape& sh, uint8_t* ex_smem,
+                                             unsigned int* slot) {
   float* qs = reinterpret_cast<float*>(ex_smem);  // EXACT_QG * dq
   const int dq = (p.d + 3) & ~3;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wpb = blockDim.x >> 5;
-  for (int dbi = 0; dbi < p.n_db; ++dbi) {
+  const int r0 = p.pass * p.f_cap;
+  const unsigned int total = sh.units[0] + sh.units[1];
+  int have_db = -1, have_g0 = -1;
+  for (;;) {
+    unsigned int u = exact_claim(p.work, slot);
+    if (u >= total) break;
+    const int dbi = u < sh.units[0] ? 0 : 1;
+    if (dbi == 1) u -= sh.units[0];
     const ExactDb& e = p.db[dbi];
-    const int nfl = *e.n_flagged;
-    const int r0 = p.pass * p.f_cap;
-    if (nfl <= r0) continue;
-    const int F = min(p.f_cap, nfl - r0);
-    const long long groups = (e.n_rows + 31) / 32;
-    for (int g0 = 0; g0 < F; g0 += EXACT_QG) {
-      const int G = min(EXACT_QG, F - g0);
-      __syncthreads();
+    const int g0 = static_cast<int>(u / sh.chunks[dbi]) * EXACT_QG;
+    const long long chunk = u % sh.chunks[dbi];
+    const int G = min(EXACT_QG, sh.F[dbi] - g0);
+    if (dbi != have_db || g0 != have_g0) {  // block-uniform; exact_claim's barrier covers the reuse of qs
       for (int i = tid; i < G * dq; i += blockDim.x) {
         const int qi = i / dq, c = i % dq;
         const int q = e.flagged[r0 + g0 + qi];
         qs[i] = c < p.d ? p.q_f32[static_cast<long long>(q) * p.d + c] : 0.f;
       }
       __syncthreads();
-      for (long long g = static_cast<long long>(blockIdx.x) * wpb + warp; g < groups;
-           g += static_cast<long long>(gridDim.x) * wpb) {
-        float keep[EXACT_QG];
+      have_db = dbi;
+      have_g0 = g0;
+    }
+    const long long groups = (e.n_rows + 31) / 32;
+    const long long g_end = min(groups, (chunk + 1) * sh.cg[dbi]);
+    for (long long g = chunk * sh.cg[dbi] + warp; g < g_end; g += wpb) {
+      float keep[EXACT_QG];
 #pragma unroll
-        for (int i = 0; i < EXACT_QG; ++i) keep[i] = 0.f;
-        for (int rr = 0; rr < 32; ++rr) {
-          const long long row = g * 32 + rr;
-          if (row >= e.n_rows) break;
-          const float* xr = e.x_f32 + row * p.d;
+      for (int i = 0; i < EXACT_QG; ++i) keep[i] = 0.f;
+      for (int rr = 0; rr < 32; ++rr) {
+        const long long row = g * 32 + rr;
+        if (row >= e.n_rows) break;
+        const float* xr = e.x_f32 + row * p.d;
 #pragma unroll
-          for (int i = 0; i < EXACT_QG; ++i) {
-            if (i < G) {
-              const float sc = warp_exact_score(qs + i * dq, xr, p.d, p.metric, lane);
-              if (lane == rr) keep[i] = p.metric == METRIC_L2 ? -sc : sc;
-            }
+        for (int i = 0; i < EXACT_QG; ++i) {
+          if (i < G) {
+            const float sc = warp_exact_score(qs + i * dq, xr, p.d, p.metric, lane);
+            if (lane == rr) keep[i] = p.metric == METRIC_L2 ? -sc : sc;
           }
         }
-        const long long row = g * 32 + lane;
-        if (row < e.n_rows) {
+      }
+      const long long row = g * 32 + lane;
+      if (row < e.n_rows) {
 #pragma unroll
-          for (int i = 0; i < EXACT_QG; ++i)
-            if (i < G) e.scratch[static_cast<long long>(g0 + i) * e.n_rows + row] = keep[i];
-        }
+        for (int i = 0; i < EXACT_QG; ++i)
+          if (i < G) e.scratch[static_cast<long long>(g0 + i) * e.n_rows + row] = keep[i];
       }
     }
+    __syncthreads();  // every warp's scores of this unit are written
+    if (tid == 0) {
+      __threadfence();
+      atomicAdd(p.done, 1u);
+    }
   }
-  ktimer_end(p.timing, t_start);
+  // wait until every unit is finished (by whichever blocks took them)
+  if (tid == 0) {
+    const unsigned long long t0 = global_timer_ns();
+    for (;;) {
+      unsigned int v;
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.done) : "memory");
+      if (v >= total) break;
+      __nanosleep(200);
+      if (global_timer_ns() - t0 > 20000000000ull) {  // never hang the device: flag and go on
+        atomicOr(p.err, EXACT_ERR_BARRIER);
+        break;
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
 }
 
-__global__ void __launch_bounds__(EXACT_THREADS)
-k_exact_select(const ExactParams p) {
-  griddep_wait();  // no early trigger: when this kernel has real work its successor must not take its SM slots
-  unsigned long long* timing = p.timing ? p.timing + 2 : nullptr;
-  const unsigned long long t_start = ktimer_begin(timing);
-  const int dbi = blockIdx.y;
+// phase 2: one (database, flagged query) per call
+__device__ __forceinline__ void exact_select(const ExactParams& p, uint8_t* ex_smem, int dbi, int f) {
   const ExactDb& e = p.db[dbi];
-  const int nfl = *e.n_flagged;
   const int r0 = p.pass * p.f_cap;
-  if (nfl <= r0) {
-    ktimer_end(timing, t_start);
-    return;
-  }
-  const int F = min(p.f_cap, nfl - r0);
 
-  extern __shared__ uint8_t ex_smem[];
   float4* part = reinterpret_cast<float4*>(ex_smem);                            // cons.part4
   unsigned int* sel_key = reinterpret_cast<unsigned int*>(part + p.cons.part4); // k
   unsigned int* sel_id = sel_key + p.k;                                         // k
@@ -117,7 +182,7 @@ k_exact_select(const ExactParams p) {
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wpb = blockDim.x >> 5;
-  for (int f = blockIdx.x; f < F; f += gridDim.x) {
+  {
     const int q = e.flagged[r0 + f];
     const float* sc = e.scratch + static_cast<long long>(f) * e.n_rows;
     const long long n = e.n_rows;
@@ -132,7 +197,7 @@ k_exact_select(const ExactParams p) {
       __syncthreads();
 #pragma unroll 8
       for (long long i = tid; i < n; i += blockDim.x) {  // unrolled: eight loads in flight per thread
-        float v = sc[i];
+        float v = __ldcg(sc + i);
         if (v == 0.f) v = 0.f;
         const unsigned int key = f32_to_key(v);
         if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
@@ -153,7 +218,7 @@ k_exact_select(const ExactParams p) {
       // taken in id order -- one pass, no block barriers (the rank sort below orders the output)
 #pragma unroll 4
       for (long long i = tid; i < n; i += blockDim.x) {
-        float v = sc[i];
+        float v = __ldcg(sc + i);
         if (v == 0.f) v = 0.f;
         const unsigned int key = f32_to_key(v);
         if (key >= kth) {
@@ -169,7 +234,7 @@ k_exact_select(const ExactParams p) {
       unsigned int key = 0;
       bool gt = false, eq = false;
       if (i < n) {
-        float v = sc[i];
+        float v = __ldcg(sc + i);
         if (v == 0.f) v = 0.f;
         key = f32_to_key(v);
         gt = key > kth;
@@ -230,7 +295,27 @@ k_exact_select(const ExactParams p) {
       consume_query<1>(p.cons, e.x_f32, dbi, q, p.k, p.d, p.metric, top_id, top_d, top_w, part);
     }
   }
-  ktimer_end(timing, t_start);
+}
+
+// Any grid size is correct; the host launches about two blocks per SM.
+__global__ void __launch_bounds__(EXACT_THREADS)
+k_exact_fallback(const ExactParams p) {
+  griddep_wait();  // no early trigger: when this kernel has real work its successor must not take its SM slots
+  const unsigned long long t_start = ktimer_begin(p.timing);
+  extern __shared__ __align__(16) uint8_t ex_smem[];
+  __shared__ unsigned int slot;
+  const ExactShape sh = exact_shape(p);  // the same in every block: the flag counts are final by now
+  if (sh.F[0] + sh.F[1] > 0) {
+    exact_scores(p, sh, ex_smem, &slot);
+    const unsigned int items = static_cast<unsigned int>(sh.F[0] + sh.F[1]);
+    for (;;) {
+      const unsigned int it = exact_claim(p.work + 1, &slot);
+      if (it >= items) break;
+      const int dbi = it < static_cast<unsigned int>(sh.F[0]) ? 0 : 1;
+      exact_select(p, ex_smem, dbi, static_cast<int>(dbi == 0 ? it : it - sh.F[0]));
+    }
+  }
+  ktimer_end(p.timing, t_start);
 }
 
 }  // namespace keds

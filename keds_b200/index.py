@@ -251,7 +251,7 @@ class GpuIndexFlat:
         _capi.check(self._lib.keds_index_profile(self._h, C.byref(ms), C.byref(n)))
         return float(ms.value), int(n.value)
 
-    CHAIN = ("k_prep_rows", "k_score_topk", "k_select_rerank", "k_exact_scores", "k_exact_select")
+    CHAIN = ("k_prep_rows", "k_score_topk", "k_select_rerank", "k_exact_fallback")
 
     def profile_chain(self) -> dict:
         """In-loop timeline of a search (mode 1): per kernel {'ms': duration, 'gap_ms': idle gap
@@ -262,7 +262,7 @@ class GpuIndexFlat:
         out["searches"] = int(n.value)
         return out
 
-    STAGES = ("", "k_prep_rows", "k_score_topk", "k_select_rerank", "k_exact_scores+select", "")
+    STAGES = ("", "k_prep_rows", "k_score_topk", "k_select_rerank", "k_exact_fallback", "")
 
     def profile_stages(self) -> dict:
         """{kernel: (summed ms, launches)} since set_profiling(True); stream time per stage."""

@@ -8,4 +8,4 @@ for line in sys.stdin:
     for k, v in j["runs"].items():
         for x in v:
             c = x["chain"]
-            print("   ", k, "total", round(x["ms"]*1e3,1), "us |", " ".join(f"{n[2:]}:{c[n]['ms']*1e3:.1f}(+{c[n]['gap_ms']*1e3:.1f})" for n in ("k_prep_rows","k_score_topk","k_select_rerank","k_exact_scores","k_exact_select")))
+            print("   ", k, "total", round(x["ms"]*1e3,1), "us |", " ".join(f"{n[2:]}:{c[n]['ms']*1e3:.1f}(+{c[n]['gap_ms']*1e3:.1f})" for n in ("k_prep_rows","k_score_topk","k_select_rerank","k_exact_fallback")))

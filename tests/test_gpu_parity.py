@@ -130,9 +130,11 @@ def test_more_queries_than_one_pass_holds():
         assert c["ok"], c
 
 
-def test_two_indices_searched_from_two_threads_on_their_own_streams():
+@pytest.mark.parametrize("flags", [0, _capi.SEARCH_EXACT_ONLY])
+def test_two_indices_searched_from_two_threads_on_their_own_streams(flags):
     """One search in flight per handle, but handles are independent: two host threads, two CUDA
-    streams, two indices at once (the ctypes calls release the GIL)."""
+    streams, two indices at once (the ctypes calls release the GIL). With EXACT_ONLY both go through
+    the fallback kernel, whose two phases must not depend on having the SMs to itself."""
     import threading
 
     dbs = [unit(30000, 256, 400 + i) for i in range(2)]
@@ -146,7 +148,7 @@ def test_two_indices_searched_from_two_threads_on_their_own_streams():
             with torch.cuda.stream(s):
                 qd = torch.from_numpy(qs[i]).cuda()
                 for _ in range(8):
-                    D, I = ixs[i].search(qd, 16)
+                    D, I = ixs[i].search(qd, 16, flags)
                 s.synchronize()
             res[i] = (D.cpu().numpy(), I.cpu().numpy())
         except Exception as e:  # pragma: no cover
@@ -163,6 +165,26 @@ def test_two_indices_searched_from_two_threads_on_their_own_streams():
         c = orc.compare_topk(Dr, Ir, res[i][0], res[i][1], dbs[i], qs[i], "ip", TIE_GAP, D_TOL)
         assert c["ok"], c
         assert ixs[i].last_stats()["err_word"] == 0
+
+
+def test_growing_batches_on_a_side_stream_and_host_arrays_there():
+    """Per-call scratch is re-allocated (and its padding rows cleared) as the batch grows: on a
+    non-default stream that must stay ordered with the search. numpy in / numpy out from inside a
+    side-stream context goes through the pinned staging buffers and must give the same answer."""
+    db = unit(20000, 128, 420)
+    ix = build(db, "l2")
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        for b in (3, 130, 1100, 2500, 129):
+            q = unit(b, 128, 430 + b)
+            Dr, Ir = orc.search(db, q, 16, "l2")
+            D, I = ix.search(torch.from_numpy(q).cuda(), 16)
+            s.synchronize()
+            c = orc.compare_topk(Dr, Ir, D.cpu().numpy(), I.cpu().numpy(), db, q, "l2", TIE_GAP, D_TOL)
+            assert c["ok"], (b, c)
+            Dh, Ih = ix.search(q, 16)
+            assert np.array_equal(Ih, I.cpu().numpy()) and np.array_equal(Dh, D.cpu().numpy())
+            assert ix.last_stats()["err_word"] == 0
 
 
 def test_odd_dimension_and_unaligned_rows():
