@@ -308,6 +308,10 @@ Plan make_plan(const keds_index* ix, int n_db, int64_t nq, int k, int64_t n_min,
       pl.S = S;
     }
   }
+  if (const char* dbg = getenv("KEDS_DEBUG_SLICES")) {  // experiments only: force the slice count
+    const int v = atoi(dbg);
+    if (v >= S_sel && v <= S_hi) pl.S = v;
+  }
   pl.n_items = groups * pl.S;
   pl.grid = std::min(pl.n_items, units) * (pl.pair ? 2 : 1);
   return pl;
