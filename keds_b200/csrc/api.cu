@@ -4,6 +4,7 @@
 #include "../../include/keds_knn.h"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -298,11 +299,24 @@ Plan make_plan(const keds_index* ix, int n_db, int64_t nq, int k, int64_t n_min,
     return pl;
   }
   double best = 1e300;
+  // one exact scan of every fp32 row, in the cost unit below (one bf16 row tile per work unit)
+  const double scan_cost = 2.0 * T_max / units;
   for (int S = S_sel; S <= S_hi; ++S) {
     const long long items = static_cast<long long>(groups) * S;
     const long long G = std::min<long long>(items, units);
     const long long per_cta = (items + G - 1) / G;
-    const double cost = static_cast<double>(per_cta) * ((T_max + S - 1) / S) + 0.35 * per_cta;
+    double cost = static_cast<double>(per_cta) * ((T_max + S - 1) / S) + 0.35 * per_cta;
+    // expected fallbacks: a query is flagged when one slice holds LKEEP or more of the ~2k rows at
+    // or above tau (Poisson tail, five-fold margin) -- large k wants more slices than the SM count
+    {
+      const double lam = 2.0 * k / S;
+      double term = std::exp(-lam), tail = 0.0;  // term_i = e^-lam lam^i / i!
+      for (int i = 1; i <= LKEEP + 40; ++i) {
+        term *= lam / i;
+        if (i >= LKEEP) tail += term;
+      }
+      cost += 5.0 * tail * static_cast<double>(nq) * n_db * S * scan_cost;
+    }
     if (cost < best - 1e-9) {
       best = cost;
       pl.S = S;
@@ -373,7 +387,19 @@ int launch_exact(keds_index* ix, keds_index* dbs[2], int n_db, const float* q_de
   long long fc = (512ll << 20) / (4 * std::max<int64_t>(rows_sum, 1));
   fc = std::max(1ll, std::min<long long>(fc, nq));
   ep.f_cap = static_cast<int>(fc);
-  CKS(ix->exact_scratch.ensure(static_cast<size_t>(fc) * rows_sum * 4));
+  // row chunks (phase-1 work units): about four per block, at least one 32-row group per warp
+  const unsigned blocks_ = static_cast<unsigned>(ix->num_sms * 2);
+  int64_t chunks_sum = 0;
+  int chunks_max = 0;
+  for (int i = 0; i < n_db; ++i) {
+    const int64_t groups = (dbs[i]->n + 31) / 32;
+    const int64_t want = 4ll * blocks_;
+    ep.db[i].cg = std::max<int64_t>(EXACT_THREADS / 32, (groups + want - 1) / want);
+    ep.db[i].chunks = static_cast<int>((groups + ep.db[i].cg - 1) / ep.db[i].cg);
+    chunks_sum += ep.db[i].chunks;
+    chunks_max = std::max(chunks_max, ep.db[i].chunks);
+  }
+  CKS(ix->exact_scratch.ensure(static_cast<size_t>(fc) * (rows_sum + chunks_sum) * 4));
   float* scratch = ix->exact_scratch.as<float>();
   for (int i = 0; i < n_db; ++i) {
     ExactDb& e = ep.db[i];
@@ -383,16 +409,20 @@ int launch_exact(keds_index* ix, keds_index* dbs[2], int n_db, const float* q_de
     e.n_flagged = ix->ctrl.as<int>() + i;
     e.scratch = scratch;
     scratch += static_cast<size_t>(fc) * dbs[i]->n;
+    e.cmax = scratch;
+    scratch += static_cast<size_t>(fc) * e.chunks;
     e.D = D[i];
     e.I = I[i];
     e.id_offset = dbs[i]->id_offset;
   }
   const int dq = (ix->d + 3) & ~3;
-  const size_t smem_sc = static_cast<size_t>(EXACT_QG) * dq * 4;
-  const size_t smem_sel = static_cast<size_t>(cons.part4) * 16 + static_cast<size_t>(k) * 20 + 256 * 4 + 16 + 16 + 32;
+  const size_t smem_sc = static_cast<size_t>(EXACT_QG) * dq * 4 + (EXACT_THREADS / 32) * EXACT_QG * 4;
+  ep.ck_cap = std::min(chunks_max, 8192);
+  const size_t smem_sel = static_cast<size_t>(cons.part4) * 16 + static_cast<size_t>(k) * 20 + 256 * 4 + 16 + 16 + 32 +
+                          static_cast<size_t>(EXACT_LIST_CAP) * 8 + static_cast<size_t>(ep.ck_cap) * 4;
   const size_t smem = std::max(smem_sc, smem_sel);
   if (smem > 160 * 1024) return fail(KEDS_ERR_ARG, "d=%d / k=%d too large for the exact fallback", ix->d, k);
-  const unsigned blocks = static_cast<unsigned>(ix->num_sms * 2);
+  const unsigned blocks = blocks_;
   // status words [3..5]: work counters of the fallback, zero at the start of every search
   ep.work = ix->ctrl.as<unsigned int>() + 3;
   ep.done = ix->ctrl.as<unsigned int>() + 5;

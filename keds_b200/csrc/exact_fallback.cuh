@@ -23,6 +23,9 @@ struct ExactDb {
   const int* flagged;
   const int* n_flagged;
   float* scratch;  // [f_cap][n_rows]
+  float* cmax;     // [f_cap][chunks] best rank score of each row chunk (phase 1 -> phase 2 pre-filter)
+  long long cg;    // 32-row groups per chunk
+  int chunks;      // row chunks = phase-1 work units per query group
   float* D;
   long long* I;
   long long id_offset;
@@ -35,11 +38,13 @@ struct ExactParams {
   const float* q_f32;
   unsigned int* work;          // [0] phase-1 units handed out, [1] phase-2 items handed out (zero at launch)
   unsigned int* done;          // phase-1 units finished (zero at launch)
+  int ck_cap;                  // chunk maxima that fit the shared-memory key array of phase 2
   unsigned int* err;           // status word: EXACT_ERR_BARRIER if the barrier watchdog fired
   unsigned long long* timing;  // nullable in-kernel launch timer
 };
 
 constexpr unsigned int EXACT_ERR_BARRIER = 0xEB000000u;
+constexpr int EXACT_LIST_CAP = 2048;  // rows at or above the pre-filter threshold held in shared memory
 
 // Work is handed out through counters, never by block index: the blocks that are resident drain
 // all of it, so the wait between the phases cannot depend on a block that has not started yet
@@ -54,8 +59,6 @@ __device__ __forceinline__ unsigned int exact_claim(unsigned int* counter, unsig
 struct ExactShape {
   int F[2];          // flagged queries of this pass per database
   int qgroups[2];    // groups of EXACT_QG queries
-  int chunks[2];     // row chunks per query group
-  long long cg[2];   // 32-row groups per chunk
   unsigned int units[2];
 };
 
@@ -66,20 +69,13 @@ __device__ __forceinline__ ExactShape exact_shape(const ExactParams& p) {
   for (int dbi = 0; dbi < 2; ++dbi) {
     sh.F[dbi] = 0;
     sh.qgroups[dbi] = 0;
-    sh.chunks[dbi] = 0;
-    sh.cg[dbi] = 1;
     sh.units[dbi] = 0;
     if (dbi < p.n_db) {
       const int nfl = *p.db[dbi].n_flagged;
       if (nfl > r0) {
         sh.F[dbi] = min(p.f_cap, nfl - r0);
         sh.qgroups[dbi] = (sh.F[dbi] + EXACT_QG - 1) / EXACT_QG;
-        const long long groups = (p.db[dbi].n_rows + 31) / 32;
-        // about four chunks per block of the grid, at least one 32-row group per warp
-        const long long want = 4ll * gridDim.x;
-        sh.cg[dbi] = max(static_cast<long long>(blockDim.x >> 5), (groups + want - 1) / want);
-        sh.chunks[dbi] = static_cast<int>((groups + sh.cg[dbi] - 1) / sh.cg[dbi]);
-        sh.units[dbi] = static_cast<unsigned int>(sh.qgroups[dbi]) * static_cast<unsigned int>(sh.chunks[dbi]);
+        sh.units[dbi] = static_cast<unsigned int>(sh.qgroups[dbi]) * static_cast<unsigned int>(p.db[dbi].chunks);
       }
     }
   }
@@ -91,6 +87,7 @@ __device__ __forceinline__ void exact_scores(const ExactParams& p, const ExactSh
                                              unsigned int* slot) {
   float* qs = reinterpret_cast<float*>(ex_smem);  // EXACT_QG * dq
   const int dq = (p.d + 3) & ~3;
+  float* wmax = qs + EXACT_QG * dq;               // [warps][EXACT_QG] per-warp chunk maxima
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wpb = blockDim.x >> 5;
   const int r0 = p.pass * p.f_cap;
@@ -102,8 +99,8 @@ __device__ __forceinline__ void exact_scores(const ExactParams& p, const ExactSh
     const int dbi = u < sh.units[0] ? 0 : 1;
     if (dbi == 1) u -= sh.units[0];
     const ExactDb& e = p.db[dbi];
-    const int g0 = static_cast<int>(u / sh.chunks[dbi]) * EXACT_QG;
-    const long long chunk = u % sh.chunks[dbi];
+    const int g0 = static_cast<int>(u / e.chunks) * EXACT_QG;
+    const long long chunk = u % e.chunks;
     const int G = min(EXACT_QG, sh.F[dbi] - g0);
     if (dbi != have_db || g0 != have_g0) {  // block-uniform; exact_claim's barrier covers the reuse of qs
       for (int i = tid; i < G * dq; i += blockDim.x) {
@@ -116,8 +113,11 @@ __device__ __forceinline__ void exact_scores(const ExactParams& p, const ExactSh
       have_g0 = g0;
     }
     const long long groups = (e.n_rows + 31) / 32;
-    const long long g_end = min(groups, (chunk + 1) * sh.cg[dbi]);
-    for (long long g = chunk * sh.cg[dbi] + warp; g < g_end; g += wpb) {
+    const long long g_end = min(groups, (chunk + 1) * e.cg);
+    float best[EXACT_QG];
+#pragma unroll
+    for (int i = 0; i < EXACT_QG; ++i) best[i] = -INFINITY;
+    for (long long g = chunk * e.cg + warp; g < g_end; g += wpb) {
       float keep[EXACT_QG];
 #pragma unroll
       for (int i = 0; i < EXACT_QG; ++i) keep[i] = 0.f;
@@ -136,11 +136,28 @@ __device__ __forceinline__ void exact_scores(const ExactParams& p, const ExactSh
       const long long row = g * 32 + lane;
       if (row < e.n_rows) {
 #pragma unroll
-        for (int i = 0; i < EXACT_QG; ++i)
-          if (i < G) e.scratch[static_cast<long long>(g0 + i) * e.n_rows + row] = keep[i];
+        for (int i = 0; i < EXACT_QG; ++i) {
+          if (i < G) {
+            e.scratch[static_cast<long long>(g0 + i) * e.n_rows + row] = keep[i];
+            best[i] = fmaxf(best[i], keep[i]);
+          }
+        }
       }
     }
-    __syncthreads();  // every warp's scores of this unit are written
+    // the chunk's best score per query: lanes -> warp -> block
+#pragma unroll
+    for (int i = 0; i < EXACT_QG; ++i) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) best[i] = fmaxf(best[i], __shfl_xor_sync(0xffffffffu, best[i], o));
+      if (lane == 0) wmax[warp * EXACT_QG + i] = best[i];
+    }
+    __syncthreads();
+    if (tid < G) {
+      float m = wmax[tid];
+      for (int w = 1; w < wpb; ++w) m = fmaxf(m, wmax[w * EXACT_QG + tid]);
+      e.cmax[static_cast<long long>(g0 + tid) * e.chunks + chunk] = m;
+    }
+    __syncthreads();  // every warp's scores of this unit and its maxima are written
     if (tid == 0) {
       __threadfence();
       atomicAdd(p.done, 1u);
@@ -179,6 +196,9 @@ __device__ __forceinline__ void exact_select(const ExactParams& p, uint8_t* ex_s
   unsigned int* bcast = hist + 256;                                             // 4
   int* counters = reinterpret_cast<int*>(bcast + 4);                            // 4
   int* wsum = counters + 4;                                                     // 8
+  unsigned int* lk = reinterpret_cast<unsigned int*>(wsum + 8);                 // EXACT_LIST_CAP keys
+  unsigned int* li = lk + EXACT_LIST_CAP;                                       // EXACT_LIST_CAP row ids
+  unsigned int* ck = li + EXACT_LIST_CAP;                                       // chunk maxima (keys)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wpb = blockDim.x >> 5;
@@ -189,82 +209,146 @@ __device__ __forceinline__ void exact_select(const ExactParams& p, uint8_t* ex_s
     const int keff = static_cast<int>(min(static_cast<long long>(p.k), n));
     __syncthreads();
     for (int r = tid; r < p.k; r += blockDim.x) top_id[r] = 0xFFFFFFFFu;
-    // k-th largest rank score: 4 x 8-bit radix passes over the score row (global / L2)
-    unsigned int prefix = 0, mask = 0;
-    int need = keff, n_eq = 0;
-    for (int shift = 24; shift >= 0; shift -= 8) {
-      for (int i = tid; i < 256; i += blockDim.x) hist[i] = 0;
-      __syncthreads();
-#pragma unroll 8
-      for (long long i = tid; i < n; i += blockDim.x) {  // unrolled: eight loads in flight per thread
-        float v = __ldcg(sc + i);
+    // Pre-filter: the k-th best row is at least as good as the k-th best chunk maximum t0 (each of
+    // the k best chunks holds such a row), so only chunks whose maximum reaches t0 can hold an
+    // answer, and only their rows at or above t0 are candidates. A handful of chunks instead of
+    // five passes over the whole score row; the dense path below stays for k > chunks and for
+    // candidate lists that do not fit (heavily duplicated data).
+    bool filled = false;
+    if (e.chunks >= keff && e.chunks <= p.ck_cap && 2 * keff <= EXACT_LIST_CAP) {
+      const float* cm = e.cmax + static_cast<long long>(f) * e.chunks;
+      for (int c = tid; c < e.chunks; c += blockDim.x) {
+        float v = __ldcg(cm + c);
         if (v == 0.f) v = 0.f;
-        const unsigned int key = f32_to_key(v);
-        if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+        ck[c] = f32_to_key(v);
+      }
+      if (tid < 4) counters[tid] = 0;
+      __syncthreads();
+      const unsigned int t0 = block_kth_largest(ck, e.chunks, keff, hist, bcast);
+      for (int c = warp; c < e.chunks; c += wpb) {
+        if (ck[c] < t0) continue;  // warp-uniform
+        const long long lo = static_cast<long long>(c) * e.cg * 32;
+        const long long hi = min(n, lo + e.cg * 32);
+#pragma unroll 4
+        for (long long i = lo + lane; i < hi; i += 32) {
+          float v = __ldcg(sc + i);
+          if (v == 0.f) v = 0.f;
+          const unsigned int key = f32_to_key(v);
+          if (key >= t0) {
+            const int pos = atomicAdd(&counters[2], 1);
+            if (pos < EXACT_LIST_CAP) {
+              lk[pos] = key;
+              li[pos] = static_cast<unsigned int>(i);
+            }
+          }
+        }
       }
       __syncthreads();
-      block_find_bin(hist, need, bcast);
-      prefix |= bcast[0] << shift;
-      mask |= 255u << shift;
-      need = static_cast<int>(bcast[1]);
-      if (shift == 0) n_eq = static_cast<int>(hist[bcast[0]]);  // rows scoring exactly the k-th value
+      const int L = counters[2];
+      if (L <= EXACT_LIST_CAP) {  // block-uniform
+        const unsigned int kth = block_kth_largest(lk, L, keff, hist, bcast);  // L >= keff: one row per chunk at least
+        for (int c = tid; c < L; c += blockDim.x) {
+          if (lk[c] > kth) {
+            const int pos = atomicAdd(&counters[0], 1);
+            sel_key[pos] = lk[c];
+            sel_id[pos] = li[c];
+          }
+        }
+        __syncthreads();
+        const int n_gt = counters[0], need = keff - n_gt;
+        // rows equal to the k-th value: the `need` lowest ids
+        for (int c = tid; c < L; c += blockDim.x) {
+          if (lk[c] != kth) continue;
+          const unsigned int mine = li[c];
+          int r = 0;
+          for (int j = 0; j < L; ++j) r += (lk[j] == kth) && (li[j] < mine);
+          if (r < need) {
+            sel_key[n_gt + r] = kth;
+            sel_id[n_gt + r] = mine;
+          }
+        }
+        filled = true;
+      }
       __syncthreads();
     }
-    const unsigned int kth = prefix;  // `need` rows equal to kth are wanted, lowest ids first
-    if (tid < 4) counters[tid] = 0;
-    __syncthreads();
-    if (n_eq == need) {
-      // the usual case: every row that ties with the k-th value is wanted, so nothing has to be
-      // taken in id order -- one pass, no block barriers (the rank sort below orders the output)
+    if (!filled) {
+      // k-th largest rank score: 4 x 8-bit radix passes over the score row (global / L2)
+      unsigned int prefix = 0, mask = 0;
+      int need = keff, n_eq = 0;
+      for (int shift = 24; shift >= 0; shift -= 8) {
+        for (int i = tid; i < 256; i += blockDim.x) hist[i] = 0;
+        __syncthreads();
+#pragma unroll 8
+        for (long long i = tid; i < n; i += blockDim.x) {  // unrolled: eight loads in flight per thread
+          float v = __ldcg(sc + i);
+          if (v == 0.f) v = 0.f;
+          const unsigned int key = f32_to_key(v);
+          if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        block_find_bin(hist, need, bcast);
+        prefix |= bcast[0] << shift;
+        mask |= 255u << shift;
+        need = static_cast<int>(bcast[1]);
+        if (shift == 0) n_eq = static_cast<int>(hist[bcast[0]]);  // rows scoring exactly the k-th value
+        __syncthreads();
+      }
+      const unsigned int kth = prefix;  // `need` rows equal to kth are wanted, lowest ids first
+      if (tid < 4) counters[tid] = 0;
+      __syncthreads();
+      if (n_eq == need) {
+        // the usual case: every row that ties with the k-th value is wanted, so nothing has to be
+        // taken in id order -- one pass, no block barriers (the rank sort below orders the output)
 #pragma unroll 4
-      for (long long i = tid; i < n; i += blockDim.x) {
-        float v = __ldcg(sc + i);
-        if (v == 0.f) v = 0.f;
-        const unsigned int key = f32_to_key(v);
-        if (key >= kth) {
-          const int pos = key > kth ? atomicAdd(&counters[0], 1) : (keff - need) + atomicAdd(&counters[1], 1);
+        for (long long i = tid; i < n; i += blockDim.x) {
+          float v = __ldcg(sc + i);
+          if (v == 0.f) v = 0.f;
+          const unsigned int key = f32_to_key(v);
+          if (key >= kth) {
+            const int pos = key > kth ? atomicAdd(&counters[0], 1) : (keff - need) + atomicAdd(&counters[1], 1);
+            sel_key[pos] = key;
+            sel_id[pos] = static_cast<unsigned int>(i);
+          }
+        }
+      } else
+      // rows strictly better than kth: any order; rows equal to kth: in id order until `need`
+      for (long long base = 0; base < n; base += blockDim.x) {
+        const long long i = base + tid;
+        unsigned int key = 0;
+        bool gt = false, eq = false;
+        if (i < n) {
+          float v = __ldcg(sc + i);
+          if (v == 0.f) v = 0.f;
+          key = f32_to_key(v);
+          gt = key > kth;
+          eq = key == kth;
+        }
+        if (gt) {
+          const int pos = atomicAdd(&counters[0], 1);
           sel_key[pos] = key;
           sel_id[pos] = static_cast<unsigned int>(i);
         }
-      }
-    } else
-    // rows strictly better than kth: any order; rows equal to kth: in id order until `need`
-    for (long long base = 0; base < n; base += blockDim.x) {
-      const long long i = base + tid;
-      unsigned int key = 0;
-      bool gt = false, eq = false;
-      if (i < n) {
-        float v = __ldcg(sc + i);
-        if (v == 0.f) v = 0.f;
-        key = f32_to_key(v);
-        gt = key > kth;
-        eq = key == kth;
-      }
-      if (gt) {
-        const int pos = atomicAdd(&counters[0], 1);
-        sel_key[pos] = key;
-        sel_id[pos] = static_cast<unsigned int>(i);
-      }
-      const int taken = counters[1];  // uniform: only updated between the syncs below
-      if (taken < need) {
-        const unsigned int bal = __ballot_sync(0xffffffffu, eq);
-        if (lane == 0) wsum[warp] = __popc(bal);
-        __syncthreads();
-        int before = 0;
-        for (int w = 0; w < warp; ++w) before += wsum[w];
-        const int my = taken + before + __popc(bal & ((1u << lane) - 1u));
-        if (eq && my < need) {
-          const int pos = (keff - need) + my;  // ties fill the tail slots
-          sel_key[pos] = key;
-          sel_id[pos] = static_cast<unsigned int>(i);
+        const int taken = counters[1];  // uniform: only updated between the syncs below
+        if (taken < need) {
+          const unsigned int bal = __ballot_sync(0xffffffffu, eq);
+          if (lane == 0) wsum[warp] = __popc(bal);
+          __syncthreads();
+          int before = 0;
+          for (int w = 0; w < warp; ++w) before += wsum[w];
+          const int my = taken + before + __popc(bal & ((1u << lane) - 1u));
+          if (eq && my < need) {
+            const int pos = (keff - need) + my;  // ties fill the tail slots
+            sel_key[pos] = key;
+            sel_id[pos] = static_cast<unsigned int>(i);
+          }
+          __syncthreads();
+          if (tid == 0) {
+            int tot = 0;
+            for (int w = 0; w < wpb; ++w) tot += wsum[w];
+            counters[1] = taken + tot;
+          }
+          __syncthreads();
         }
-        __syncthreads();
-        if (tid == 0) {
-          int tot = 0;
-          for (int w = 0; w < wpb; ++w) tot += wsum[w];
-          counters[1] = taken + tot;
-        }
-        __syncthreads();
       }
     }
     __syncthreads();
