@@ -223,6 +223,25 @@ k_score_topk(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // The database rows do not depend on the previous kernel (they only change in add(), which
+  // synchronises the device): the producer sends the row half of its first stages now, under
+  // k_prep_rows, and the query half once the wait below has passed.
+  int pre_rows = 0;
+  if constexpr (!kPair) {
+    if (warp == 0 && lane == 0 && unit < p.n_items) {
+      const ItemCoord c = decode_item(p, unit);
+      if (c.t0 < c.t1) {
+        const CUtensorMap* tmx = c.db == 0 ? &tm_x0 : &tm_x1;
+        pre_rows = min(NSTAGE, p.kblocks);
+        for (int kb = 0; kb < pre_rows; ++kb) {
+          mbar_arrive_expect_tx(full_bar(kb), Cfg::kStageBytes);
+          tma_load_2d(sbase + kb * Cfg::kStageBytes + Q_STAGE_BYTES, tmx, full_bar(kb), kb * BK, c.t0 * BN,
+                      p.n_qt > 1 ? kEvictNormal : kEvictFirst);
+        }
+      }
+    }
+  }
+
   // Programmatic dependent launch: everything above overlapped the tail of the previous kernel
   // (k_prep_rows); from here on its outputs (bf16 queries) are needed. Let the next kernel
   // (k_select_rerank) be scheduled as soon as SMs free up.
@@ -250,6 +269,10 @@ k_score_topk(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
               tma_load_2d_2sm(sq, &tm_q, full_bar(stage), kb * BK, qt * BM, kEvictLast);
               tma_load_2d_2sm(sx, tmx, full_bar(stage), kb * BK,
                               tile * BN + static_cast<int>(crank) * Cfg::kRowsPerCta, kEvictNormal);
+            } else if (pre_rows > 0) {
+              // first stages of the first tile: armed, and their rows requested, before the wait
+              --pre_rows;
+              tma_load_2d(sq, &tm_q, full_bar(stage), kb * BK, qt * BM, kEvictLast);
             } else {
               mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
               tma_load_2d(sq, &tm_q, full_bar(stage), kb * BK, qt * BM, kEvictLast);
