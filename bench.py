@@ -200,7 +200,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": qps_full, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -420,7 +420,7 @@ def run_ours(args, rank, world, local):
             "value": BATCH / tmed, "unit": "queries/s", "cores": torch.get_num_threads(), "kind": "port",
             "sample": f"full workload ({BATCH} queries x 2 x {n} rows), median of {reps} repetitions; torch-CPU fp32 "
                       f"matmul+topk+gather (the reference's own non-Faiss formulation, src/trainer.py:246-257)"}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_sharded(args, rank, world, local, dev):
@@ -475,8 +475,32 @@ def run_sharded(args, rank, world, local, dev):
     return out
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """stdout carries the JSON line and nothing else: whatever libraries write to fd 1 (NCCL prints
+    its version banner there when NCCL_DEBUG is set) goes to stderr instead."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
     args = parse()
+    if os.environ.get("WORLD_SIZE") or args.gpus == 1 or args.impl == "reference":
+        claim_stdout()  # not in the parent that re-execs under torchrun: its children own fd 1
     rank, world, local = dist_setup(args)
     if args.impl == "reference":
         run_reference(args, rank, world)
