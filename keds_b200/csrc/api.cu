@@ -707,6 +707,14 @@ int search_impl(keds_index* ix[2], int n_db, const float* q, int64_t nq, int k, 
     // then plain memcpy into the caller's arrays
     const size_t db_ = static_cast<size_t>(nq) * k * 4, ib_ = static_cast<size_t>(nq) * k * 8;
     const size_t per = db_ + ib_;
+    if (per * n_db > (size_t(256) << 20)) {
+      // very large result blocks: not worth pinning that much host memory, copy straight out
+      for (int i = 0; i < n_db; ++i) {
+        CK(cudaMemcpyAsync(D[i], Dd[i], db_, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(I[i], Id[i], ib_, cudaMemcpyDeviceToHost, st));
+      }
+      return finish_sync(a, st);
+    }
     CKS(a->h_out.ensure(per * n_db + CTRL_WORDS * 4));
     uint8_t* h = static_cast<uint8_t*>(a->h_out.p);
     for (int i = 0; i < n_db; ++i) {
