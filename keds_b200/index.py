@@ -315,6 +315,17 @@ def search2(a: GpuIndexFlat, b: GpuIndexFlat, x, k: int, flags: int = 0):
     return (Da, Ia), (Db, Ib)
 
 
+def _run_parallel(jobs):
+    """Run the callables on one thread each and return their results in order (first error re-raised)."""
+    if len(jobs) == 1:
+        return [jobs[0]()]
+    from concurrent.futures import ThreadPoolExecutor
+
+    with ThreadPoolExecutor(max_workers=len(jobs)) as pool:
+        futs = [pool.submit(j) for j in jobs]
+        return [f.result() for f in futs]
+
+
 class IndexReplicas:
     """Faiss' default for index_cpu_to_all_gpus: a full copy per GPU, queries split across them.
     Results are identical to a single-GPU search (src/eval_retrieval.py:292,295)."""
@@ -340,15 +351,12 @@ class IndexReplicas:
         a = _as_f32_matrix(x.cpu().numpy() if _is_tensor(x) else x, self.d, "search")
         n = a.shape[0]
         bounds = np.linspace(0, n, len(self.subs) + 1).astype(np.int64)
-        Ds, Is = [], []
-        for s, lo, hi in zip(self.subs, bounds[:-1], bounds[1:]):
-            if hi > lo:
-                D, I = s.search(a[lo:hi], k)
-                Ds.append(D)
-                Is.append(I)
-        if not Ds:
+        parts = [(s, int(lo), int(hi)) for s, lo, hi in zip(self.subs, bounds[:-1], bounds[1:]) if hi > lo]
+        if not parts:
             return np.empty((0, k), np.float32), np.empty((0, k), np.int64)
-        return np.concatenate(Ds), np.concatenate(Is)
+        # one host thread per GPU, as Faiss' IndexReplicas does (the native call releases the GIL)
+        res = _run_parallel([lambda s=s, lo=lo, hi=hi: s.search(a[lo:hi], k) for s, lo, hi in parts])
+        return np.concatenate([r[0] for r in res]), np.concatenate([r[1] for r in res])
 
 
 class IndexShards:
@@ -394,11 +402,16 @@ class IndexShards:
         dev0 = torch.device("cuda", self.devices[0])
         Dp = torch.empty((R, nq, k), dtype=torch.float32, device=dev0)
         Ip = torch.empty((R, nq, k), dtype=torch.int64, device=dev0)
-        for r, s in enumerate(self.subs):
+
+        def one(s):
             q = torch.from_numpy(a).to(torch.device("cuda", s.device))
             with torch.cuda.device(s.device):
                 D, I = s.search(q, k)
                 s.sync()
+            return D, I
+
+        # every shard searches at the same time (one host thread per GPU), then the parts meet on GPU 0
+        for r, (D, I) in enumerate(_run_parallel([lambda s=s: one(s) for s in self.subs])):
             Dp[r].copy_(D)
             Ip[r].copy_(I)
         D = torch.empty((nq, k), dtype=torch.float32, device=dev0)
