@@ -248,6 +248,10 @@ int keds_clip_loss_check(keds_clip_loss_t* h, void* cuda_stream);
  * Approximate (bf16 tensor-core) scores of q against every row: out [nq][ntotal] device float32.
  * Test hook for the GEMM alone; not a product path. */
 int keds_debug_scores(keds_index_t* idx, const float* q, int64_t nq, float* out, void* cuda_stream);
+/* Host only, needs no GPU: the work decomposition the planner picks for n_db databases of n_rows
+ * rows each, nq queries, k neighbours on a device with num_sms SMs.
+ * out = {exact_only, cta_pair, slices S, query tiles, work items, grid (CTAs)}. */
+int keds_debug_plan(int n_db, int64_t nq, int k, int64_t n_rows, int num_sms, int32_t out[6]);
 /* Programmatic dependent launch between the kernels of a search (default on; env KEDS_NO_PDL=1
  * turns the default off). Tuning/diagnostic switch; results do not depend on it. */
 int keds_index_set_pdl(keds_index_t* idx, int enable);

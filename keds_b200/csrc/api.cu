@@ -1065,6 +1065,23 @@ int keds_debug_scores(keds_index_t* ix, const float* q, int64_t nq, float* out, 
   return finish_sync(ix, st);
 }
 
+int keds_debug_plan(int n_db, int64_t nq, int k, int64_t n_rows, int num_sms, int32_t out[6]) {
+  if (!out || n_db < 1 || n_db > 2 || nq <= 0 || k <= 0 || n_rows <= 0 || num_sms <= 0)
+    return fail(KEDS_ERR_ARG, "debug_plan: bad argument");
+  keds_index ix;  // never touches the device: only the planner's inputs are read
+  ix.num_sms = num_sms;
+  const char* no_pair = getenv("KEDS_NO_PAIR");
+  ix.use_pair = !(no_pair && no_pair[0] == '1');
+  const Plan pl = make_plan(&ix, n_db, nq, k, n_rows, n_rows, 0u);
+  out[0] = pl.exact_only;
+  out[1] = pl.pair ? 1 : 0;
+  out[2] = pl.S;
+  out[3] = pl.n_qt;
+  out[4] = pl.n_items;
+  out[5] = pl.grid;
+  return 0;
+}
+
 int keds_gather_pool(const float* base, int64_t n_base, const int64_t* I, const float* W,
                      const int32_t* perm, int64_t B, int k, int H, int d, float* out, void* stream) {
   if (!base || !I || !out || B < 0 || k <= 0 || d <= 0 || n_base < 0)

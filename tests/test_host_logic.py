@@ -79,3 +79,48 @@ def test_database_sampling_and_pair_loading(tmp_path):
     img, txt, kept = kdb.load_pair_folders(str(tmp_path), picked)
     assert img.shape == (7, 6) and txt.shape == (7, 6) and picked[2] not in kept
     assert img.dtype == torch.float32 and float(img[0, 0]) == 0.0 and float(txt[1, 0]) == -1.0
+
+
+# ------------------------------------------------------------------ the planner (host only)
+def _plan(n_db, nq, k, n_rows, sms=148):
+    import ctypes as C
+
+    from keds_b200 import _capi
+    out = (C.c_int32 * 6)()
+    _capi.check(_capi.load().keds_debug_plan(n_db, nq, k, n_rows, sms, out))
+    return dict(zip(("exact_only", "pair", "S", "n_qt", "items", "grid"), [int(v) for v in out]))
+
+
+def test_planner_training_step_shape_fills_the_sms_with_one_item_each():
+    """BASELINE.json configs[1]: 128 queries, 2 x 0.5M rows, k = 16 on 148 SMs."""
+    p = _plan(2, 128, 16, 500_000)
+    assert p == {"exact_only": 0, "pair": 0, "S": 73, "n_qt": 1, "items": 146, "grid": 146}
+
+
+def test_planner_invariants_over_a_sweep():
+    for n_db in (1, 2):
+        for nq in (1, 128, 129, 1024, 4096, 16384):
+            for k in (1, 16, 64, 200):
+                for n in (300, 5_000, 50_000, 500_000, 1_000_000):
+                    p = _plan(n_db, nq, k, n)
+                    assert p["n_qt"] == -(-nq // 128)
+                    if p["exact_only"]:
+                        continue
+                    tiles = -(-n // 256)
+                    assert -(-6 * k // 16) <= p["S"] <= min(tiles, 192)      # enough slices, none empty
+                    assert p["pair"] == (1 if nq > 128 else 0)                  # CTA pairs share row tiles
+                    groups = n_db * (-(-p["n_qt"] // 2) if p["pair"] else p["n_qt"])
+                    assert p["items"] == groups * p["S"]
+                    assert 0 < p["grid"] <= 148 and (p["grid"] % 2 == 0 or not p["pair"])
+
+
+def test_planner_small_databases_and_huge_k_go_to_the_exact_kernel():
+    assert _plan(1, 128, 16, 300)["exact_only"] == 1        # fewer tiles than the slices k needs
+    assert _plan(1, 128, 600, 500_000)["exact_only"] == 1   # k beyond the candidate capacity
+
+
+def test_planner_large_k_buys_slices_against_fallbacks():
+    """k = 64 at 4096 queries x 1M rows: 37 slices balance the SMs just as well as 74 but leave about
+    one query per batch to the exact fallback (a full fp32 scan); the planner must prefer 74."""
+    assert _plan(1, 4096, 64, 1_000_000)["S"] == 74
+    assert _plan(1, 4096, 16, 500_000)["S"] == 23           # small k: unchanged by the fallback term
