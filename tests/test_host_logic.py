@@ -124,3 +124,26 @@ def test_planner_large_k_buys_slices_against_fallbacks():
     one query per batch to the exact fallback (a full fp32 scan); the planner must prefer 74."""
     assert _plan(1, 4096, 64, 1_000_000)["S"] == 74
     assert _plan(1, 4096, 16, 500_000)["S"] == 23           # small k: unchanged by the fallback term
+
+
+def test_parallel_runner_keeps_order_and_raises_the_first_error():
+    """IndexReplicas / IndexShards run one host thread per GPU: results come back in job order and a
+    failing sub-search surfaces as its exception, not as a missing part."""
+    import time
+
+    from keds_b200.index import _run_parallel
+
+    def job(i, delay):
+        def f():
+            time.sleep(delay)
+            return i
+        return f
+
+    assert _run_parallel([job(0, 0.05), job(1, 0.0), job(2, 0.02)]) == [0, 1, 2]
+    assert _run_parallel([job(7, 0.0)]) == [7]
+
+    def boom():
+        raise RuntimeError("shard 1 failed")
+
+    with pytest.raises(RuntimeError, match="shard 1 failed"):
+        _run_parallel([job(0, 0.0), boom, job(2, 0.0)])
