@@ -368,8 +368,8 @@ int prof_mark(keds_index* a, cudaStream_t st, int tag) {
   return 0;
 }
 
-// The exact-fallback kernel pair, ceil(nq / f_cap) passes; every launch returns at once when its
-// slice of the flagged list is empty.
+// The exact-fallback kernel, ceil(nq / f_cap) passes; every launch returns at once when its slice
+// of the flagged list is empty.
 int launch_exact(keds_index* ix, keds_index* dbs[2], int n_db, const float* q_dev, int64_t nq, int k,
                  float* D[2], long long* I[2], int metric, const ConsumeParams& cons,
                  unsigned long long* timing, cudaStream_t st) {
