@@ -34,7 +34,7 @@ enum keds_status {
 };
 
 /* search flags */
-#define KEDS_SEARCH_EXACT_ONLY 1u  /* skip the bf16 tensor-core pass, answer with the fp32 scan */
+#define KEDS_SEARCH_EXACT_ONLY 1u  /* skip the 16-bit tensor-core pass, answer with the fp32 scan */
 #define KEDS_SEARCH_NO_FALLBACK 2u /* debugging: do not run the exact fallback for flagged queries */
 #define KEDS_SEARCH_FORCE_IP 4u    /* rank by inner product whatever the index metric (the reference's
                                       use_faiss=False branch, src/trainer.py:246-257) */
@@ -56,8 +56,8 @@ int keds_index_create(int d, int metric, int device, keds_index_t** out);
 void keds_index_free(keds_index_t* idx);
 
 /* index.add(x) (src/main.py:78,83; src/eval_retrieval.py:293,296). x: [n][d] float32, host or
- * device. Copies; the caller may free x on return. Builds the fp32 master, the bf16 operand copy
- * and the per-row norms on the index's device. */
+ * device. Copies; the caller may free x on return. Builds the fp32 master, the 16-bit operand copy
+ * (fp16 or bf16, see keds_index_operand_format) and the per-row norms on the index's device. */
 int keds_index_add(keds_index_t* idx, const float* x, int64_t n);
 /* add with options. KEDS_ADD_NORMALIZE: rows are L2-normalised on the device while they are added
  * (the database builder's `bases / bases.norm(dim=1, keepdim=True)`, src/main.py:465-466), so the
@@ -76,6 +76,19 @@ int keds_index_device(const keds_index_t* idx);
 const float* keds_index_rows(const keds_index_t* idx);
 /* added to every returned label (row-sharded indices report global ids) */
 int keds_index_set_id_offset(keds_index_t* idx, int64_t offset);
+/* 16-bit operand format of the tensor-core pass: 0 = bf16, 1 = fp16 (fp32 accumulate either way,
+ * same rate, same bytes). Chosen per index from the rows it holds: fp16 keeps 11 significant bits,
+ * so on unit-norm embeddings the certificate's error bound is ~6x tighter (fewer candidates to
+ * re-score, clustered data stays on the fast path); bf16 is used when a value would leave fp16's
+ * range or fp16 would lose more of the rows. Results are exact fp32 under both. set: -1 = automatic
+ * (default; also env KEDS_OPERAND=bf16|fp16), 0 / 1 pin the format (rows already added are
+ * re-rounded from the fp32 master). */
+int keds_index_operand_format(const keds_index_t* idx);
+int keds_index_set_operand_format(keds_index_t* idx, int fmt);
+/* Bumped whenever a device buffer of idx moves or its rows change (add / reset, a search with a
+ * larger batch or k growing the per-call scratch). A CUDA graph captured over a search on idx holds
+ * those addresses: compare before every replay and re-capture on a change. */
+uint64_t keds_index_generation(const keds_index_t* idx);
 
 /* ---- search ---------------------------------------------------------------------------------
  * D, I = index.search(q, k) (src/trainer.py:213,221,271; src/eval_utils.py:169,177).
@@ -162,6 +175,31 @@ int keds_topk_merge_wait(const float* D_parts, const int64_t* I_parts, int64_t s
                          const uint32_t* flags, int my_rank, uint32_t epoch, uint32_t* err_word,
                          void* cuda_stream);
 
+/* Row-sharded search with the exchange fused into the search kernels (the north_star's "local
+ * top-k -> all-gather -> merge" as ONE launch chain, no collective call and no extra copy kernel):
+ * the block that finishes query b's exact top-k stores that row straight into every peer's receive
+ * buffer over NVLink, the last block of the chain publishes the epoch flag, and the merge kernel
+ * waits for the peers' flags. Every rank passes the same queries, calls in the same order, and ends
+ * with the global (D, I). Bit-identical to an unsharded index.
+ *   exchange_create   peer_base[r] = rank r's symmetric buffer (buf_bytes each, zero-filled before
+ *                     the first search) as mapped into this process; entry my_rank = the local one.
+ *                     Layout is the library's: 256 flag bytes, then 2 parities x n_ranks slots.
+ *   exchange_capacity largest nq * k one search may carry.
+ *   search_sharded    q [nq][d], D [nq][k], I [nq][k]: device memory; idx holds this rank's rows
+ *                     with keds_index_set_id_offset(first global row). Asynchronous on cuda_stream.
+ *   exchange_stats    synchronises; average / maximum time (us) block 0 of the merge waited for the
+ *                     peers since the last call (rank skew), merges counted, and the error word
+ *                     (non-zero: a peer never delivered). */
+typedef struct keds_exchange keds_exchange_t;
+int keds_exchange_create(int n_ranks, int my_rank, int device, void* const* peer_base, int64_t buf_bytes,
+                         keds_exchange_t** out);
+void keds_exchange_free(keds_exchange_t* ex);
+int64_t keds_exchange_capacity(const keds_exchange_t* ex);
+int keds_index_search_sharded(keds_index_t* idx, keds_exchange_t* ex, const float* q, int64_t nq, int k,
+                              float* D, int64_t* I, void* cuda_stream);
+int keds_exchange_stats(keds_exchange_t* ex, void* cuda_stream, double* wait_us_avg, double* wait_us_max,
+                        int64_t* steps, uint32_t* err_word);
+
 /* ---- gallery ranking --------------------------------------------------------------------------
  * rank_out[q] = #{ g != target[q], g != exclude[q] : (s(q,g), -g) > (s(q,target), -target) } with
  * s = fp32 inner product. Replaces the similarity matrix + full argsort + name matching of
@@ -245,7 +283,7 @@ int keds_clip_loss_forward_backward(keds_clip_loss_t* h, const float* I_all, con
 int keds_clip_loss_check(keds_clip_loss_t* h, void* cuda_stream);
 
 /* ---- diagnostics ------------------------------------------------------------------------------
- * Approximate (bf16 tensor-core) scores of q against every row: out [nq][ntotal] device float32.
+ * Approximate (16-bit operand tensor-core) scores of q against every row: out [nq][ntotal] device float32.
  * Test hook for the GEMM alone; not a product path. */
 int keds_debug_scores(keds_index_t* idx, const float* q, int64_t nq, float* out, void* cuda_stream);
 /* Host only, needs no GPU: the work decomposition the planner picks for n_db databases of n_rows

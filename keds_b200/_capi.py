@@ -47,6 +47,17 @@ SIGNATURES = {
     "keds_index_device": (C.c_int, [_vp]),
     "keds_index_rows": (_vp, [_vp]),
     "keds_index_set_id_offset": (C.c_int, [_vp, C.c_int64]),
+    "keds_index_operand_format": (C.c_int, [_vp]),
+    "keds_index_set_operand_format": (C.c_int, [_vp, C.c_int]),
+    "keds_index_generation": (C.c_uint64, [_vp]),
+    "keds_exchange_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(_vp), C.c_int64, C.POINTER(_vp)]),
+    "keds_exchange_free": (None, [_vp]),
+    "keds_exchange_capacity": (C.c_int64, [_vp]),
+    "keds_index_search_sharded": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int, _vp, _vp, _vp]),
+    "keds_exchange_stats": (
+        C.c_int,
+        [_vp, _vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_uint32)],
+    ),
     "keds_index_search": (C.c_int, [_vp, _vp, C.c_int64, C.c_int, _vp, _vp, _vp]),
     "keds_index_search_ex": (C.c_int, [_vp, _vp, C.c_int64, C.c_int, _vp, _vp, C.c_uint32, _vp]),
     "keds_index_search2": (

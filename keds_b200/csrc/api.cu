@@ -4,6 +4,7 @@
 #include "../../include/keds_knn.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -47,12 +48,19 @@ int fail(int code, const char* fmt, ...) {
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
+  // Bumped whenever the buffer moves: a CUDA graph captured over a handle bakes these addresses in,
+  // and its owner compares keds_index_generation() before every replay (RetrievalStep.run()).
+  uint64_t* gen = nullptr;
+  void moved() {
+    if (gen) ++*gen;
+  }
   // grow without keeping contents
   int ensure(size_t bytes) {
     if (bytes <= cap) return 0;
     if (p) cudaFree(p);
     p = nullptr;
     cap = 0;
+    moved();
     CK(cudaMalloc(&p, bytes));
     cap = bytes;
     return 0;
@@ -66,10 +74,14 @@ struct DevBuf {
     if (p) cudaFree(p);
     p = np;
     cap = bytes;
+    moved();
     return 0;
   }
   void release() {
-    if (p) cudaFree(p);
+    if (p) {
+      cudaFree(p);
+      moved();
+    }
     p = nullptr;
     cap = 0;
   }
@@ -127,16 +139,17 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// bf16 [rows][d_pad] row-major -> boxes of {BK columns x box_rows rows}, 128-byte swizzle,
+// 16-bit [rows][d_pad] row-major -> boxes of {BK columns x box_rows rows}, 128-byte swizzle,
 // out-of-range rows read as zeros.
-int encode_rows_map(CUtensorMap* tm, const void* base, int64_t rows, int d_pad, int box_rows) {
+int encode_rows_map(CUtensorMap* tm, const void* base, int64_t rows, int d_pad, int box_rows, int fmt) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail(KEDS_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(d_pad), static_cast<cuuint64_t>(rows)};
   cuuint64_t gstr[1] = {static_cast<cuuint64_t>(d_pad) * 2};
   cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box,
+  CUresult r = fn(tm, fmt == FMT_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                  const_cast<void*>(base), gdim, gstr, box,
                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(KEDS_ERR_CUDA, "cuTensorMapEncodeTiled failed: CUresult %d", (int)r);
@@ -164,7 +177,10 @@ int device_of(const void* p) {
   return (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) ? a.device : -1;
 }
 
-constexpr int CTRL_WORDS = 8;  // [0],[1] n_flagged per db, [2] err word, [3..5] work counters of the exact fallback
+// [0],[1] n_flagged per db, [2] err word, [3..5] work counters of the exact fallback, [6] largest
+// candidate band |C| of the search (planner feedback), [7] spare
+constexpr int CTRL_WORDS = 8;
+constexpr int CTRL_BAND = 6;
 constexpr int S_MAX = 192;
 constexpr size_t CAND_BUDGET = size_t(1) << 30;
 constexpr int64_t Q_PASS_MAX = 16384;
@@ -184,7 +200,14 @@ struct keds_index {
   int64_t n = 0;
   int64_t id_offset = 0;
   float eps_scale = 1.f;
-  DevBuf x_f32, x_bf16, bias, dbstat;
+  // 16-bit operand format of x_bf16 / q_bf16 (FMT_FP16 or FMT_BF16; the buffer names predate the
+  // choice) and what it was chosen from: running maxima over every row added so far
+  int fmt = FMT_FP16;
+  int fmt_forced = -1;  // -1: automatic (KEDS_OPERAND / keds_index_set_operand_format override it)
+  float amax = 0.f, res_bf16 = 0.f, res_fp16 = 0.f;
+  uint64_t generation = 0;        // bumped when a buffer a captured graph may hold is reallocated
+  unsigned int* h_feedback = nullptr;  // mapped host word: largest candidate band of a recent search
+  DevBuf x_f32, x_bf16, bias, dbstat, probe;
   CUtensorMap tm_x;   // {64 x 256}-row boxes (one CTA per tile)
   CUtensorMap tm_xh;  // {64 x 128}-row boxes (CTA pair: half a tile each)
   bool tm_x_ok = false;
@@ -196,6 +219,7 @@ struct keds_index {
   CUtensorMap tm_q;
   const void* tm_q_base = nullptr;
   int64_t tm_q_rows = 0;
+  int tm_q_fmt = -1;
   keds_search_stats stats;
   bool attrs_set = false;
   bool use_pdl = true;
@@ -275,8 +299,12 @@ int launch_k(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
 
 // Pick the number of row slices: enough that no slice is expected to hold more than a third of
 // LKEEP of the top-k, enough work items to fill the SMs, then whatever minimises the longest CTA.
+// band_hint: the largest candidate band |C| a recent search on this handle reported (0: none).
+// On i.i.d. data about 2k rows sit at or above tau; clustered embeddings put a whole cluster there,
+// and a slice that holds LKEEP of them fails the certificate -- so the expected-fallback term
+// below takes whichever is larger and the planner answers crowded bands with more, shorter slices.
 Plan make_plan(const keds_index* ix, int n_db, int64_t nq, int k, int64_t n_min, int64_t n_max,
-               uint32_t flags) {
+               uint32_t flags, unsigned int band_hint = 0) {
   Plan pl;
   pl.n_qt = static_cast<int>((nq + BM - 1) / BM);
   const int T_min = static_cast<int>((n_min + BN - 1) / BN);
@@ -309,7 +337,7 @@ Plan make_plan(const keds_index* ix, int n_db, int64_t nq, int k, int64_t n_min,
     // expected fallbacks: a query is flagged when one slice holds LKEEP or more of the ~2k rows at
     // or above tau (Poisson tail, five-fold margin) -- large k wants more slices than the SM count
     {
-      const double lam = 2.0 * k / S;
+      const double lam = std::max(2.0 * k, 1.25 * static_cast<double>(band_hint)) / S;
       double term = std::exp(-lam), tail = 0.0;  // term_i = e^-lam lam^i / i!
       for (int i = 1; i <= LKEEP + 40; ++i) {
         term *= lam / i;
@@ -341,11 +369,12 @@ int ensure_q_map(keds_index* ix, int64_t rows_needed, cudaStream_t st) {
     CK(cudaMemsetAsync(ix->q_bf16.p, 0, ix->q_bf16.cap, st));
     ix->tm_q_base = nullptr;
   }
-  if (ix->tm_q_base != ix->q_bf16.p) {
+  if (ix->tm_q_base != ix->q_bf16.p || ix->tm_q_fmt != ix->fmt) {
     const int64_t rows = static_cast<int64_t>(ix->q_bf16.cap / (static_cast<size_t>(ix->d_pad) * 2));
-    CKS(encode_rows_map(&ix->tm_q, ix->q_bf16.p, rows, ix->d_pad, BM));
+    CKS(encode_rows_map(&ix->tm_q, ix->q_bf16.p, rows, ix->d_pad, BM, ix->fmt));
     ix->tm_q_base = ix->q_bf16.p;
     ix->tm_q_rows = rows;
+    ix->tm_q_fmt = ix->fmt;
   }
   return 0;
 }
@@ -372,7 +401,7 @@ int prof_mark(keds_index* a, cudaStream_t st, int tag) {
 // of the flagged list is empty.
 int launch_exact(keds_index* ix, keds_index* dbs[2], int n_db, const float* q_dev, int64_t nq, int k,
                  float* D[2], long long* I[2], int metric, const ConsumeParams& cons,
-                 unsigned long long* timing, cudaStream_t st) {
+                 unsigned long long* timing, cudaStream_t st, const PeerOut* peer = nullptr) {
   ExactParams ep;
   memset(&ep, 0, sizeof ep);
   ep.cons = cons;
@@ -427,9 +456,15 @@ int launch_exact(keds_index* ix, keds_index* dbs[2], int n_db, const float* q_de
   ep.work = ix->ctrl.as<unsigned int>() + 3;
   ep.done = ix->ctrl.as<unsigned int>() + 5;
   ep.err = ix->ctrl.as<unsigned int>() + 2;
+  ep.band_dev = ix->ctrl.as<unsigned int>() + CTRL_BAND;
   const int passes = static_cast<int>((nq + fc - 1) / fc);
   for (int pass = 0; pass < passes; ++pass) {
     ep.pass = pass;
+    ep.band_host = pass == passes - 1 ? ix->h_feedback : nullptr;
+    if (peer) {
+      ep.peer = *peer;
+      ep.peer.publish = peer->publish && pass == passes - 1;  // only the step's very last launch publishes
+    }
     ep.timing = pass == 0 ? timing : nullptr;
     if (pass > 0) CK(cudaMemsetAsync(ix->ctrl.as<unsigned int>() + 3, 0, 12, st));
     CKS(launch_k(ix->use_pdl, k_exact_fallback, dim3(blocks), dim3(EXACT_THREADS), smem, st, ep));
@@ -442,7 +477,7 @@ int launch_exact(keds_index* ix, keds_index* dbs[2], int n_db, const float* q_de
 // cons_in (nullable): neighbour-consumer outputs for this pass, already offset to its first query.
 int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int k, float* D[2],
                 long long* I[2], uint32_t flags, cudaStream_t st, float* dump, int64_t ld_dump,
-                const ConsumeParams* cons_in) {
+                const ConsumeParams* cons_in, const PeerOut* peer = nullptr) {
   keds_index* a = ix[0];
   const int metric = (flags & KEDS_SEARCH_FORCE_IP) ? METRIC_IP : a->metric;
   CKS(set_kernel_attrs(a));
@@ -464,7 +499,8 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
     n_min = std::min(n_min, ix[1]->n);
     n_max = std::max(n_max, ix[1]->n);
   }
-  Plan pl = make_plan(a, n_db, nq, k, n_min, n_max, flags);
+  const unsigned int band_hint = a->h_feedback ? *static_cast<volatile unsigned int*>(a->h_feedback) : 0u;
+  Plan pl = make_plan(a, n_db, nq, k, n_min, n_max, flags, band_hint);
   if (dump && pl.exact_only) return fail(KEDS_ERR_ARG, "debug_scores needs at least one 256-row tile");
   a->stats.exact_only = pl.exact_only;
   a->stats.slices = pl.S;
@@ -490,7 +526,7 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
       const unsigned blocks =
           static_cast<unsigned>(std::min<long long>((warps_needed * 32 + threads - 1) / threads, 4096));
       CKS(launch_k(a->use_pdl, k_prep_rows, dim3(blocks), dim3(threads), 0, st, q_dev,
-                   static_cast<long long>(nq), a->d, a->d_pad, a->q_bf16.as<__nv_bfloat16>(),
+                   static_cast<long long>(nq), a->d, a->d_pad, a->fmt, a->q_bf16.as<uint16_t>(),
                    a->qstat.as<float4>(), static_cast<float*>(nullptr), static_cast<unsigned int*>(nullptr),
                    a->ctrl.as<unsigned int>(), CTRL_WORDS, tchain));
       a->stats.launches++;
@@ -509,6 +545,7 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
     sp.S = pl.S;
     sp.n_items = pl.n_items;
     sp.kblocks = a->d_pad / BK;
+    sp.fmt_bits = a->fmt == FMT_BF16 ? kIdescBf16Bits : 0u;
     sp.nq = static_cast<int>(nq);
     for (int i = 0; i < n_db; ++i) {
       sp.n_rows[i] = static_cast<int>(ix[i]->n);
@@ -558,16 +595,28 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
       rp.n_flagged[i] = a->ctrl.as<int>() + i;
     }
     rp.eps_scale = a->eps_scale;
+    rp.band_max = a->ctrl.as<unsigned int>() + CTRL_BAND;
+    // one wave of blocks (two per SM): the latency variant; more: the four-per-SM throughput variant
+    const bool small_batch = nq * n_db <= 2ll * a->num_sms;
+    // Candidate capacity. A single wave has the shared memory to spare: full size. Large batches
+    // live on blocks per SM, so they start small and follow the band a recent search reported (a
+    // query that does not fit is answered by the exact fallback and raises the next call's figure).
+    int rmax = R_MAX;
+    if (!small_batch) {
+      const unsigned int want = std::max<unsigned int>(static_cast<unsigned int>(4 * k), band_hint + band_hint / 2);
+      rmax = 256;
+      while (rmax < static_cast<int>(std::min<unsigned int>(want, R_MAX))) rmax *= 2;
+    }
+    rp.rmax = rmax;
+    if (peer) rp.peer = *peer;
     rp.cons = cons;
     rp.timing = tchain ? tchain + 4 : nullptr;
     const size_t slots = static_cast<size_t>(pl.S) * LKEEP;
-    // qvec | part | keys, ids | smax | a_key, a_id, sel_id, sel_sc | hist | red | bcast | counters | top_*
+    // qvec | part | okey | keys, ids | smax | a_key, a_id, sel_id, sel_sc | hist | red | bcast | counters | top_*
     const size_t smem = static_cast<size_t>((a->d + 3) & ~3) * 4 + static_cast<size_t>(cons.part4) * 16 +
-                        slots * 8 + pl.S * 4 + R_MAX * 16 + 256 * 4 + 32 * 4 + 16 + 16 +
+                        static_cast<size_t>(rmax) * 24 + slots * 8 + pl.S * 4 + 256 * 4 + 32 * 4 + 16 + 16 +
                         static_cast<size_t>(k) * 12;
     if (smem > 200 * 1024) return fail(KEDS_ERR_ARG, "re-rank shared memory %zu too large", smem);
-    // one wave of blocks (two per SM): the latency variant; more: the four-per-SM throughput variant
-    const bool small_batch = nq * n_db <= 2ll * a->num_sms;
     if (small_batch)
       CKS(launch_k(a->use_pdl, k_select_rerank<3, 2>, dim3(static_cast<unsigned>(nq), n_db),
                    dim3(RERANK_THREADS), smem, st, rp));
@@ -579,7 +628,7 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
     CK(cudaGetLastError());
   }
   if (!(flags & KEDS_SEARCH_NO_FALLBACK) || pl.exact_only) {
-    CKS(launch_exact(a, ix, n_db, q_dev, nq, k, D, I, metric, cons, tchain ? tchain + 6 : nullptr, st));
+    CKS(launch_exact(a, ix, n_db, q_dev, nq, k, D, I, metric, cons, tchain ? tchain + 6 : nullptr, st, peer));
     CKS(prof_mark(a, st, 4));
   }
   CK(cudaGetLastError());
@@ -607,7 +656,8 @@ int finish_sync(keds_index* a, cudaStream_t st) {
 }
 
 int search_impl(keds_index* ix[2], int n_db, const float* q, int64_t nq, int k, float* D[2],
-                int64_t* I[2], uint32_t flags, void* stream, const ConsumeParams* cons = nullptr) {
+                int64_t* I[2], uint32_t flags, void* stream, const ConsumeParams* cons = nullptr,
+                const PeerOut* peer = nullptr) {
   keds_index* a = ix[0];
   if (!a || !q || nq < 0 || k <= 0) return fail(KEDS_ERR_ARG, "search: null handle/query or bad nq/k");
   if (k > K_MAX) return fail(KEDS_ERR_ARG, "search: k=%d exceeds the maximum %d", k, K_MAX);
@@ -622,6 +672,11 @@ int search_impl(keds_index* ix[2], int n_db, const float* q, int64_t nq, int k, 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   memset(&a->stats, 0, sizeof a->stats);
   if (nq == 0) return 0;
+  // one query operand feeds both databases: they must share the 16-bit format. bf16 is the one
+  // every database can take, so a mixed pair settles there (once; the rows are re-rounded).
+  if (n_db > 1 && ix[0]->fmt != ix[1]->fmt)
+    for (int i = 0; i < 2; ++i)
+      if (ix[i]->fmt != FMT_BF16) CKS(keds_index_set_operand_format(ix[i], FMT_BF16));
 
   const bool q_dev = is_device_ptr(q);
   bool out_dev = true;
@@ -697,7 +752,17 @@ int search_impl(keds_index* ix[2], int n_db, const float* q, int64_t nq, int k, 
           if (cp.pool[s]) cp.pool[s] += q0 * a->d;
         }
       }
-      CKS(search_pass(ix, n_db, qd + q0 * a->d, nb, k, Dp, Ip, flags, st, nullptr, 0, cons ? &cp : nullptr));
+      PeerOut pp;
+      if (peer) {
+        pp = *peer;
+        for (int r = 0; r < pp.n; ++r) {
+          if (pp.D[r]) pp.D[r] += q0 * k;
+          if (pp.I[r]) pp.I[r] += q0 * k;
+        }
+        pp.publish = q0 + nb >= nq;  // the flags go out behind the step's last pass
+      }
+      CKS(search_pass(ix, n_db, qd + q0 * a->d, nb, k, Dp, Ip, flags, st, nullptr, 0, cons ? &cp : nullptr,
+                      peer ? &pp : nullptr));
       // the per-call status words are rewritten by the next pass: read this pass's first
       if (q0 + nb < nq) CKS(finish_sync(a, st));
     }
@@ -780,12 +845,31 @@ int keds_index_create(int d, int metric, int device, keds_index_t** out) {
   ix->device = device;
   ix->num_sms = prop.multiProcessorCount;
   memset(&ix->stats, 0, sizeof ix->stats);
-  int s = ix->dbstat.ensure(8);
-  if (s == 0 && cudaMemset(ix->dbstat.p, 0, 8) != cudaSuccess) s = fail(KEDS_ERR_CUDA, "memset failed");
+  if (const char* op = getenv("KEDS_OPERAND")) {  // "bf16" / "fp16" pin the operand format; default: automatic
+    if (!strcmp(op, "bf16")) ix->fmt_forced = FMT_BF16;
+    if (!strcmp(op, "fp16")) ix->fmt_forced = FMT_FP16;
+  }
+  int s = ix->dbstat.ensure(16);
+  if (s == 0 && cudaMemset(ix->dbstat.p, 0, 16) != cudaSuccess) s = fail(KEDS_ERR_CUDA, "memset failed");
+  if (s == 0) s = ix->probe.ensure(16);
+  if (s == 0) {
+    void* h = nullptr;
+    if (cudaHostAlloc(&h, 64, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess)
+      s = fail(KEDS_ERR_CUDA, "cudaHostAlloc of the feedback word failed");
+    else {
+      memset(h, 0, 64);
+      ix->h_feedback = static_cast<unsigned int*>(h);
+    }
+  }
   if (s != 0) {
-    delete ix;
+    keds_index_free(ix);
     return s;
   }
+  // every buffer whose address a captured search bakes in reports its moves
+  DevBuf* tracked[] = {&ix->x_f32, &ix->x_bf16, &ix->bias, &ix->q_f32, &ix->q_bf16, &ix->qstat, &ix->cand,
+                       &ix->cand_cnt, &ix->cand_theta, &ix->flagged[0], &ix->flagged[1], &ix->ctrl,
+                       &ix->exact_scratch, &ix->D_stage[0], &ix->D_stage[1], &ix->I_stage[0], &ix->I_stage[1]};
+  for (DevBuf* b : tracked) b->gen = &ix->generation;
   *out = ix;
   return 0;
 }
@@ -796,10 +880,11 @@ void keds_index_free(keds_index_t* ix) {
   DevBuf* bufs[] = {&ix->x_f32, &ix->x_bf16, &ix->bias, &ix->dbstat, &ix->q_f32, &ix->q_bf16,
                     &ix->qstat, &ix->cand, &ix->cand_cnt, &ix->cand_theta, &ix->flagged[0],
                     &ix->flagged[1], &ix->ctrl, &ix->exact_scratch, &ix->D_stage[0], &ix->D_stage[1],
-                    &ix->I_stage[0], &ix->I_stage[1], &ix->timing};
+                    &ix->I_stage[0], &ix->I_stage[1], &ix->timing, &ix->probe};
   for (DevBuf* b : bufs) b->release();
   ix->h_q.release();
   ix->h_out.release();
+  if (ix->h_feedback) cudaFreeHost(ix->h_feedback);
   for (cudaEvent_t e : ix->prof_ev) cudaEventDestroy(e);
   delete ix;
 }
@@ -814,6 +899,26 @@ int keds_index_get_rows(const keds_index_t* ix, int64_t first, int64_t n, float*
   DeviceGuard g(ix->device);
   CK(cudaMemcpy(out, ix->x_f32.as<float>() + first * ix->d, static_cast<size_t>(n) * ix->d * 4,
                 cudaMemcpyDefault));
+  return 0;
+}
+
+// Operand format from what the rows look like (running maxima over every add): fp16 when nothing
+// comes near its range limit and it keeps more of the rows than bf16 does (always the case for
+// unit-norm embeddings: 11 significant bits against 8), bf16 otherwise.
+static int choose_format(const keds_index* ix) {
+  if (ix->fmt_forced >= 0) return ix->fmt_forced;
+  return (ix->amax < 3.0e4f && ix->res_fp16 <= ix->res_bf16) ? FMT_FP16 : FMT_BF16;
+}
+
+// (re)build the 16-bit operand copy, the L2 bias and the certificate statistics of rows [r0, r1)
+static int prep_db_rows(keds_index* ix, int64_t r0, int64_t r1) {
+  const size_t d = ix->d, dp = ix->d_pad;
+  const int64_t n = r1 - r0;
+  const unsigned blocks = static_cast<unsigned>(std::min<int64_t>((n * 32 + 255) / 256, ix->num_sms * 16));
+  k_prep_rows<<<blocks, 256>>>(ix->x_f32.as<float>() + r0 * d, n, ix->d, ix->d_pad, ix->fmt,
+                               ix->x_bf16.as<uint16_t>() + r0 * dp, nullptr, ix->bias.as<float>() + r0,
+                               ix->dbstat.as<unsigned int>(), nullptr, 0, nullptr);
+  CK(cudaGetLastError());
   return 0;
 }
 
@@ -833,11 +938,29 @@ int keds_index_add_ex(keds_index_t* ix, const float* x, int64_t n, uint32_t flag
     CKS(ix->bias.grow_keep(static_cast<size_t>(tiles_cap) * BN * 4, static_cast<size_t>(n0) * 4));
   }
   CK(cudaMemcpy(ix->x_f32.as<float>() + n0 * d, x, static_cast<size_t>(n) * d * 4, cudaMemcpyDefault));
-  const unsigned blocks = static_cast<unsigned>(std::min<int64_t>((n * 32 + 255) / 256, 148 * 16));
+  const unsigned blocks = static_cast<unsigned>(std::min<int64_t>((n * 32 + 255) / 256, ix->num_sms * 16));
   if (flags & KEDS_ADD_NORMALIZE) k_normalize_rows<<<blocks, 256>>>(ix->x_f32.as<float>() + n0 * d, n, ix->d);
-  k_prep_rows<<<blocks, 256>>>(ix->x_f32.as<float>() + n0 * d, n, ix->d, ix->d_pad,
-                               ix->x_bf16.as<__nv_bfloat16>() + n0 * dp, nullptr,
-                               ix->bias.as<float>() + n0, ix->dbstat.as<unsigned int>(), nullptr, 0, nullptr);
+  // which 16-bit format keeps more of these rows (one extra read of the upload)
+  {
+    CK(cudaMemset(ix->probe.p, 0, 16));
+    k_probe_rows<<<blocks, 256>>>(ix->x_f32.as<float>() + n0 * d, n, ix->d, ix->probe.as<unsigned int>());
+    CK(cudaGetLastError());
+    float h[4] = {0.f, 0.f, 0.f, 0.f};
+    CK(cudaMemcpy(h, ix->probe.p, 12, cudaMemcpyDeviceToHost));
+    ix->amax = std::max(ix->amax, h[0]);
+    ix->res_bf16 = std::max(ix->res_bf16, h[1]);
+    ix->res_fp16 = std::max(ix->res_fp16, h[2]);
+  }
+  const int want = choose_format(ix);
+  if (n0 > 0 && want != ix->fmt) {
+    // rows added earlier were rounded to the other format: redo them from the fp32 master
+    ix->fmt = want;
+    CK(cudaMemset(ix->dbstat.p, 0, 16));
+    CKS(prep_db_rows(ix, 0, n1));
+  } else {
+    ix->fmt = want;
+    CKS(prep_db_rows(ix, n0, n1));
+  }
   const int64_t padded = (n1 + BN - 1) / BN * BN;
   if (padded > n1)
     k_fill_f32<<<static_cast<unsigned>((padded - n1 + 255) / 256), 256>>>(ix->bias.as<float>() + n1,
@@ -845,11 +968,35 @@ int keds_index_add_ex(keds_index_t* ix, const float* x, int64_t n, uint32_t flag
   CK(cudaGetLastError());
   CK(cudaDeviceSynchronize());
   ix->n = n1;
-  CKS(encode_rows_map(&ix->tm_x, ix->x_bf16.p, n1, ix->d_pad, BN));
-  CKS(encode_rows_map(&ix->tm_xh, ix->x_bf16.p, n1, ix->d_pad, BN / 2));
+  CKS(encode_rows_map(&ix->tm_x, ix->x_bf16.p, n1, ix->d_pad, BN, ix->fmt));
+  CKS(encode_rows_map(&ix->tm_xh, ix->x_bf16.p, n1, ix->d_pad, BN / 2, ix->fmt));
   ix->tm_x_ok = true;
+  ix->generation++;  // the row count and the tensor maps are part of what a captured search holds
   return 0;
 }
+
+int keds_index_operand_format(const keds_index_t* ix) { return ix ? ix->fmt : -1; }
+
+int keds_index_set_operand_format(keds_index_t* ix, int fmt) {
+  if (!ix || fmt < -1 || fmt > FMT_FP16) return fail(KEDS_ERR_ARG, "set_operand_format: fmt must be -1 (auto), 0 (bf16) or 1 (fp16)");
+  DeviceGuard g(ix->device);
+  if (!g.ok) return fail(KEDS_ERR_NO_GPU, "cannot select CUDA device %d", ix->device);
+  ix->fmt_forced = fmt;
+  const int want = choose_format(ix);
+  if (want == ix->fmt) return 0;
+  ix->fmt = want;
+  ix->generation++;
+  if (ix->n == 0) return 0;
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemset(ix->dbstat.p, 0, 16));
+  CKS(prep_db_rows(ix, 0, ix->n));
+  CK(cudaDeviceSynchronize());
+  CKS(encode_rows_map(&ix->tm_x, ix->x_bf16.p, ix->n, ix->d_pad, BN, ix->fmt));
+  CKS(encode_rows_map(&ix->tm_xh, ix->x_bf16.p, ix->n, ix->d_pad, BN / 2, ix->fmt));
+  return 0;
+}
+
+uint64_t keds_index_generation(const keds_index_t* ix) { return ix ? ix->generation : 0; }
 
 int keds_index_reset(keds_index_t* ix) {
   if (!ix) return fail(KEDS_ERR_ARG, "reset: null handle");
@@ -860,7 +1007,9 @@ int keds_index_reset(keds_index_t* ix) {
   ix->bias.release();
   ix->n = 0;
   ix->tm_x_ok = false;
-  CK(cudaMemset(ix->dbstat.p, 0, 8));
+  ix->amax = ix->res_bf16 = ix->res_fp16 = 0.f;
+  ix->generation++;
+  CK(cudaMemset(ix->dbstat.p, 0, 16));
   return 0;
 }
 
@@ -1094,13 +1243,13 @@ int keds_gather_pool(const float* base, int64_t n_base, const int64_t* I, const 
   if (!W) {
     const long long warps = static_cast<long long>(B) * k;
     k_gather_rows<<<static_cast<unsigned>((warps * 32 + 255) / 256), 256, 0, st>>>(
-        base, reinterpret_cast<const long long*>(I), perm, B, k, d, out);
+        base, static_cast<long long>(n_base), reinterpret_cast<const long long*>(I), perm, B, k, d, out);
   } else {
     if (H <= 0) return fail(KEDS_ERR_ARG, "gather_pool: H must be positive with weights");
     const size_t smem = static_cast<size_t>(k) * 8 + static_cast<size_t>(H) * k * 4;
     if (smem > 48 * 1024) return fail(KEDS_ERR_ARG, "gather_pool: H*k too large");
     k_weighted_pool<<<static_cast<unsigned>(B), 256, smem, st>>>(
-        base, reinterpret_cast<const long long*>(I), W, B, k, H, d, out);
+        base, static_cast<long long>(n_base), reinterpret_cast<const long long*>(I), W, B, k, H, d, out);
   }
   CK(cudaGetLastError());
   return 0;
@@ -1123,10 +1272,11 @@ static int merge_impl(const float* Dp, const int64_t* Ip, int64_t stride_d, int6
   const int dev = device_of(D);
   if (dev < 0) return fail(KEDS_ERR_ARG, "topk_merge: device pointers only");
   DeviceGuard g(dev);
-  static bool attr[64] = {false};  // the attribute is per device
-  if (dev >= 64 || !attr[dev]) {
+  // the attribute is per device; IndexShards / IndexReplicas search from one host thread per GPU
+  static std::atomic<bool> attr[64];
+  if (dev >= 64 || !attr[dev].load(std::memory_order_acquire)) {
     CK(cudaFuncSetAttribute(k_topk_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    if (dev < 64) attr[dev] = true;
+    if (dev < 64) attr[dev].store(true, std::memory_order_release);
   }
   // launched behind the local search / the push kernel with the programmatic attribute: its
   // launch latency hides under their tails (it starts with griddepcontrol.wait)
@@ -1178,11 +1328,160 @@ int keds_topk_merge_wait(const float* Dp, const int64_t* Ip, int64_t stride_d, i
   if (!flags || !err_word || my_rank < 0 || my_rank >= parts)
     return fail(KEDS_ERR_ARG, "topk_merge_wait: bad argument");
   MergeWait mw;
+  memset(&mw, 0, sizeof mw);
   mw.flags = flags;
   mw.my_rank = my_rank;
   mw.epoch = epoch;
   mw.err_word = err_word;
   return merge_impl(Dp, Ip, stride_d, stride_i, parts, nq, k, metric, D, I, mw, stream);
+}
+
+// ---- row-sharded search with the exchange fused into the search kernels ------------------------
+struct keds_exchange {
+  int n_ranks = 0, my_rank = 0, device = 0;
+  uint8_t* base[P2P_MAX_RANKS] = {nullptr};  // rank r's symmetric buffer as mapped into this process
+  int64_t buf_bytes = 0, slot_bytes = 0, i_off = 0;
+  uint32_t epoch = 0;
+  DevBuf words;  // [0] ticket, [1] error word, [2..3] pad, then {sum, max, count} wait statistics (u64)
+};
+
+namespace {
+constexpr int64_t EX_FLAG_BYTES = 256;  // 2 parities x P2P_MAX_RANKS flag words at the start of every buffer
+uint8_t* ex_slot(const keds_exchange* ex, int owner, int parity, int r) {
+  return ex->base[owner] + EX_FLAG_BYTES + (static_cast<int64_t>(parity) * ex->n_ranks + r) * ex->slot_bytes;
+}
+uint32_t* ex_flag(const keds_exchange* ex, int owner, int parity, int r) {
+  return reinterpret_cast<uint32_t*>(ex->base[owner]) + parity * P2P_MAX_RANKS + r;
+}
+}  // namespace
+
+int keds_exchange_create(int n_ranks, int my_rank, int device, void* const* peer_base, int64_t buf_bytes,
+                         keds_exchange_t** out) {
+  if (!out) return fail(KEDS_ERR_ARG, "exchange_create: out is null");
+  *out = nullptr;
+  if (n_ranks < 1 || n_ranks > P2P_MAX_RANKS || my_rank < 0 || my_rank >= n_ranks || !peer_base)
+    return fail(KEDS_ERR_ARG, "exchange_create: 1..%d ranks, my_rank inside", P2P_MAX_RANKS);
+  const int64_t slot = (buf_bytes - EX_FLAG_BYTES) / (2 * n_ranks) / 48 * 48;  // D : I = 1 : 2, both 16-byte aligned
+  if (slot < 48) return fail(KEDS_ERR_ARG, "exchange_create: buffer of %lld bytes is too small", (long long)buf_bytes);
+  for (int r = 0; r < n_ranks; ++r)
+    if (!peer_base[r] || (reinterpret_cast<uintptr_t>(peer_base[r]) & 15))
+      return fail(KEDS_ERR_ARG, "exchange_create: peer buffer %d is null or not 16-byte aligned", r);
+  DeviceGuard g(device);
+  if (!g.ok) return fail(KEDS_ERR_NO_GPU, "cannot select CUDA device %d", device);
+  keds_exchange* ex = new keds_exchange();
+  ex->n_ranks = n_ranks;
+  ex->my_rank = my_rank;
+  ex->device = device;
+  for (int r = 0; r < n_ranks; ++r) ex->base[r] = static_cast<uint8_t*>(peer_base[r]);
+  ex->buf_bytes = buf_bytes;
+  ex->slot_bytes = slot;
+  ex->i_off = slot / 3;
+  int s = ex->words.ensure(64);
+  if (s == 0 && cudaMemset(ex->words.p, 0, 64) != cudaSuccess) s = fail(KEDS_ERR_CUDA, "memset failed");
+  if (s != 0) {
+    ex->words.release();
+    delete ex;
+    return s;
+  }
+  *out = ex;
+  return 0;
+}
+
+void keds_exchange_free(keds_exchange_t* ex) {
+  if (!ex) return;
+  DeviceGuard g(ex->device);
+  ex->words.release();
+  delete ex;
+}
+
+int64_t keds_exchange_capacity(const keds_exchange_t* ex) { return ex ? ex->i_off / 4 : -1; }
+
+int keds_index_search_sharded(keds_index_t* ix, keds_exchange_t* ex, const float* q, int64_t nq, int k, float* D,
+                              int64_t* I, void* stream) {
+  if (!ix || !ex || !q || !D || !I || nq <= 0 || k <= 0)
+    return fail(KEDS_ERR_ARG, "search_sharded: null handle / pointer or bad nq / k");
+  if (ex->device != ix->device) return fail(KEDS_ERR_ARG, "search_sharded: exchange and index live on different devices");
+  if (!is_device_ptr(q) || !is_device_ptr(D) || !is_device_ptr(I))
+    return fail(KEDS_ERR_ARG, "search_sharded: device pointers only");
+  if (nq * k > ex->i_off / 4)
+    return fail(KEDS_ERR_ARG, "search_sharded: nq*k = %lld exceeds the exchange capacity %lld", (long long)(nq * k),
+                (long long)(ex->i_off / 4));
+  DeviceGuard g(ix->device);
+  if (!g.ok) return fail(KEDS_ERR_NO_GPU, "cannot select CUDA device %d", ix->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const uint32_t epoch = ++ex->epoch;
+  const int parity = static_cast<int>(epoch & 1u);
+  const int me = ex->my_rank, R = ex->n_ranks;
+  // this rank's block lands in slot `me` of every rank's buffer (its own included: the merge reads it there)
+  uint8_t* mine = ex_slot(ex, me, parity, me);
+  float* Dl = reinterpret_cast<float*>(mine);
+  int64_t* Il = reinterpret_cast<int64_t*>(mine + ex->i_off);
+  PeerOut po;
+  memset(&po, 0, sizeof po);
+  po.n = R;
+  po.my_rank = me;
+  po.publish = 1;
+  po.epoch = epoch;
+  po.ticket = ex->words.as<unsigned int>();
+  for (int r = 0; r < R; ++r) {
+    uint8_t* there = ex_slot(ex, r, parity, me);
+    po.D[r] = reinterpret_cast<float*>(there);
+    po.I[r] = reinterpret_cast<long long*>(there + ex->i_off);
+    po.flag[r] = ex_flag(ex, r, parity, me);
+  }
+  if (ix->n == 0) {
+    // an empty shard still has to deliver (padding) and publish: plain fill + the stand-alone push
+    const long long tot = static_cast<long long>(nq) * k;
+    k_fill_pad<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, st>>>(
+        Dl, reinterpret_cast<long long*>(Il), tot, ix->metric == METRIC_L2 ? FLT_MAX : -FLT_MAX);
+    CK(cudaGetLastError());
+    if (R > 1) {
+      void* dst[P2P_MAX_RANKS];
+      uint32_t* flg[P2P_MAX_RANKS];
+      for (int r = 0; r < R; ++r) {
+        dst[r] = ex_slot(ex, r, parity, me);
+        flg[r] = ex_flag(ex, r, parity, me);
+      }
+      CKS(keds_p2p_push(mine, ex->slot_bytes, dst, flg, R, me, epoch, po.ticket, stream));
+    }
+  } else {
+    keds_index* v[2] = {ix, nullptr};
+    float* Dv[2] = {Dl, nullptr};
+    int64_t* Iv[2] = {Il, nullptr};
+    CKS(search_impl(v, 1, q, nq, k, Dv, Iv, 0u, stream, nullptr, R > 1 ? &po : nullptr));
+  }
+  MergeWait mw;
+  memset(&mw, 0, sizeof mw);
+  if (R > 1) {
+    mw.flags = ex_flag(ex, me, parity, 0);
+    mw.my_rank = me;
+    mw.epoch = epoch;
+    mw.err_word = ex->words.as<unsigned int>() + 1;
+    mw.stats = reinterpret_cast<unsigned long long*>(ex->words.as<uint8_t>() + 16);
+  }
+  uint8_t* parts = ex_slot(ex, me, parity, 0);
+  return merge_impl(reinterpret_cast<const float*>(parts), reinterpret_cast<const int64_t*>(parts + ex->i_off),
+                    ex->slot_bytes / 4, ex->slot_bytes / 8, R, nq, k, ix->metric, D, I, mw, stream);
+}
+
+int keds_exchange_stats(keds_exchange_t* ex, void* stream, double* wait_us_avg, double* wait_us_max,
+                        int64_t* steps, uint32_t* err_word) {
+  if (!ex) return fail(KEDS_ERR_ARG, "exchange_stats: null handle");
+  DeviceGuard g(ex->device);
+  CK(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  uint8_t h[64];
+  CK(cudaMemcpy(h, ex->words.p, 64, cudaMemcpyDeviceToHost));
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(h);
+  const unsigned long long* st = reinterpret_cast<const unsigned long long*>(h + 16);
+  if (wait_us_avg) *wait_us_avg = st[2] ? static_cast<double>(st[0]) / static_cast<double>(st[2]) * 1e-3 : 0.0;
+  if (wait_us_max) *wait_us_max = static_cast<double>(st[1]) * 1e-3;
+  if (steps) *steps = static_cast<int64_t>(st[2]);
+  if (err_word) *err_word = w[1];
+  CK(cudaMemset(ex->words.as<uint8_t>() + 16, 0, 24));  // statistics restart; ticket and error word stay
+  if (w[1] != 0)
+    return fail(KEDS_ERR_KERNEL, "sharded exchange: peer %u did not deliver within the watchdog window (error word 0x%x)",
+                w[1] - 0x500u, w[1]);
+  return 0;
 }
 
 int keds_gallery_rank(const float* Q, int64_t nq, const float* G, int64_t ng, int d,

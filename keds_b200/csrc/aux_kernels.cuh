@@ -3,6 +3,7 @@
 // merge, neighbour gather / weighted pool, gallery rank counting and label-hit counting.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <float.h>
 #include "score_topk_sm100.cuh"
 
@@ -11,7 +12,8 @@ namespace keds {
 constexpr int METRIC_IP = 0;
 constexpr int METRIC_L2 = 1;
 constexpr int RERANK_THREADS = 256;  // ~112 regs/thread: two blocks per SM, one wave for 2 x 128 queries
-constexpr int R_MAX = 512;      // most candidates one query may send to the fp32 re-rank
+constexpr int R_MAX = 1024;     // most candidates one query may send to the fp32 re-rank
+constexpr int P2P_MAX_RANKS = 8;  // GPUs of one box taking part in a row-sharded exchange
 constexpr int K_MAX = 2048;     // largest k (Faiss' GPU flat index has the same limit)
 constexpr int EXACT_THREADS = 256;
 constexpr int EXACT_QG = 8;     // queries scored together against one pass over the rows
@@ -132,13 +134,40 @@ __device__ __forceinline__ unsigned long long order_key(float rank_score, uint32
 }
 
 // ---------------------------------------------------------------------------------------------
-// Operand preparation: fp32 rows -> bf16 rows padded to d_pad, plus the per-row statistics the
-// exactness certificate needs. One warp per row.
-//   stat[r] = { |x|^2, |bf16(x)|, |x - bf16(x)|, 0 }        (optional)
+// Operand preparation: fp32 rows -> 16-bit rows padded to d_pad, plus the per-row statistics the
+// exactness certificate needs. One warp per row. x16 = the row rounded to the operand format.
+//   stat[r] = { |x|^2, |x16|, |x - x16|, 0 }                (optional)
 //   bias[r] = -0.5 |x|^2                                    (optional; L2 ranking bias)
-//   gmax[0] = max_r |bf16(x_r)| , gmax[1] = max_r |x_r - bf16(x_r)|   as float bit patterns
-__global__ void k_prep_rows(const float* __restrict__ x, long long n, int d, int d_pad,
-                            __nv_bfloat16* __restrict__ out, float4* __restrict__ stat,
+//   gmax[0] = max_r |x16_r| , gmax[1] = max_r |x_r - x16_r| , gmax[2] = max_r |x_r|^2   (float bits)
+//
+// Operand format (fmt). FMT_FP16: 11 significant bits -- on unit-norm embeddings the rounding
+// residual |x - x16|, and with it the certificate's error bound, is 8x smaller than bf16's (8
+// bits) at the same tensor-core rate and the same bytes. FMT_BF16 keeps fp32's exponent range and
+// is chosen for data fp16 would overflow or flush (see choose_format in api.cu). Under FMT_FP16
+// values beyond +-65504 are clamped and the row's residual is set to 3e38, so that such a query
+// can only be answered by the exact path.
+constexpr int FMT_BF16 = 0;
+constexpr int FMT_FP16 = 1;
+
+__device__ __forceinline__ unsigned int round_pair(int fmt, float a, float b, float& ra, float& rb, bool& bad) {
+  if (fmt == FMT_FP16) {
+    const float ca = fminf(fmaxf(a, -65504.f), 65504.f), cb = fminf(fmaxf(b, -65504.f), 65504.f);
+    bad = bad || (ca != a) || (cb != b);  // out of range or NaN
+    const __half2 h = __floats2half2_rn(ca, cb);
+    const float2 f = __half22float2(h);
+    ra = f.x;
+    rb = f.y;
+    return *reinterpret_cast<const unsigned int*>(&h);
+  }
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  const float2 f = __bfloat1622float2(h);
+  ra = f.x;
+  rb = f.y;
+  return *reinterpret_cast<const unsigned int*>(&h);
+}
+
+__global__ void k_prep_rows(const float* __restrict__ x, long long n, int d, int d_pad, int fmt,
+                            uint16_t* __restrict__ out, float4* __restrict__ stat,
                             float* __restrict__ bias, unsigned int* __restrict__ gmax,
                             unsigned int* __restrict__ zero_words, int n_zero,
                             unsigned long long* timing) {
@@ -151,11 +180,12 @@ __global__ void k_prep_rows(const float* __restrict__ x, long long n, int d, int
   if (zero_words != nullptr && blockIdx.x == 0 && threadIdx.x < n_zero) zero_words[threadIdx.x] = 0u;
   const long long warp0 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
-  float mx_b = 0.f, mx_d = 0.f;
+  float mx_b = 0.f, mx_d = 0.f, mx_n = 0.f;
   for (long long r = warp0; r < n; r += nwarps) {
     const float* xr = x + r * d;
-    __nv_bfloat16* orow = out + r * d_pad;
+    uint16_t* orow = out + r * d_pad;
     float n2 = 0.f, b2 = 0.f, e2 = 0.f;
+    bool bad = false;
     if ((d & 3) == 0 && (reinterpret_cast<uintptr_t>(xr) & 15) == 0) {
       // 16-byte loads, 8-byte stores (d_pad is a multiple of 64, rows of `out` are 128-B aligned)
       const float4* x4 = reinterpret_cast<const float4*>(xr);
@@ -164,27 +194,25 @@ __global__ void k_prep_rows(const float* __restrict__ x, long long n, int d, int
 #pragma unroll 4
       for (int c = lane; c < dp4; c += 32) {
         const float4 v = c < d4 ? __ldg(x4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y);
-        const __nv_bfloat162 hi = __floats2bfloat162_rn(v.z, v.w);
+        float4 f;
         uint2 pk;
-        pk.x = *reinterpret_cast<const unsigned int*>(&lo);
-        pk.y = *reinterpret_cast<const unsigned int*>(&hi);
+        pk.x = round_pair(fmt, v.x, v.y, f.x, f.y, bad);
+        pk.y = round_pair(fmt, v.z, v.w, f.z, f.w, bad);
         o2[c] = pk;
-        const float2 fl = __bfloat1622float2(lo), fh = __bfloat1622float2(hi);
         n2 = fmaf(v.x, v.x, n2); n2 = fmaf(v.y, v.y, n2); n2 = fmaf(v.z, v.z, n2); n2 = fmaf(v.w, v.w, n2);
-        b2 = fmaf(fl.x, fl.x, b2); b2 = fmaf(fl.y, fl.y, b2); b2 = fmaf(fh.x, fh.x, b2); b2 = fmaf(fh.y, fh.y, b2);
+        b2 = fmaf(f.x, f.x, b2); b2 = fmaf(f.y, f.y, b2); b2 = fmaf(f.z, f.z, b2); b2 = fmaf(f.w, f.w, b2);
         float e;
-        e = v.x - fl.x; e2 = fmaf(e, e, e2);
-        e = v.y - fl.y; e2 = fmaf(e, e, e2);
-        e = v.z - fh.x; e2 = fmaf(e, e, e2);
-        e = v.w - fh.y; e2 = fmaf(e, e, e2);
+        e = v.x - f.x; e2 = fmaf(e, e, e2);
+        e = v.y - f.y; e2 = fmaf(e, e, e2);
+        e = v.z - f.z; e2 = fmaf(e, e, e2);
+        e = v.w - f.w; e2 = fmaf(e, e, e2);
       }
     } else {
       for (int c = lane; c < d_pad; c += 32) {
         const float v = c < d ? xr[c] : 0.f;
-        const __nv_bfloat16 b = __float2bfloat16_rn(v);
-        const float bf = __bfloat162float(b);
-        orow[c] = b;
+        float bf, unused;
+        const unsigned int pk = round_pair(fmt, v, 0.f, bf, unused, bad);
+        orow[c] = static_cast<uint16_t>(pk & 0xFFFFu);
         n2 = fmaf(v, v, n2);
         b2 = fmaf(bf, bf, b2);
         const float e = v - bf;
@@ -194,20 +222,59 @@ __global__ void k_prep_rows(const float* __restrict__ x, long long n, int d, int
     n2 = warp_sum(n2);
     b2 = warp_sum(b2);
     e2 = warp_sum(e2);
-    const float bn = sqrtf(b2), dn = sqrtf(e2);
+    bad = __any_sync(0xffffffffu, bad);
+    const float bn = sqrtf(b2);
+    const float dn = bad ? 3.0e38f : sqrtf(e2);
     if (lane == 0) {
       if (stat != nullptr) stat[r] = make_float4(n2, bn, dn, 0.f);
       if (bias != nullptr) bias[r] = -0.5f * n2;
     }
     mx_b = fmaxf(mx_b, bn);
     mx_d = fmaxf(mx_d, dn);
+    mx_n = fmaxf(mx_n, n2);
   }
   if (gmax != nullptr && lane == 0) {
     // round the maxima up by an ulp-ish factor so they stay upper bounds
     atomicMax(gmax + 0, __float_as_uint(mx_b * 1.000001f));
-    atomicMax(gmax + 1, __float_as_uint(mx_d * 1.000001f));
+    atomicMax(gmax + 1, __float_as_uint(fminf(mx_d * 1.000001f, 3.0e38f)));
+    atomicMax(gmax + 2, __float_as_uint(fminf(mx_n * 1.000001f, 3.0e38f)));
   }
   ktimer_end(timing, t_start);
+}
+
+// Which 16-bit format loses less of these rows? One warp per row.
+//   out[0] = max |x_rc|, out[1] = max_r |x_r - bf16(x_r)|, out[2] = max_r |x_r - fp16(x_r)|
+// as float bit patterns (atomicMax; the caller zeroes them). NaN / inf elements count as inf.
+__global__ void k_probe_rows(const float* __restrict__ x, long long n, int d, unsigned int* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  float amax = 0.f, mx_bf = 0.f, mx_fp = 0.f;
+  for (long long r = warp0; r < n; r += nwarps) {
+    const float* xr = x + r * d;
+    float e_bf = 0.f, e_fp = 0.f;
+    for (int c = lane; c < d; c += 32) {
+      const float v = __ldg(xr + c);
+      const float av = (v == v) ? fabsf(v) : INFINITY;
+      amax = fmaxf(amax, av);
+      float eb = v - __bfloat162float(__float2bfloat16_rn(v));
+      float eh = v - __half2float(__float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f)));
+      e_bf = fmaf(eb, eb, e_bf);
+      e_fp = fmaf(eh, eh, e_fp);
+    }
+    e_bf = warp_sum(e_bf);
+    e_fp = warp_sum(e_fp);
+    mx_bf = fmaxf(mx_bf, sqrtf(e_bf));
+    mx_fp = fmaxf(mx_fp, sqrtf(e_fp));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  if (lane == 0) {
+    const float big = 3.0e38f;
+    atomicMax(out + 0, __float_as_uint(fminf(amax, big)));
+    atomicMax(out + 1, __float_as_uint(mx_bf == mx_bf ? fminf(mx_bf, big) : big));
+    atomicMax(out + 2, __float_as_uint(mx_fp == mx_fp ? fminf(mx_fp, big) : big));
+  }
 }
 
 // In-place L2 normalisation of fp32 rows (x / |x|, zero rows stay zero): the database builder's
@@ -259,6 +326,38 @@ struct ConsumeParams {
   float* pool[2];   // [nq][d]
 };
 
+// Row-sharded exchange fused into the search (p2p_exchange.cuh): the block that has ranked query b
+// also stores that [k] result row into every peer's receive buffer (NVLink P2P stores), and the
+// last block of the search's last kernel publishes the epoch flag. n == 0: off.
+struct PeerOut {
+  int n, my_rank;
+  int publish;                          // this launch is the last writer of the step: publish the flags
+  unsigned int epoch;
+  float* D[P2P_MAX_RANKS];              // where THIS rank's [nq][k] score block lives in rank r's buffer
+  long long* I[P2P_MAX_RANKS];          // ... and its label block
+  unsigned int* flag[P2P_MAX_RANKS];    // "rank my_rank has delivered `epoch`" word in rank r's buffer
+  unsigned int* ticket;                 // local counter for "last block publishes" (zero between launches)
+};
+
+// Store one query's final row to the peers. top_id: local row ids in rank order (0xFFFFFFFF =
+// padding); called by every thread of the block after the row is complete in shared memory.
+__device__ __forceinline__ void push_row_to_peers(const PeerOut& po, long long q, int k,
+                                                  const unsigned int* top_id, const float* top_d,
+                                                  long long id_offset, int metric) {
+  for (int r = 0; r < po.n; ++r) {
+    if (r == po.my_rank) continue;
+    float* Dr = po.D[r] + q * k;
+    long long* Ir = po.I[r] + q * k;
+    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+      const unsigned int id = top_id[j];
+      const bool pad = id == 0xFFFFFFFFu;
+      Dr[j] = pad ? (metric == METRIC_L2 ? FLT_MAX : -FLT_MAX) : top_d[j];
+      Ir[j] = pad ? -1ll : static_cast<long long>(id) + id_offset;
+    }
+  }
+  __threadfence_system();  // ordered before the flag a later block publishes with release.sys
+}
+
 // top_id: local row ids in rank order (0xFFFFFFFF = padding), top_d: their D values.
 // NIF = neighbour rows in flight per warp (2 for latency, 1 where registers are scarce).
 template <int NIF>
@@ -278,6 +377,7 @@ __device__ __forceinline__ void consume_query(const ConsumeParams& c, const floa
   for (int t = 0; t < NIF; ++t) {
     const int jo = (tid >> 5) * NIF + t;
     jr_first[t] = jo < k ? (perm ? perm[jo] : jo) : 0;
+    if (static_cast<unsigned int>(jr_first[t]) >= static_cast<unsigned int>(k)) jr_first[t] = -1;  // bad perm entry: zero row
   }
   if (tid < 32) {
     // weights by one warp (k is small: 16 in KEDs)
@@ -326,7 +426,9 @@ __device__ __forceinline__ void consume_query(const ConsumeParams& c, const floa
           const int jo = jo0 + t;
           // output slot jo shows rank jr
           jr[t] = jo0 == warp * NIF ? jr_first[t] : (jo < k ? (perm ? perm[jo] : jo) : 0);
-          idv[t] = jo < k ? top_id[jr[t]] : 0xFFFFFFFFu;
+          const bool jr_ok = static_cast<unsigned int>(jr[t]) < static_cast<unsigned int>(k);
+          if (!jr_ok) jr[t] = 0;
+          idv[t] = (jo < k && jr_ok) ? top_id[jr[t]] : 0xFFFFFFFFu;
 #pragma unroll
           for (int u = 0; u < U; ++u) {
             const int col = cb + u * 32 + lane;
@@ -377,8 +479,10 @@ __device__ __forceinline__ void consume_query(const ConsumeParams& c, const floa
     for (int col = tid; col < d; col += blockDim.x) {
       float acc = 0.f;
       for (int jo = 0; jo < k; ++jo) {
-        const int j = perm ? perm[jo] : jo;
-        const unsigned int id = top_id[j];
+        int j = perm ? perm[jo] : jo;
+        const bool j_ok = static_cast<unsigned int>(j) < static_cast<unsigned int>(k);
+        if (!j_ok) j = 0;
+        const unsigned int id = j_ok ? top_id[j] : 0xFFFFFFFFu;
         const float v = id != 0xFFFFFFFFu ? rows[static_cast<long long>(id) * d + col] : 0.f;
         if (feat) feat[static_cast<long long>(jo) * d + col] = v;
         acc = fmaf(w[j], v, acc);
@@ -487,6 +591,7 @@ struct MergeWait {
   int my_rank;
   unsigned int epoch;
   unsigned int* err_word;
+  unsigned long long* stats;  // nullable: {sum, max, count} of block 0's wait for the peers, ns (rank skew)
 };
 
 __global__ void k_topk_merge(const float* Dp, const long long* Ip,
@@ -501,7 +606,16 @@ __global__ void k_topk_merge(const float* Dp, const long long* Ip,
   const int tot = parts * k;
   griddep_wait();
   if (mw.flags != nullptr) {
-    if (threadIdx.x == 0) p2p_wait_flags(mw.flags, parts, mw.my_rank, mw.epoch, mw.err_word);
+    if (threadIdx.x == 0) {
+      const unsigned long long t0 = global_timer_ns();
+      p2p_wait_flags(mw.flags, parts, mw.my_rank, mw.epoch, mw.err_word);
+      if (mw.stats != nullptr && blockIdx.x == 0) {
+        const unsigned long long dt = global_timer_ns() - t0;
+        atomicAdd(mw.stats, dt);
+        atomicMax(mw.stats + 1, dt);
+        atomicAdd(mw.stats + 2, 1ull);
+      }
+    }
     __syncthreads();
   }
   for (int i = threadIdx.x; i < tot; i += blockDim.x) {
@@ -549,8 +663,9 @@ __global__ void k_topk_merge(const float* Dp, const long long* Ip,
 //   gather: out[b][j][:] = base[I[b][perm ? perm[j] : j]][:]              (W == nullptr)
 //   pool:   out[b][h][:] = sum_j W[b][h][j] * base[I[b][j]][:]
 // Replaces the CPU index_select + randperm copy + H2D of src/trainer.py:214-230 and the attn@v
-// shaped reduction of src/model/model.py:69-73. Rows with id < 0 read as zeros.
-__global__ void k_gather_rows(const float* __restrict__ base, const long long* __restrict__ I,
+// shaped reduction of src/model/model.py:69-73. Rows with id < 0 or id >= n_base, and slots whose
+// perm entry is outside [0, k), read as zeros.
+__global__ void k_gather_rows(const float* __restrict__ base, long long n_base, const long long* __restrict__ I,
                               const int* __restrict__ perm, long long B, int k, int d,
                               float* __restrict__ out) {
   const int lane = threadIdx.x & 31;
@@ -558,7 +673,9 @@ __global__ void k_gather_rows(const float* __restrict__ base, const long long* _
   if (w >= B * k) return;
   const long long b = w / k;
   const int j = static_cast<int>(w % k);
-  const long long id = I[b * k + (perm ? perm[j] : j)];
+  const int pj = perm ? perm[j] : j;
+  long long id = static_cast<unsigned int>(pj) < static_cast<unsigned int>(k) ? I[b * k + pj] : -1;
+  if (id >= n_base) id = -1;
   float* o = out + w * d;
   if ((d & 3) == 0 && ((reinterpret_cast<uintptr_t>(base) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
     const float4* s4 = reinterpret_cast<const float4*>(base + (id < 0 ? 0 : id) * d);
@@ -570,7 +687,7 @@ __global__ void k_gather_rows(const float* __restrict__ base, const long long* _
   }
 }
 
-__global__ void k_weighted_pool(const float* __restrict__ base, const long long* __restrict__ I,
+__global__ void k_weighted_pool(const float* __restrict__ base, long long n_base, const long long* __restrict__ I,
                                 const float* __restrict__ W, long long B, int k, int H, int d,
                                 float* __restrict__ out) {
   extern __shared__ uint8_t pl_smem[];
@@ -585,7 +702,7 @@ __global__ void k_weighted_pool(const float* __restrict__ base, const long long*
       float acc = 0.f;
       for (int j = 0; j < k; ++j) {
         const long long id = ids[j];
-        if (id >= 0) acc = fmaf(w[h * k + j], __ldg(base + id * d + c), acc);
+        if (id >= 0 && id < n_base) acc = fmaf(w[h * k + j], __ldg(base + id * d + c), acc);
       }
       out[(b * H + h) * d + c] = acc;
     }

@@ -352,10 +352,12 @@ int keds_consumer_forward(keds_consumer_t* c, const float* q, const float* base_
   float* xin = c->xin.as<float>();
   CK(cudaMemcpyAsync(xin, q, static_cast<size_t>(B) * c->d_in * 4, cudaMemcpyDeviceToDevice, st));
   const unsigned gblocks = static_cast<unsigned>((Bk * 32 + 255) / 256);
-  k_gather_rows<<<gblocks, 256, 0, st>>>(base_img, reinterpret_cast<const long long*>(I_img), perm, B, k,
-                                         c->d_in, xin + B * c->d_in);
-  k_gather_rows<<<gblocks, 256, 0, st>>>(base_txt, reinterpret_cast<const long long*>(I_txt), nullptr, B, k,
-                                         c->d_in, xin + (B + Bk) * c->d_in);
+  k_gather_rows<<<gblocks, 256, 0, st>>>(base_img, static_cast<long long>(n_img),
+                                         reinterpret_cast<const long long*>(I_img), perm, B, k, c->d_in,
+                                         xin + B * c->d_in);
+  k_gather_rows<<<gblocks, 256, 0, st>>>(base_txt, static_cast<long long>(n_txt),
+                                         reinterpret_cast<const long long*>(I_txt), nullptr, B, k, c->d_in,
+                                         xin + (B + Bk) * c->d_in);
   CK(cudaGetLastError());
   c->launches += 2;
 

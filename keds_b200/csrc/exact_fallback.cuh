@@ -40,6 +40,9 @@ struct ExactParams {
   unsigned int* done;          // phase-1 units finished (zero at launch)
   int ck_cap;                  // chunk maxima that fit the shared-memory key array of phase 2
   unsigned int* err;           // status word: EXACT_ERR_BARRIER if the barrier watchdog fired
+  const unsigned int* band_dev;  // status word written by the re-rank kernel: largest |C| of this search
+  unsigned int* band_host;     // nullable: mapped host word that receives it (planner feedback, no copy node)
+  PeerOut peer;                // row-sharded exchange (database 0 only); n == 0: off
   unsigned long long* timing;  // nullable in-kernel launch timer
 };
 
@@ -374,9 +377,11 @@ __device__ __forceinline__ void exact_select(const ExactParams& p, uint8_t* ex_s
       Dq[r] = p.metric == METRIC_L2 ? FLT_MAX : -FLT_MAX;
       Iq[r] = -1;
     }
-    if (p.cons.enabled) {
+    if (p.cons.enabled || (p.peer.n > 1 && dbi == 0)) {
       __syncthreads();
-      consume_query<1>(p.cons, e.x_f32, dbi, q, p.k, p.d, p.metric, top_id, top_d, top_w, part);
+      if (p.peer.n > 1 && dbi == 0) push_row_to_peers(p.peer, q, p.k, top_id, top_d, e.id_offset, p.metric);
+      if (p.cons.enabled)
+        consume_query<1>(p.cons, e.x_f32, dbi, q, p.k, p.d, p.metric, top_id, top_d, top_w, part);
     }
   }
 }
@@ -389,6 +394,9 @@ k_exact_fallback(const ExactParams p) {
   extern __shared__ __align__(16) uint8_t ex_smem[];
   __shared__ unsigned int slot;
   const ExactShape sh = exact_shape(p);  // the same in every block: the flag counts are final by now
+  // planner feedback: the search's largest candidate band goes to a mapped host word (a posted
+  // write; the host reads it, possibly a search late, when it plans the next call)
+  if (p.band_host != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *p.band_host = *p.band_dev;
   if (sh.F[0] + sh.F[1] > 0) {
     exact_scores(p, sh, ex_smem, &slot);
     const unsigned int items = static_cast<unsigned int>(sh.F[0] + sh.F[1]);
@@ -397,6 +405,22 @@ k_exact_fallback(const ExactParams p) {
       if (it >= items) break;
       const int dbi = it < static_cast<unsigned int>(sh.F[0]) ? 0 : 1;
       exact_select(p, ex_smem, dbi, static_cast<int>(dbi == 0 ? it : it - sh.F[0]));
+    }
+  }
+  if (p.peer.n > 1 && p.peer.publish) {
+    // Row-sharded exchange: every result row of this step has been stored to the peers by now --
+    // by the re-rank kernel (complete before this grid started) or by the blocks of this grid,
+    // each of which fenced its stores. The last block to get here publishes the epoch.
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) slot = atomicAdd(p.peer.ticket, 1u);
+    __syncthreads();
+    if (slot == gridDim.x - 1) {
+      if (threadIdx.x < p.peer.n && static_cast<int>(threadIdx.x) != p.peer.my_rank) {
+        __threadfence_system();
+        st_release_sys(p.peer.flag[threadIdx.x], p.peer.epoch);
+      }
+      if (threadIdx.x == 0) *p.peer.ticket = 0u;
     }
   }
   ktimer_end(p.timing, t_start);

@@ -8,8 +8,6 @@
 
 namespace keds {
 
-constexpr int P2P_MAX_RANKS = 8;
-
 struct P2PPush {
   int n_ranks, my_rank;
   unsigned int epoch;
@@ -19,15 +17,6 @@ struct P2PPush {
   unsigned int* flag[P2P_MAX_RANKS];   // flag word "rank my_rank has delivered" in each rank's buffer
   unsigned int* ticket;                // local counter for "last CTA publishes"
 };
-
-__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
 
 __global__ void __launch_bounds__(256)
 k_p2p_push(const P2PPush p) {

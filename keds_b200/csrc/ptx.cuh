@@ -45,6 +45,16 @@ __device__ __forceinline__ void ktimer_end(unsigned long long* t, unsigned long 
   }
 }
 
+// ---------------------------------------------------------------- system-scope flags (NVLink peers)
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -242,6 +252,12 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
 // Instruction descriptor, kind::f16: A=B=bf16, D=fp32, both operands K-major, dense.
 __host__ __device__ constexpr uint32_t idesc_bf16_f32(uint32_t M, uint32_t N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+// The operand-format bits of that descriptor (a_format [7,10), b_format [10,13)): 1 = bf16,
+// 0 = fp16. The scoring kernel takes the format at run time: idesc_f16_base | kIdescBf16Bits.
+constexpr uint32_t kIdescBf16Bits = (1u << 7) | (1u << 10);
+__host__ __device__ constexpr uint32_t idesc_f16_base(uint32_t M, uint32_t N) {
+  return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
 // kind::tf32: A=B=tf32 (fp32 words in shared memory, 8 per K step), D=fp32, K-major, dense.

@@ -32,6 +32,9 @@ struct RerankParams {
   int* flagged[2];
   int* n_flagged[2];
   float eps_scale;           // 1.0 normally; tests shrink/grow it to exercise the fallback
+  int rmax;                  // candidate capacity of this launch (<= R_MAX; sizes the shared arrays)
+  unsigned int* band_max;    // status word: largest |C| of this search (feeds the planner's next slice count)
+  PeerOut peer;              // row-sharded exchange (database 0 only); n == 0: off
   unsigned long long* timing;  // nullable in-kernel launch timer
 };
 
@@ -50,14 +53,15 @@ k_select_rerank(const RerankParams p) {
   // shared layout
   float* qvec = reinterpret_cast<float*>(rr_smem);                       // d (16-B aligned)
   float4* part = reinterpret_cast<float4*>(qvec + ((p.d + 3) & ~3));     // cons.part4
-  unsigned int* keys = reinterpret_cast<unsigned int*>(part + p.cons.part4);  // slots
+  unsigned long long* okey = reinterpret_cast<unsigned long long*>(part + p.cons.part4);  // R_MAX order keys
+  unsigned int* keys = reinterpret_cast<unsigned int*>(okey + p.rmax);   // slots
   unsigned int* ids = keys + slots;                                      // slots
   unsigned int* smax = ids + slots;                                      // S   slice maxima (keys)
-  unsigned int* a_key = smax + p.S;                                      // R_MAX survivors
-  unsigned int* a_id = a_key + R_MAX;                                    // R_MAX
-  unsigned int* sel_id = a_id + R_MAX;                                   // R_MAX  the set C
-  float* sel_sc = reinterpret_cast<float*>(sel_id + R_MAX);              // R_MAX
-  unsigned int* hist = reinterpret_cast<unsigned int*>(sel_sc + R_MAX);  // 256 (radix path only)
+  unsigned int* a_key = smax + p.S;                                      // rmax survivors
+  unsigned int* a_id = a_key + p.rmax;                                   // rmax
+  unsigned int* sel_id = a_id + p.rmax;                                  // rmax  the set C
+  float* sel_sc = reinterpret_cast<float*>(sel_id + p.rmax);             // rmax
+  unsigned int* hist = reinterpret_cast<unsigned int*>(sel_sc + p.rmax); // 256 (radix path only)
   float* red = reinterpret_cast<float*>(hist + 256);                     // 32
   unsigned int* bcast = reinterpret_cast<unsigned int*>(red + 32);       // 4
   int* counters = reinterpret_cast<int*>(bcast + 4);                     // 4
@@ -72,6 +76,7 @@ k_select_rerank(const RerankParams p) {
   for (int c = tid; c < p.d; c += blockDim.x) qvec[c] = p.q_f32[static_cast<long long>(q) * p.d + c];
   const float xb = __uint_as_float(p.dbstat[db][0]);
   const float xd = __uint_as_float(p.dbstat[db][1]);
+  const float xn2 = __uint_as_float(p.dbstat[db][2]);
   griddep_wait();  // candidates (and qstat from k_prep_rows) are visible from here on
   const unsigned long long t_start = ktimer_begin(p.timing);
 
@@ -136,11 +141,17 @@ k_select_rerank(const RerankParams p) {
   for (int w = 1; w < nwarps; ++w) th_max = fmaxf(th_max, red[w]);
   const int n = counters[3];
 
-  // eps: |a - s| <= |dq| |bf(x)| + |q| |dx| + accumulation allowance
+  // eps: |a - s| <= |dq| |x16| + |q| |dx| + accumulation allowance (x16 / q16: the operands as
+  // rounded to the 16-bit format, dq / dx the rounding residuals). Under L2 the approximate score
+  // also carries bias = fl(-0.5 fl(|x|^2)) and one more fp32 add: |x|^2 is a 24-term chain per lane
+  // plus a 5-level tree (<= 29 roundings), so 0.5 * 30 * 2^-24 |x|^2 covers the bias and
+  // 2^-23 (|a| + |bias|) the add.
   const float qn = sqrtf(qs.x);
   const int d_pad = (p.d + BK - 1) / BK * BK;
   float eps = qs.z * xb + qn * xd + (static_cast<float>(d_pad) * 2.4e-7f) * qs.y * xb;
+  if (p.metric == METRIC_L2) eps += 1.0e-6f * xn2 + 1.2e-7f * (qs.y * xb + 0.5f * xn2);
   eps *= 1.0001f * p.eps_scale;
+  if (!(eps == eps)) eps = INFINITY;  // inf * 0 from a degenerate query: nothing is certified
 
   // ---- B: survivors A' = { a >= t0 - 2 eps } with t0 <= a_(k) a cheap lower bound, so that
   // C = { a >= a_(k) - 2 eps } is a subset of A'.
@@ -178,7 +189,7 @@ k_select_rerank(const RerankParams p) {
           if (lane == 0) base = atomicAdd(&counters[2], __popc(bal));
           base = __shfl_sync(0xffffffffu, base, 0);
           const int pos = base + __popc(bal & ((1u << lane) - 1u));
-          if (hit && pos < R_MAX) {
+          if (hit && pos < p.rmax) {
             a_key[pos] = key;
             a_id[pos] = id;
           }
@@ -186,21 +197,26 @@ k_select_rerank(const RerankParams p) {
       }
       __syncthreads();  // (3)
       const int na = counters[2];
-      if (na <= R_MAX) {
-        // a_(k): the survivor with fewer than k keys above it and at least k keys at or above it
-        for (int c = tid; c < na; c += blockDim.x) {
-          const unsigned int mine = a_key[c];
-          int gt = 0, ge = 0;
+      if (na <= p.rmax) {
+        if (na <= 256) {
+          // a_(k): the survivor with fewer than k keys above it and at least k keys at or above it
+          for (int c = tid; c < na; c += blockDim.x) {
+            const unsigned int mine = a_key[c];
+            int gt = 0, ge = 0;
 #pragma unroll 8
-          for (int j = 0; j < na; ++j) {
-            const unsigned int o = a_key[j];
-            gt += o > mine;
-            ge += o >= mine;
+            for (int j = 0; j < na; ++j) {
+              const unsigned int o = a_key[j];
+              gt += o > mine;
+              ge += o >= mine;
+            }
+            if (gt < p.k && ge >= p.k) bcast[3] = mine;
           }
-          if (gt < p.k && ge >= p.k) bcast[3] = mine;
+          __syncthreads();  // (4)
+          kth = bcast[3];
+        } else {
+          // crowded band (clustered data): the quadratic count would dominate -- radix select
+          kth = block_kth_largest(a_key, na, p.k, hist, bcast);
         }
-        __syncthreads();  // (4)
-        kth = bcast[3];
         tau = key_to_f32(kth) - 2.f * eps;
         // C = survivors at or above tau
         for (int c = tid; c < na; c += blockDim.x) {
@@ -235,7 +251,7 @@ k_select_rerank(const RerankParams p) {
         const unsigned int id = ids[i];
         if (id != PAD_ID && key_to_f32(keys[i]) >= tau) {
           const int pos = atomicAdd(&counters[1], 1);
-          if (pos < R_MAX) sel_id[pos] = id;
+          if (pos < p.rmax) sel_id[pos] = id;
         }
       }
     } else {
@@ -250,7 +266,7 @@ k_select_rerank(const RerankParams p) {
         const unsigned int id = ids[i];
         if (id != PAD_ID && key_to_f32(keys[i]) >= tau) {
           const int pos = atomicAdd(&counters[1], 1);
-          if (pos < R_MAX) sel_id[pos] = id;
+          if (pos < p.rmax) sel_id[pos] = id;
         }
       }
     }
@@ -260,18 +276,22 @@ k_select_rerank(const RerankParams p) {
       const unsigned int id = ids[i];
       if (id != PAD_ID) {
         const int pos = atomicAdd(&counters[1], 1);
-        if (pos < R_MAX) sel_id[pos] = id;
+        if (pos < p.rmax) sel_id[pos] = id;
       }
     }
   }
   __syncthreads();  // (5)
   int m = counters[1];
-  const bool ok = (m <= R_MAX) && (th_max == -INFINITY || th_max < tau);
-  if (!ok && tid == 0) {
-    const int pos = atomicAdd(p.n_flagged[db], 1);
-    p.flagged[db][pos] = q;
+  const bool ok = (m <= p.rmax) && (th_max == -INFINITY || th_max < tau);
+  if (tid == 0) {
+    if (!ok) {
+      const int pos = atomicAdd(p.n_flagged[db], 1);
+      p.flagged[db][pos] = q;
+    }
+    // an unusually crowded band is reported to the host planner (more slices next time)
+    if (p.band_max != nullptr && m > 2 * p.k) atomicMax(p.band_max, static_cast<unsigned int>(m));
   }
-  m = min(m, R_MAX);
+  m = min(m, p.rmax);
 
   // ---- C: exact fp32 scores of the candidates, R rows per warp in flight
   const float* xbase = p.x_f32[db];
@@ -293,14 +313,27 @@ k_select_rerank(const RerankParams p) {
   // ---- D: order by (score desc, id asc), write the top k
   float* Dq = p.D[db] + static_cast<long long>(q) * p.k;
   long long* Iq = p.I[db] + static_cast<long long>(q) * p.k;
+  if (m > 64) {
+    // many candidates: build the 64-bit order keys once instead of inside the quadratic loop
+    for (int c = tid; c < m; c += blockDim.x) {
+      const float sc = sel_sc[c];
+      okey[c] = order_key(p.metric == METRIC_L2 ? -sc : sc, sel_id[c]);
+    }
+    __syncthreads();
+  }
   for (int c = tid; c < m; c += blockDim.x) {
     const float sc = sel_sc[c];
     const unsigned long long mine = order_key(p.metric == METRIC_L2 ? -sc : sc, sel_id[c]);
     int rank = 0;
+    if (m > 64) {
 #pragma unroll 8
-    for (int j = 0; j < m; ++j) {
-      const float sj = sel_sc[j];
-      rank += order_key(p.metric == METRIC_L2 ? -sj : sj, sel_id[j]) > mine;
+      for (int j = 0; j < m; ++j) rank += okey[j] > mine;
+    } else {
+#pragma unroll 8
+      for (int j = 0; j < m; ++j) {
+        const float sj = sel_sc[j];
+        rank += order_key(p.metric == METRIC_L2 ? -sj : sj, sel_id[j]) > mine;
+      }
     }
     if (rank < p.k) {
       Dq[rank] = sc;
@@ -313,10 +346,14 @@ k_select_rerank(const RerankParams p) {
     Dq[r] = p.metric == METRIC_L2 ? FLT_MAX : -FLT_MAX;
     Iq[r] = -1;
   }
-  // a flagged query is consumed by the exact fallback instead, once its answer is final
-  if (p.cons.enabled && ok) {
+  // a flagged query is consumed (and sent to the peers) by the exact fallback instead, once its
+  // answer is final
+  if (ok && (p.cons.enabled || (p.peer.n > 1 && db == 0))) {
     __syncthreads();  // (7)
-    consume_query<(R >= 2 ? 2 : 1)>(p.cons, xbase, db, q, p.k, p.d, p.metric, top_id, top_d, top_w, part);
+    if (p.peer.n > 1 && db == 0)
+      push_row_to_peers(p.peer, q, p.k, top_id, top_d, p.id_offset[db], p.metric);
+    if (p.cons.enabled)
+      consume_query<(R >= 2 ? 2 : 1)>(p.cons, xbase, db, q, p.k, p.d, p.metric, top_id, top_d, top_w, part);
   }
   ktimer_end(p.timing, t_start);
 }

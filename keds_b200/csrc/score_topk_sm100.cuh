@@ -1,4 +1,5 @@
-// Fused bf16 scoring GEMM + per-query candidate selection for sm_100a.
+// Fused 16-bit (fp16 or bf16 operands, fp32 accumulate) scoring GEMM + per-query candidate
+// selection for sm_100a.
 //
 // Replaces the "SGEMM tile -> HBM -> k-select" pair inside the Faiss GPU flat index that KEDs
 // calls at src/trainer.py:213,221,271 and src/eval_utils.py:169,177. The [queries x rows] score
@@ -63,6 +64,7 @@ struct ScoreParams {
   int S;             // row slices per (db, query tile)
   int n_items;       // n_db * S * n_qg ; item = ((db * S) + s) * n_qg + qg
   int kblocks;       // d_pad / BK
+  uint32_t fmt_bits; // operand format bits of the instruction descriptor (kIdescBf16Bits, or 0 = fp16)
   int nq;            // live queries
   int n_rows[2];     // rows per database
   int n_tiles[2];    // ceil(n_rows / BN)
@@ -290,7 +292,7 @@ k_score_topk(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (pair: leader only)
     if (lane == 0 && crank == 0) {
-      constexpr uint32_t idesc = idesc_bf16_f32(kPair ? 2 * BM : BM, BN);
+      const uint32_t idesc = idesc_f16_base(kPair ? 2 * BM : BM, BN) | p.fmt_bits;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;

@@ -156,6 +156,22 @@ class GpuIndexFlat:
     def set_eps_scale(self, scale: float) -> None:
         _capi.check(self._lib.keds_index_set_eps_scale(self._h, float(scale)))
 
+    @property
+    def operand_format(self) -> str:
+        """16-bit operand format of the tensor-core pass: 'fp16' or 'bf16' (chosen from the rows)."""
+        return {0: "bf16", 1: "fp16"}[int(self._lib.keds_index_operand_format(self._h))]
+
+    def set_operand_format(self, fmt: Optional[str]) -> None:
+        """Pin the operand format ('bf16' / 'fp16') or return to the automatic choice (None)."""
+        code = {None: -1, "auto": -1, "bf16": 0, "fp16": 1}[fmt]
+        _capi.check(self._lib.keds_index_set_operand_format(self._h, code))
+
+    @property
+    def generation(self) -> int:
+        """Changes whenever a device buffer of the handle moves or its rows change; owners of a CUDA
+        graph captured over a search compare it before every replay."""
+        return int(self._lib.keds_index_generation(self._h))
+
     # -- add
     def add(self, x, normalize: bool = False) -> None:
         """index.add(x). normalize=True L2-normalises the rows on the device as they are added."""

@@ -53,6 +53,10 @@ def gallery_rank(query: torch.Tensor, gallery: torch.Tensor, target, exclude=Non
     if exclude is not None:
         e = torch.as_tensor(np.asarray(exclude) if not isinstance(exclude, torch.Tensor) else exclude)
         e = e.to(device=dev, dtype=torch.int64).contiguous()
+        if e.numel() != Q.shape[0]:
+            raise ValueError("one excluded row (or -1) per query")
+        if e.numel() and (int(e.min()) < -1 or int(e.max()) >= G.shape[0]):
+            raise IndexError("excluded id outside the gallery")
         e_ptr = e.data_ptr()
     out = torch.empty(Q.shape[0], dtype=torch.int64, device=dev)
     with torch.cuda.device(dev):
@@ -116,13 +120,15 @@ def get_cirr_testoutput(image_features, ref_features, reference_names, index_nam
     ref = np.array([pos[n] for n in reference_names], np.int64)
     ix = GpuIndexFlat(G.shape[1], METRIC_INNER_PRODUCT, dev.index)
     ix.add(G)
-    kk = min(51, G.shape[0])
-    _, I = ix.search(Q, kk)
+    if G.shape[0] < 51:  # the reference indexes sorted names [0, 50) after the removal (:1084-1086)
+        raise IndexError("get_cirr_testoutput needs at least 51 gallery images (50 names per pair after "
+                         "removing the reference image)")
+    _, I = ix.search(Q, 51)
     I = I.cpu().numpy()
     result = {"version": "rc2", "metric": "recall"}
     for ind in range(len(id_names)):
         pairid = str(id_names[ind].item() if hasattr(id_names[ind], "item") else id_names[ind])
-        row = [j for j in I[ind] if j != ref[ind] and j >= 0][:50]
+        row = [j for j in I[ind] if j != ref[ind]][:50]
         result[pairid] = [index_names[j].replace(".png", "") for j in row]
     return result
 

@@ -100,7 +100,7 @@ class KnowledgeBase:
         image_bases = torch.load(image_pt, map_location="cpu")
         text_bases = torch.load(text_pt, map_location="cpu")
         with open(names_txt) as f:
-            basenames = [line.rstrip("\n") for line in f]
+            basenames = [line.strip() for line in f]  # line.strip(), as src/main.py:474-475
         return cls(image_bases, text_bases, basenames, device, metric)
 
     # sequence protocol: database[0..4]
@@ -229,6 +229,11 @@ class RetrievalStep:
         # fp32 fallback -- tens of milliseconds per warm-up run.)
         self.q_host.normal_(generator=torch.Generator().manual_seed(0))
         self.q_host.div_(self.q_host.norm(dim=1, keepdim=True))
+        self.recaptures = -1
+        self._capture()
+
+    def _capture(self) -> None:
+        dev = self.q_dev.device
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
@@ -240,6 +245,11 @@ class RetrievalStep:
             with torch.cuda.graph(self.graph, stream=side):
                 self._body()
         torch.cuda.current_stream(dev).wait_stream(side)
+        # The graph holds raw addresses of the handles' scratch and row buffers. Any other call on
+        # the same handles may move them (a larger batch or k, index.add): the handles count such
+        # moves, and run() re-captures instead of replaying over freed memory.
+        self._gen = (self.ia.generation, self.ib.generation)
+        self.recaptures += 1
 
     def _body(self) -> None:
         self.q_dev.copy_(self.q_host, non_blocking=True)
@@ -249,6 +259,8 @@ class RetrievalStep:
     def run(self, q: Optional[torch.Tensor] = None, sync: bool = True) -> dict:
         if q is not None:
             self.q_host.copy_(q)
+        if (self.ia.generation, self.ib.generation) != self._gen:
+            self._capture()  # reads q_host only; the batch just written stays in place
         self.graph.replay()
         if sync:
             torch.cuda.current_stream(self.q_dev.device).synchronize()

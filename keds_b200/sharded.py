@@ -1,7 +1,8 @@
 """Row-sharded knowledge database across the GPUs of one box: one process per GPU
 (torch.distributed), every rank holds rows [lo_r, hi_r) and answers the full query batch locally
-with exact fp32-re-ranked scores and GLOBAL labels; one packed all-gather of [B, k] (score, label)
-blocks over NVLink (NCCL) and a merge kernel give every rank the global top-k.  The result is
+with exact fp32-re-ranked scores and GLOBAL labels; the [B, k] (score, label) blocks cross NVLink --
+stored by the search kernels themselves into the peers' buffers (exchange="fused") or with one packed
+NCCL all-gather (exchange="nccl") -- and a merge kernel gives every rank the global top-k.  The result is
 bit-identical for 1, 2, 4 or 8 shards (same scores, same total order).
 
 The reference has no such path (full replica per DDP rank: src/main.py:76,82; replicas in eval:
@@ -37,52 +38,71 @@ def packed_layout(nq: int, k: int) -> Tuple[int, int, int]:
     return off_i + nq * k * 8, off_i, d_bytes
 
 
-class _PeerExchange:
-    """Symmetric (peer-mapped) exchange buffers for one (nq, k) shape: two parities of
-    [world] result blocks + per-parity flag words, allocated with torch symmetric memory so that
-    every rank holds raw pointers into every other rank's copy (NVLink P2P)."""
+class _FusedExchange:
+    """Symmetric (peer-mapped) receive buffers + the native exchange handle over them. The buffer
+    is allocated with torch symmetric memory, so every rank holds raw pointers into every other
+    rank's copy (NVLink P2P through NVSwitch); the library lays it out (flag words, two parities
+    of one slot per rank) and never sees torch types."""
 
-    def __init__(self, world: int, rank: int, slot_bytes: int, device: torch.device, group) -> None:
+    def __init__(self, world: int, rank: int, capacity: int, device: torch.device, group) -> None:
+        import ctypes as C
         import torch.distributed._symmetric_memory as symm_mem
 
-        self.world, self.rank, self.slot = world, rank, slot_bytes
-        self.flags_off = 2 * world * slot_bytes
-        total = self.flags_off + 2 * world * 4
-        total = (total + 255) // 256 * 256
+        lib = _capi.load()
+        slot = -(-(12 * capacity) // 48) * 48
+        total = (256 + 2 * world * slot + 255) // 256 * 256
         self.buf = symm_mem.empty(total, dtype=torch.uint8, device=device)
         self.buf.zero_()
         torch.cuda.synchronize(device)
         self.hdl = symm_mem.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
-        self.peer_base = [int(p) for p in self.hdl.buffer_ptrs]
-        assert self.peer_base[rank] == self.buf.data_ptr()
-        self.ticket = torch.zeros(1, dtype=torch.int32, device=device)
-        self.err = torch.zeros(1, dtype=torch.int32, device=device)
-        self.epoch = 0
-        self.ptrs = [None, None]  # per parity: (ctypes peer block pointers, ctypes peer flag pointers)
+        peers = [int(p) for p in self.hdl.buffer_ptrs]
+        assert peers[rank] == self.buf.data_ptr()
+        h = C.c_void_p()
+        _capi.check(lib.keds_exchange_create(world, rank, device.index, (C.c_void_p * world)(*peers), total, C.byref(h)))
+        self.handle, self._lib = h, lib
+        self.capacity = int(lib.keds_exchange_capacity(h))
+        assert self.capacity >= capacity
         self.hdl.barrier()  # every rank's buffer is zeroed before anyone pushes
 
-    def region(self, parity: int, r: int) -> int:
-        return (parity * self.world + r) * self.slot
+    def stats(self, stream_ptr: int) -> dict:
+        import ctypes as C
+
+        avg, mx, n, err = C.c_double(0), C.c_double(0), C.c_int64(0), C.c_uint32(0)
+        _capi.check(self._lib.keds_exchange_stats(self.handle, stream_ptr, C.byref(avg), C.byref(mx), C.byref(n),
+                                                  C.byref(err)))
+        return {"wait_us_avg": float(avg.value), "wait_us_max": float(mx.value), "merges": int(n.value)}
+
+    def __del__(self) -> None:
+        h = getattr(self, "handle", None)
+        if h is not None and h.value:
+            try:
+                self._lib.keds_exchange_free(h)
+            except Exception:
+                pass
+            self.handle = None
 
 
 class ShardedIndex:
-    """exchange="nccl": one packed all-gather per search (default).
-    exchange="p2p":  no collective call in the step -- every rank stores its block straight into
-    the peers' buffers over NVLink and the merge kernel waits on epoch flags (needs torch symmetric
-    memory and peer access between the GPUs of the box)."""
+    """exchange="fused" (default on GPUs): no collective call and no copy kernel in the step -- the
+    search kernels store every finished result row straight into the peers' buffers over NVLink,
+    the chain's last block publishes an epoch flag and the merge kernel waits on the peers' flags
+    (keds_index_search_sharded; needs torch symmetric memory and peer access inside the box).
+    exchange="nccl": one packed all-gather per search, then the merge kernel."""
 
     def __init__(self, d: int, metric: int, device: Optional[int] = None, group=None,
-                 exchange: str = "nccl", _local_index=None, _merge: Optional[Callable] = None) -> None:
+                 exchange: str = "fused", _local_index=None, _merge: Optional[Callable] = None) -> None:
         if not dist.is_initialized():
             raise RuntimeError("ShardedIndex needs an initialised torch.distributed process group")
-        if exchange not in ("nccl", "p2p"):
-            raise ValueError("exchange must be 'nccl' or 'p2p'")
+        if exchange == "p2p":
+            exchange = "fused"
+        if exchange not in ("nccl", "fused"):
+            raise ValueError("exchange must be 'nccl' or 'fused'")
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         self.d, self.metric_type = int(d), int(metric)
         self.exchange = exchange
-        self._px = {}  # (nq, k) -> _PeerExchange
+        self._fx: Optional[_FusedExchange] = None
         self._merge = _merge
         if _local_index is not None:
             self.local = _local_index
@@ -106,12 +126,13 @@ class ShardedIndex:
         lo, hi = shard_bounds(int(x.shape[0]), self.world, self.rank)
         self.add_local(x[lo:hi], lo, int(x.shape[0]))
 
-    def search(self, q: torch.Tensor, k: int):
-        """q: [nq, d] float32 on this rank's device, identical on all ranks. Returns (D, I)."""
+    def search(self, q: torch.Tensor, k: int, out=None):
+        """q: [nq, d] float32 on this rank's device, identical on all ranks. Returns (D, I);
+        `out=(D, I)` may name preallocated contiguous device tensors to fill (fused exchange)."""
         nq = int(q.shape[0])
         total, off_i, d_bytes = packed_layout(nq, k)
-        if self.exchange == "p2p" and isinstance(self.local, GpuIndexFlat) and self.world > 1:
-            return self._search_p2p(q, nq, k, total, off_i, d_bytes)
+        if self.exchange == "fused" and isinstance(self.local, GpuIndexFlat):
+            return self._search_fused(q, nq, k, out)
         if isinstance(self.local, GpuIndexFlat):
             # the local search writes straight into the exchange buffer: no repacking copies
             send = torch.empty(total, dtype=torch.uint8, device=q.device)
@@ -140,47 +161,36 @@ class ShardedIndex:
         )
         return Dg, Ig
 
-    def _search_p2p(self, q: torch.Tensor, nq: int, k: int, total: int, off_i: int, d_bytes: int):
-        """local search -> k_p2p_push (stores into every peer + epoch flag) -> merge that waits on
-        the peers' flags. Parities alternate so a fast rank never overwrites a block a slow rank is
-        still merging (a rank can only publish step t+1 after finishing its merge of step t)."""
-        import ctypes as C
-
+    def _search_fused(self, q: torch.Tensor, nq: int, k: int, out=None):
+        """One native call: local search with the peer stores fused into its kernels, flag
+        publication by the chain's last block, merge that waits on the peers' flags. Two buffer
+        parities keep a fast rank from overwriting a block a slow rank is still merging (a rank can
+        only publish step t+1 after finishing its merge of step t)."""
         lib = _capi.load()
-        slot = (total + 15) // 16 * 16
-        px = self._px.get((nq, k))
-        if px is None:
-            px = self._px[(nq, k)] = _PeerExchange(self.world, self.rank, slot, q.device, self.group)
-        px.epoch += 1
-        parity = px.epoch & 1
-        mine = px.region(parity, self.rank)
-        blk = px.buf[mine:mine + total]
-        self.local.search(q, k, out=(blk[:d_bytes].view(torch.float32), blk[off_i:].view(torch.int64)))
-        stream = _stream_ptr(self.device.index)
-        if px.ptrs[parity] is None:  # pointer tables are fixed per parity: build them once
-            vp = C.c_void_p * self.world
-            px.ptrs[parity] = (
-                vp(*[px.peer_base[r] + mine for r in range(self.world)]),
-                vp(*[px.peer_base[r] + px.flags_off + (parity * self.world + self.rank) * 4
-                     for r in range(self.world)]),
-            )
-        dst, flg = px.ptrs[parity]
-        _capi.check(lib.keds_p2p_push(px.buf.data_ptr() + mine, slot, dst, flg, self.world, self.rank, px.epoch,
-                                      px.ticket.data_ptr(), stream))
-        Dg = torch.empty((nq, k), dtype=torch.float32, device=q.device)
-        Ig = torch.empty((nq, k), dtype=torch.int64, device=q.device)
-        base = px.buf.data_ptr() + px.region(parity, 0)
-        flags = px.buf.data_ptr() + px.flags_off + parity * self.world * 4
-        _capi.check(
-            lib.keds_topk_merge_wait(base, base + off_i, slot // 4, slot // 8, self.world, nq, k, self.metric_type,
-                                     Dg.data_ptr(), Ig.data_ptr(), flags, self.rank, px.epoch, px.err.data_ptr(),
-                                     stream)
-        )
+        q = self.local._check_q_tensor(q)
+        if self._fx is None or self._fx.capacity < nq * k:
+            # (re)allocation is collective: every rank sees the same shapes in the same order
+            if self._fx is not None:
+                torch.cuda.synchronize(self.device)
+                dist.barrier(group=self.group)
+            self._fx = _FusedExchange(self.world, self.rank, max(nq * k, 8192), self.device, self.group)
+        if out is not None:
+            Dg, Ig = out
+            assert Dg.is_cuda and Ig.is_cuda and Dg.is_contiguous() and Ig.is_contiguous()
+            assert Dg.dtype == torch.float32 and Ig.dtype == torch.int64 and Dg.numel() == nq * k == Ig.numel()
+        else:
+            Dg = torch.empty((nq, k), dtype=torch.float32, device=q.device)
+            Ig = torch.empty((nq, k), dtype=torch.int64, device=q.device)
+        _capi.check(lib.keds_index_search_sharded(self.local._h, self._fx.handle, q.data_ptr(), nq, k, Dg.data_ptr(),
+                                                  Ig.data_ptr(), _stream_ptr(self.device.index)))
         return Dg, Ig
 
+    def exchange_stats(self) -> dict:
+        """Synchronise and report how long the merge waited for the peers (rank skew); raises if a
+        peer failed to deliver within the watchdog window."""
+        if self._fx is None:
+            return {}
+        return self._fx.stats(_stream_ptr(self.device.index))
+
     def check_exchange(self) -> None:
-        """Raise if a peer failed to deliver within the watchdog window of any p2p merge so far."""
-        for px in self._px.values():
-            e = int(px.err.item())
-            if e:
-                raise RuntimeError(f"p2p exchange: peer {e - 0x500} did not deliver (error word {e:#x})")
+        self.exchange_stats()

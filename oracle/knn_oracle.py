@@ -174,6 +174,22 @@ def metrics_cirr(image_features, ref_features, reference_names, index_names, tar
     return {f"recall_R@{k}": float(np.sum(r < k)) / len(r) * 100 for k in [1, 5, 10, 50, 100]}
 
 
+def cirr_testoutput(image_features, ref_features, reference_names, index_names, id_names) -> Dict:
+    """get_cirr_testoutput (src/eval_utils.py:1070-1087): gallery names in ascending 1 - q.g order
+    (float64 here, ties by lower gallery row), the query's own reference image removed (:1076-1080;
+    names are matched raw, no basename), the first 50 kept, ".png" stripped (:1082-1086). Raises
+    like the reference (IndexError) when fewer than 50 names remain."""
+    s = np.asarray(ref_features, np.float64) @ np.asarray(image_features, np.float64).T
+    pos = {n: i for i, n in enumerate(index_names)}
+    out: Dict = {"version": "rc2", "metric": "recall"}
+    for ind in range(len(id_names)):
+        order = np.lexsort((np.arange(s.shape[1]), -s[ind]))
+        row = [int(j) for j in order if j != pos[reference_names[ind]]]
+        pid = id_names[ind]
+        out[str(pid.item() if hasattr(pid, "item") else pid)] = [index_names[row[t]].replace(".png", "") for t in range(50)]
+    return out
+
+
 def metrics_fashion(image_features, ref_features, target_names, answer_names) -> Dict[str, float]:
     """get_metrics_fashion (src/eval_utils.py:1025-1037)."""
     pos = {n: i for i, n in enumerate(target_names)}

@@ -30,7 +30,7 @@ sys.path.insert(0, ROOT)
 from oracle import knn_oracle as orc  # noqa: E402
 
 REF = os.environ.get("KEDS_REFERENCE", "/root/reference")
-OUT = os.path.join(ROOT, "tests", "golden")
+OUT = os.environ.get("KEDS_GOLDEN_OUT", os.path.join(ROOT, "tests", "golden"))
 
 
 def extract(path: str, names):
@@ -68,7 +68,8 @@ def main() -> None:
     os.makedirs(OUT, exist_ok=True)
     tr = extract(os.path.join(REF, "src", "trainer.py"), ["get_retrieved_features", "get_extra_cap_features"])
     ev = extract(os.path.join(REF, "src", "eval_utils.py"),
-                 ["get_metrics_coco", "get_metrics_fashion", "get_metrics_cirr", "get_metrics_imgnet"])
+                 ["get_metrics_coco", "get_metrics_fashion", "get_metrics_cirr", "get_metrics_imgnet",
+                  "get_cirr_testoutput"])
 
     # ---- retrieval: 2048 x 64 bases (aligned pairs), 32 queries, k = 16
     n, d, b, k = 2048, 64, 32, 16
@@ -115,6 +116,12 @@ def main() -> None:
     reference_names = [f"dev-{i}.png" for i in ref]
     target_names = [f"dev-{i}.png" for i in tgt]
     metrics["cirr"] = ev["get_metrics_cirr"](gal, qf, reference_names, index_names, target_names)
+    # CIRR test split (src/eval_utils.py:1070-1087): names are matched raw (no basename loop there),
+    # the reference image is removed, the first 50 names per pair id are emitted without ".png"
+    test_index_names = [f"test1-{i}-img0.png" for i in range(G)]
+    test_reference_names = [test_index_names[i] for i in ref]
+    pair_ids = torch.arange(7000, 7000 + Q)
+    cirr_test = ev["get_cirr_testoutput"](gal, qf, test_reference_names, test_index_names, pair_ids)
     # FashionIQ-shaped
     fnames = [f"B{i:05d}" for i in range(G)]
     metrics["fashion"] = ev["get_metrics_fashion"](gal, qf, fnames, [fnames[i] for i in tgt])
@@ -147,7 +154,9 @@ def main() -> None:
     )
     with open(os.path.join(OUT, "metrics_expected.json"), "w") as f:
         json.dump({"index_names": index_names, "reference_names": reference_names,
-                   "target_names": target_names, "fashion_names": fnames, "metrics": metrics}, f, indent=1)
+                   "target_names": target_names, "fashion_names": fnames, "metrics": metrics,
+                   "cirr_test": {"index_names": test_index_names, "reference_names": test_reference_names,
+                                 "pair_ids": pair_ids.tolist(), "output": cirr_test}}, f, indent=1)
     print("wrote", sorted(os.listdir(OUT)))
     for kk, v in metrics.items():
         print(kk, v)

@@ -136,3 +136,13 @@ def test_clip_loss_oracle_matches_torch_autograd_of_the_reference_statements(gol
         assert abs(loss - float(g[f"loss{r}"])) < 1e-12
         assert np.abs(dI - g[f"dI{r}"]).max() < 1e-12 and np.abs(dT - g[f"dT{r}"]).max() < 1e-12
         assert abs(ds - float(g[f"dscale{r}"])) < 1e-12
+
+
+def test_cirr_testoutput_matches_reference(golden_dir):
+    """get_cirr_testoutput (src/eval_utils.py:1070-1087), produced by the reference's own function."""
+    z = np.load(os.path.join(golden_dir, "metrics_inputs.npz"))
+    e = json.load(open(os.path.join(golden_dir, "metrics_expected.json")))["cirr_test"]
+    got = orc.cirr_testoutput(z["gal"], z["qf"], e["reference_names"], e["index_names"], e["pair_ids"])
+    assert got == e["output"]
+    with pytest.raises(IndexError):   # fewer than 51 gallery images: the reference's [t] for t < 50 runs out
+        orc.cirr_testoutput(z["gal"][:40], z["qf"][:3], e["index_names"][:3], e["index_names"][:40], [1, 2, 3])
