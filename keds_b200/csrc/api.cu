@@ -190,6 +190,7 @@ constexpr size_t TIMING_PAIRS = 5;  // k_prep_rows, k_score_topk, k_select_reran
 struct Plan {
   int exact_only = 0;
   bool pair = false;  // CTA-pair scoring kernel (two query tiles per work item)
+  int sub = 1;        // candidate lines per (slice, query): 2 in the pair kernel (one per column half)
   int S = 1, n_qt = 1, n_qg = 1, n_items = 0, grid = 0;
 };
 
@@ -312,15 +313,17 @@ Plan make_plan(const keds_index* ix, int n_db, int64_t nq, int k, int64_t n_min,
   // a slice hands over its best LKEEP-1 rows and drops the rest (theta = its LKEEP-th best): for
   // the certificate to pass, theta must sit well below the k-th best score overall, i.e. the
   // top-k must be spread over many slices (expected share per slice <= LKEEP / 6)
-  const int S_sel = std::max(1, (6 * k + LKEEP - 1) / LKEEP);
   // more than one query tile: CTA pairs share each row tile (two query tiles per work item)
   pl.pair = ix->use_pair && pl.n_qt >= 2 && ix->num_sms >= 2;
+  pl.sub = pl.pair ? ScoreCfg<true>::kSub : ScoreCfg<false>::kSub;
+  // (in candidate lists: the pair kernel keeps one per column half of every slice)
+  const int S_sel = std::max(1, ((6 * k + LKEEP - 1) / LKEEP + pl.sub - 1) / pl.sub);
   pl.n_qg = pl.pair ? (pl.n_qt + 1) / 2 : pl.n_qt;
   const int units = pl.pair ? ix->num_sms / 2 : ix->num_sms;
   const int groups = n_db * pl.n_qg;
   int S_hi = std::min(T_min, S_MAX);
-  const long long by_mem =
-      static_cast<long long>(CAND_BUDGET / (size_t(LKEEP) * BM * 8)) / (static_cast<long long>(n_db) * pl.n_qt);
+  const long long by_mem = static_cast<long long>(CAND_BUDGET / (size_t(LKEEP) * BM * 8)) /
+                           (static_cast<long long>(n_db) * pl.n_qt * pl.sub);
   S_hi = static_cast<int>(std::min<long long>(S_hi, by_mem));
   if ((flags & KEDS_SEARCH_EXACT_ONLY) || S_hi < S_sel || k > R_MAX / 2) {
     pl.exact_only = 1;
@@ -337,13 +340,13 @@ Plan make_plan(const keds_index* ix, int n_db, int64_t nq, int k, int64_t n_min,
     // expected fallbacks: a query is flagged when one slice holds LKEEP or more of the ~2k rows at
     // or above tau (Poisson tail, five-fold margin) -- large k wants more slices than the SM count
     {
-      const double lam = std::max(2.0 * k, 1.25 * static_cast<double>(band_hint)) / S;
+      const double lam = std::max(2.0 * k, 1.25 * static_cast<double>(band_hint)) / (S * pl.sub);
       double term = std::exp(-lam), tail = 0.0;  // term_i = e^-lam lam^i / i!
       for (int i = 1; i <= LKEEP + 40; ++i) {
         term *= lam / i;
         if (i >= LKEEP) tail += term;
       }
-      cost += 5.0 * tail * static_cast<double>(nq) * n_db * S * scan_cost;
+      cost += 5.0 * tail * static_cast<double>(nq) * n_db * S * pl.sub * scan_cost;
     }
     if (cost < best - 1e-9) {
       best = cost;
@@ -532,7 +535,7 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
       a->stats.launches++;
     }
     // candidate lines are indexed by (db, slice, query tile) whatever the work-item grouping
-    const size_t items = static_cast<size_t>(n_db) * pl.S * pl.n_qt;
+    const size_t items = static_cast<size_t>(n_db) * pl.S * pl.sub * pl.n_qt;
     CKS(a->cand.ensure(items * LKEEP * BM * 8));
     CKS(a->cand_cnt.ensure(items * BM * 4));
     CKS(a->cand_theta.ensure(items * BM * 4));
@@ -561,7 +564,7 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
     sp.timing = tchain ? tchain + 2 : nullptr;
     CKS(prof_mark(a, st, 1));
     if (pl.pair)
-      CKS(launch_kc(a->use_pdl, 2, k_score_topk<true>, dim3(pl.grid), dim3(SCORE_THREADS), SCORE_PAIR_SMEM_BYTES,
+      CKS(launch_kc(a->use_pdl, 2, k_score_topk<true>, dim3(pl.grid), dim3(SCORE_PAIR_THREADS), SCORE_PAIR_SMEM_BYTES,
                     st, a->tm_q, ix[0]->tm_xh, n_db > 1 ? ix[1]->tm_xh : ix[0]->tm_xh, sp));
     else
       CKS(launch_k(a->use_pdl, k_score_topk<false>, dim3(pl.grid), dim3(SCORE_THREADS), SCORE_SMEM_BYTES, st,
@@ -575,7 +578,7 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
     memset(&rp, 0, sizeof rp);
     rp.n_db = n_db;
     rp.n_qt = pl.n_qt;
-    rp.S = pl.S;
+    rp.S = pl.S * pl.sub;  // candidate lines per (database, query)
     rp.nq = static_cast<int>(nq);
     rp.k = k;
     rp.d = a->d;
@@ -611,10 +614,10 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
     if (peer) rp.peer = *peer;
     rp.cons = cons;
     rp.timing = tchain ? tchain + 4 : nullptr;
-    const size_t slots = static_cast<size_t>(pl.S) * LKEEP;
+    const size_t slots = static_cast<size_t>(pl.S) * pl.sub * LKEEP;
     // qvec | part | okey | keys, ids | smax | a_key, a_id, sel_id, sel_sc | hist | red | bcast | counters | top_*
     const size_t smem = static_cast<size_t>((a->d + 3) & ~3) * 4 + static_cast<size_t>(cons.part4) * 16 +
-                        static_cast<size_t>(rmax) * 24 + slots * 8 + pl.S * 4 + 256 * 4 + 32 * 4 + 16 + 16 +
+                        static_cast<size_t>(rmax) * 24 + slots * 8 + pl.S * pl.sub * 4 + 256 * 4 + 32 * 4 + 16 + 16 +
                         static_cast<size_t>(k) * 12;
     if (smem > 200 * 1024) return fail(KEDS_ERR_ARG, "re-rank shared memory %zu too large", smem);
     if (small_batch)

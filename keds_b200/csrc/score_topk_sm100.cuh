@@ -9,6 +9,8 @@
 //   warp 0        TMA producer: per k-block one {64 x 128} query box + one row box
 //   warp 1        tcgen05.mma issuer (one lane), owns the TMEM allocation
 //   warps 2..5    epilogue: TMEM lane == query, so one thread owns one query's scores
+//   warps 6..9    (CTA-pair variant) a second set of epilogue warps: the same 128 queries, the
+//                 other 128 columns of the tile, their own candidate lists ("sub-slices")
 //
 // Tile: M = 128 queries (TMEM lanes) x N = 256 DB rows (TMEM columns), K streamed in 64-wide
 // k-blocks (one 128-byte swizzle row). Two 256-column accumulators double-buffer MMA vs epilogue.
@@ -20,6 +22,12 @@
 //                  CTA holds its own 128 queries and loads HALF of the row tile, the leader CTA
 //                  issues one MMA for both. Per CTA and k-block 32 KB cross L2->SM instead of 48 KB,
 //                  which is what bounds the single-CTA variant once the batch is compute-bound.
+//                  Here the selection epilogue is the co-bottleneck (ncu, round 2: tensor pipe
+//                  76 % busy at 4096 x 0.5M, 53 % at 4096 x 50k -- a tile's 48 MMAs take ~6,100
+//                  cycles, one epilogue warp per sub-partition needed about as long and stalled
+//                  the issuer at every compaction), so each sub-partition gets TWO epilogue warps
+//                  that split the tile's columns; all latencies (tcgen05.ld, the select chain,
+//                  votes) of one hide under the other.
 #pragma once
 #include "ptx.cuh"
 
@@ -31,7 +39,8 @@ constexpr int BK = 64;
 constexpr int UK = 16;
 constexpr int LKEEP = 16;   // a compaction keeps scores above the LKEEP-th best seen
 constexpr int CHUNK = 32;   // TMEM columns per tcgen05.ld
-constexpr int SCORE_THREADS = 192;
+constexpr int SCORE_THREADS = 192;       // single-CTA variant: producer, issuer, 4 epilogue warps
+constexpr int SCORE_PAIR_THREADS = 320;  // CTA-pair variant: 8 epilogue warps
 constexpr uint32_t Q_STAGE_BYTES = BM * BK * 2;
 constexpr uint32_t TMEM_COLS = 512;
 
@@ -41,16 +50,21 @@ struct ScoreCfg {
   // slots are cut to 32 per query (32 KB) to make room for a fourth 48-KB stage; the slot count
   // is then checked every 8 scores. CTA pair (compute-bound): 64 slots, checked every 32 scores --
   // compactions are what its epilogue can least afford.
-  static constexpr int kStages = 4;
-  static constexpr int kCap = kPair ? 64 : 32;
-  static constexpr int kAppend = kPair ? 32 : 8;
+  // CTA pair (compute-bound): 8 epilogue warps of 32 slots each (the same 64 KB as 4 x 64 before)
+  // and, with 32-KB stages, room for a fifth stage.
+  static constexpr int kStages = kPair ? 5 : 4;
+  static constexpr int kEpiWarps = kPair ? 8 : 4;
+  static constexpr int kSub = kEpiWarps / 4;                        // candidate lists ("sub-slices") per (slice, query)
+  static constexpr int kThreads = 64 + 32 * kEpiWarps;
+  static constexpr int kCap = 32;
+  static constexpr int kAppend = 8;
   static constexpr uint32_t kCandWarpBytes = kCap * 32 * 8;
   static constexpr int kRowsPerCta = kPair ? BN / 2 : BN;           // row-tile rows this CTA loads
   static constexpr uint32_t kXBytes = kRowsPerCta * BK * 2;
   static constexpr uint32_t kStageBytes = Q_STAGE_BYTES + kXBytes;  // 48 KB / 32 KB
   // dynamic shared memory map (offsets from a 1024-aligned base)
   static constexpr uint32_t kOffCand = kStages * kStageBytes;
-  static constexpr uint32_t kOffBias = kOffCand + 4 * kCandWarpBytes;
+  static constexpr uint32_t kOffBias = kOffCand + kEpiWarps * kCandWarpBytes;
   static constexpr uint32_t kOffBars = kOffBias + 2 * BN * 4;
   static constexpr uint32_t kSmemBytes = kOffBars + 256 + 768;      // barriers + alignment slack (227 KB exactly for the single-CTA variant)
 };
@@ -61,7 +75,7 @@ struct ScoreParams {
   int n_db;          // 1 or 2 databases scored against the same queries
   int n_qt;          // query tiles of BM
   int n_qg;          // query groups per (db, slice): n_qt (single CTA) or ceil(n_qt / 2) (pair)
-  int S;             // row slices per (db, query tile)
+  int S;             // row slices per (db, query tile); the pair variant writes 2 candidate lines per slice
   int n_items;       // n_db * S * n_qg ; item = ((db * S) + s) * n_qg + qg
   int kblocks;       // d_pad / BK
   uint32_t fmt_bits; // operand format bits of the instruction descriptor (kIdescBf16Bits, or 0 = fp16)
@@ -69,7 +83,7 @@ struct ScoreParams {
   int n_rows[2];     // rows per database
   int n_tiles[2];    // ceil(n_rows / BN)
   const float* bias[2];  // nullable; additive per-row bias padded with -inf to n_tiles * BN
-  uint2* cand;       // [n_db * S * n_qt][BM][LKEEP] {approx score bits, row id}, padded {-inf, ~0}
+  uint2* cand;       // [n_db * S * kSub * n_qt][BM][LKEEP] {approx score bits, row id}, padded {-inf, ~0}
   int* cand_cnt;     // [..][BM]
   float* cand_theta; // [..][BM]  everything the slice dropped scored <= theta
   uint32_t* err;     // device error word (0 = ok)
@@ -163,7 +177,7 @@ __device__ __noinline__ CandState compact_candidates(uint32_t slot0, int cnt, fl
 }
 
 template <bool kPair>
-__global__ void __launch_bounds__(SCORE_THREADS, 1)
+__global__ void __launch_bounds__(ScoreCfg<kPair>::kThreads, 1)
 k_score_topk(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_x0,
              const __grid_constant__ CUtensorMap tm_x1, const ScoreParams p) {
   using Cfg = ScoreCfg<kPair>;
@@ -206,7 +220,7 @@ k_score_topk(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), kPair ? 8 : 4);  // pair: the leader collects both CTAs' epilogue warps
+      mbar_init(tempty_bar(a), kPair ? 2 * Cfg::kEpiWarps : Cfg::kEpiWarps);  // pair: the leader collects both CTAs' epilogue warps
     }
     *dead = 0;
     fence_mbar_init();
@@ -335,10 +349,13 @@ k_score_topk(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
     const int q_local = quad * 32 + lane;
     constexpr int CAP = Cfg::kCap;
     constexpr int APPEND = Cfg::kAppend;
+    constexpr int SUB = Cfg::kSub;
+    constexpr int CH_PER = (BN / CHUNK) / SUB;  // column chunks of a tile this warp scans
+    const int half = (warp - 2) >> 2;           // which columns: 0 (the only set in the single-CTA variant) or 1
     const uint32_t wbuf = sbase + Cfg::kOffCand + static_cast<uint32_t>(warp - 2) * Cfg::kCandWarpBytes;
     const uint32_t slot0 = wbuf + lane * 8;   // entry e of this lane lives at slot0 + e * 256
     float* sbias = reinterpret_cast<float*>(gbase + Cfg::kOffBias);
-    const int et = threadIdx.x - 64;          // 0..127 among epilogue threads
+    const int et = threadIdx.x - 64;          // 0 .. 32 * kEpiWarps - 1 among epilogue threads
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int item = unit; item < p.n_items; item += n_units) {
@@ -352,9 +369,14 @@ k_score_topk(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
       const int n_rows = p.n_rows[c.db];
       for (int tile = c.t0; tile < c.t1; ++tile) {
         if (bias != nullptr) {
-          sbias[acc * BN + et] = bias[static_cast<long long>(tile) * BN + et];
-          sbias[acc * BN + 128 + et] = bias[static_cast<long long>(tile) * BN + 128 + et];
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if constexpr (SUB == 2) {
+            sbias[acc * BN + et] = bias[static_cast<long long>(tile) * BN + et];
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+          } else {
+            sbias[acc * BN + et] = bias[static_cast<long long>(tile) * BN + et];
+            sbias[acc * BN + 128 + et] = bias[static_cast<long long>(tile) * BN + 128 + et];
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+          }
         }
         mbar_wait(tfull_bar(acc), acc_phase, dead, p.err, 0x400u + acc);
         tc_fence_after();
@@ -362,7 +384,7 @@ k_score_topk(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
             tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN);
         const int nvalid = n_rows - tile * BN;  // >= BN for full tiles
 #pragma unroll 1
-        for (int ch = 0; ch < BN / CHUNK; ++ch) {
+        for (int ch = half * CH_PER; ch < (half + 1) * CH_PER; ++ch) {
           uint32_t v[CHUNK];
           tmem_ld32(taddr + ch * CHUNK, v);
           tmem_ld_wait(v);
@@ -437,7 +459,9 @@ k_score_topk(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
         theta = st.theta;
       }
       if (!kPair || qt < p.n_qt) {
-        const long long oitem = (static_cast<long long>(c.db) * p.S + c.s) * p.n_qt + qt;
+        // one candidate line per (slice, column half, query): the re-rank kernel sees S * SUB slices
+        const long long oitem =
+            (static_cast<long long>(c.db) * (p.S * SUB) + (c.s * SUB + half)) * p.n_qt + qt;
         uint2* cbase = p.cand + (oitem * BM + q_local) * LKEEP;
 #pragma unroll
         for (int e = 0; e < LKEEP; e += 2) {

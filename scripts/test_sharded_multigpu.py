@@ -44,6 +44,7 @@ def main():
         for _ in range(reps):  # several steps: parities, epochs
             D, I = sh.search(q, k)
         torch.cuda.synchronize()
+        sh.local.sync()  # the status words of the last local search reach last_stats()
         same = bool(torch.equal(I, Ir) and torch.equal(D, Dr))
         ok = ok and same
         out[tag] = {"bit_identical_to_unsharded": same, "B": int(q.shape[0]), "k": k,

@@ -107,7 +107,8 @@ def test_planner_invariants_over_a_sweep():
                     if p["exact_only"]:
                         continue
                     tiles = -(-n // 256)
-                    assert -(-6 * k // 16) <= p["S"] <= min(tiles, 192)      # enough slices, none empty
+                    sub = 2 if p["pair"] else 1     # the pair kernel keeps a candidate list per column half of a slice
+                    assert -(-6 * k // 16) <= p["S"] * sub and p["S"] <= min(tiles, 192)   # enough lists, no empty slice
                     assert p["pair"] == (1 if nq > 128 else 0)                  # CTA pairs share row tiles
                     groups = n_db * (-(-p["n_qt"] // 2) if p["pair"] else p["n_qt"])
                     assert p["items"] == groups * p["S"]
@@ -120,10 +121,12 @@ def test_planner_small_databases_and_huge_k_go_to_the_exact_kernel():
 
 
 def test_planner_large_k_buys_slices_against_fallbacks():
-    """k = 64 at 4096 queries x 1M rows: 37 slices balance the SMs just as well as 74 but leave about
-    one query per batch to the exact fallback (a full fp32 scan); the planner must prefer 74."""
-    assert _plan(1, 4096, 64, 1_000_000)["S"] == 74
+    """k = 64 at 4096 queries x 1M rows: 37 candidate lists per query balance the SMs just as well as
+    74 but leave about one query per batch to the exact fallback (a full fp32 scan); the planner must
+    prefer 74 lists -- 37 slices in the CTA-pair kernel, which keeps one list per column half."""
+    assert _plan(1, 4096, 64, 1_000_000)["S"] == 37
     assert _plan(1, 4096, 16, 500_000)["S"] == 23           # small k: unchanged by the fallback term
+    assert _plan(1, 4096, 16, 50_000)["S"] == 9             # short database: few, long slices (two rounds of items)
 
 
 def test_parallel_runner_keeps_order_and_raises_the_first_error():
