@@ -148,7 +148,8 @@ int keds_gather_pool(const float* base, int64_t n_base, const int64_t* I, const 
                      void* cuda_stream);
 
 /* ---- row-sharded merge ------------------------------------------------------------------------
- * D_parts/I_parts: [parts][nq][k] per-shard results with global labels (device); writes the global
+ * D_parts/I_parts: [parts][nq][k] per-shard results with global labels (device), each part sorted
+ * best-first with its -1 padding last, exactly as keds_index_search returns it; writes the global
  * top-k with the same ordering rule. New relative to the reference (replicas only). */
 int keds_topk_merge(const float* D_parts, const int64_t* I_parts, int parts, int64_t nq, int k,
                     int metric, float* D, int64_t* I, void* cuda_stream);
@@ -208,6 +209,15 @@ int keds_exchange_stats(keds_exchange_t* ex, void* cuda_stream, double* wait_us_
 int keds_gallery_rank(const float* Q, int64_t nq, const float* G, int64_t ng, int d,
                       const int64_t* target, const int64_t* exclude, int64_t* rank_out,
                       void* cuda_stream);
+/* The same ranks against the rows of an index (the gallery added once, many query sets ranked
+ * against it: the reference scores 30 checkpoints x 3 feature sets against one gallery,
+ * src/eval_utils.py:617,735). The dense Q x G contraction runs on the tensor cores: the scoring
+ * kernel counts the rows whose 16-bit-operand score beats the target's exact score by more than the
+ * certificate's error bound, lists the rows inside the bound, and those are settled with exact fp32
+ * scores -- so the ranks equal the fp32 count bit for bit. Inner product whatever the index metric.
+ * Device pointers; asynchronous on cuda_stream. */
+int keds_index_rank(keds_index_t* idx, const float* q, int64_t nq, const int64_t* target,
+                    const int64_t* exclude, int64_t* rank_out, void* cuda_stream);
 /* hits[q][i] = #{ j < ks[i] : labels[I[q][j]] == qlabel[q] } for ascending ks (device pointers).
  * The counting core of get_metrics_imgnet (src/eval_utils.py:1107-1118). */
 int keds_label_hits(const int64_t* I, int64_t nq, int kmax, const int64_t* labels,

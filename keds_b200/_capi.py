@@ -95,6 +95,7 @@ SIGNATURES = {
          C.c_uint32, _vp, _vp],
     ),
     "keds_gallery_rank": (C.c_int, [_vp, C.c_int64, _vp, C.c_int64, C.c_int, _vp, _vp, _vp, _vp]),
+    "keds_index_rank": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, _vp, _vp]),
     "keds_label_hits": (C.c_int, [_vp, C.c_int64, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp]),
     "keds_consumer_create": (
         C.c_int,

@@ -214,7 +214,7 @@ struct keds_index {
   bool tm_x_ok = false;
   bool use_pair = true;
   // per-call scratch (one search in flight per handle)
-  DevBuf q_f32, q_bf16, qstat, cand, cand_cnt, cand_theta, flagged[2], ctrl, exact_scratch;
+  DevBuf q_f32, q_bf16, qstat, cand, cand_cnt, cand_theta, flagged[2], ctrl, exact_scratch, rk;
   DevBuf D_stage[2], I_stage[2];
   HostBuf h_q, h_out;  // pinned staging for host-pointer calls
   CUtensorMap tm_q;
@@ -243,6 +243,10 @@ int set_kernel_attrs(keds_index* ix) {
   CK(cudaFuncSetAttribute(k_score_topk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)SCORE_SMEM_BYTES));
   CK(cudaFuncSetAttribute(k_score_topk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)SCORE_PAIR_SMEM_BYTES));
+  CK(cudaFuncSetAttribute(k_score_topk<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)SCORE_SMEM_BYTES));
+  CK(cudaFuncSetAttribute(k_score_topk<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)SCORE_PAIR_SMEM_BYTES));
   const char* no_pair = getenv("KEDS_NO_PAIR");
   ix->use_pair = !(no_pair && no_pair[0] == '1');
@@ -871,7 +875,8 @@ int keds_index_create(int d, int metric, int device, keds_index_t** out) {
   // every buffer whose address a captured search bakes in reports its moves
   DevBuf* tracked[] = {&ix->x_f32, &ix->x_bf16, &ix->bias, &ix->q_f32, &ix->q_bf16, &ix->qstat, &ix->cand,
                        &ix->cand_cnt, &ix->cand_theta, &ix->flagged[0], &ix->flagged[1], &ix->ctrl,
-                       &ix->exact_scratch, &ix->D_stage[0], &ix->D_stage[1], &ix->I_stage[0], &ix->I_stage[1]};
+                       &ix->exact_scratch, &ix->D_stage[0], &ix->D_stage[1], &ix->I_stage[0], &ix->I_stage[1],
+                       &ix->rk};
   for (DevBuf* b : tracked) b->gen = &ix->generation;
   *out = ix;
   return 0;
@@ -883,7 +888,7 @@ void keds_index_free(keds_index_t* ix) {
   DevBuf* bufs[] = {&ix->x_f32, &ix->x_bf16, &ix->bias, &ix->dbstat, &ix->q_f32, &ix->q_bf16,
                     &ix->qstat, &ix->cand, &ix->cand_cnt, &ix->cand_theta, &ix->flagged[0],
                     &ix->flagged[1], &ix->ctrl, &ix->exact_scratch, &ix->D_stage[0], &ix->D_stage[1],
-                    &ix->I_stage[0], &ix->I_stage[1], &ix->timing, &ix->probe};
+                    &ix->I_stage[0], &ix->I_stage[1], &ix->timing, &ix->probe, &ix->rk};
   for (DevBuf* b : bufs) b->release();
   ix->h_q.release();
   ix->h_out.release();
@@ -1270,7 +1275,7 @@ static int merge_impl(const float* Dp, const int64_t* Ip, int64_t stride_d, int6
     return fail(KEDS_ERR_ARG, "topk_merge: bad argument");
   if (nq == 0) return 0;
   const size_t tot = static_cast<size_t>(parts) * k;
-  const size_t smem = tot * 8 + ((tot + 1) & ~size_t(1)) * 4 + tot * 8;
+  const size_t smem = tot * 8 + tot * 4;  // labels, rank scores
   if (smem > 200 * 1024) return fail(KEDS_ERR_ARG, "topk_merge: parts*k too large");
   const int dev = device_of(D);
   if (dev < 0) return fail(KEDS_ERR_ARG, "topk_merge: device pointers only");
@@ -1487,6 +1492,118 @@ int keds_exchange_stats(keds_exchange_t* ex, void* stream, double* wait_us_avg, 
   return 0;
 }
 
+// Gallery ranking against the rows of an index, on the tensor cores: the same scoring kernel with
+// a counting epilogue between two small kernels (target scores + error band before, exact
+// settlement of the band rows after), and the exact fp32 recount for queries whose band overflowed.
+int keds_index_rank(keds_index_t* ix, const float* q, int64_t nq, const int64_t* target, const int64_t* exclude,
+                    int64_t* rank_out, void* stream) {
+  if (!ix || !q || !target || !rank_out || nq < 0) return fail(KEDS_ERR_ARG, "index_rank: null argument or bad nq");
+  if (nq == 0) return 0;
+  if (ix->n == 0) return fail(KEDS_ERR_ARG, "index_rank: empty index");
+  if (!is_device_ptr(q) || !is_device_ptr(target) || !is_device_ptr(rank_out) || (exclude && !is_device_ptr(exclude)))
+    return fail(KEDS_ERR_ARG, "index_rank: device pointers only");
+  DeviceGuard g(ix->device);
+  if (!g.ok) return fail(KEDS_ERR_NO_GPU, "cannot select CUDA device %d", ix->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CKS(set_kernel_attrs(ix));
+  const float* G = ix->x_f32.as<float>();
+  const long long* tg = reinterpret_cast<const long long*>(target);
+  const long long* ex = reinterpret_cast<const long long*>(exclude);
+  long long* out = reinterpret_cast<long long*>(rank_out);
+  const int d = ix->d;
+  const size_t simt_smem = static_cast<size_t>((d + 3) & ~3) * 4 * 8;  // 8 queries per block
+  if (simt_smem > 48 * 1024) return fail(KEDS_ERR_ARG, "index_rank: d too large");
+  const int T = static_cast<int>((ix->n + BN - 1) / BN);
+  if (T < 2) {
+    // less than two row tiles: nothing for the tensor cores to win
+    k_gallery_rank<<<static_cast<unsigned>((nq + 7) / 8), 256, simt_smem, st>>>(q, nq, G, ix->n, d, tg, ex, out,
+                                                                                  nullptr, nullptr);
+    CK(cudaGetLastError());
+    return 0;
+  }
+  for (int64_t q0 = 0; q0 < nq; q0 += Q_PASS_MAX) {
+    const int64_t nb = std::min<int64_t>(Q_PASS_MAX, nq - q0);
+    const float* qp = q + q0 * d;
+    const int n_qt = static_cast<int>((nb + BM - 1) / BM);
+    const bool pair = ix->use_pair && n_qt >= 2 && ix->num_sms >= 2;
+    const int sub = pair ? ScoreCfg<true>::kSub : ScoreCfg<false>::kSub;
+    const int n_qg = pair ? (n_qt + 1) / 2 : n_qt;
+    const int units = pair ? ix->num_sms / 2 : ix->num_sms;
+    // as many candidate lists as the tiles allow: the band around a mid-ranked target is crowded
+    const long long by_mem = static_cast<long long>(CAND_BUDGET / (size_t(LKEEP) * BM * 8)) / (static_cast<long long>(n_qt) * sub);
+    const int S = static_cast<int>(std::max<long long>(1, std::min<long long>(std::min(T, S_MAX), by_mem)));
+    const int n_items = n_qg * S;
+    const int grid = std::min(n_items, units) * (pair ? 2 : 1);
+    const int n_lists = S * sub;
+    CKS(ix->ctrl.ensure(CTRL_WORDS * 4));
+    CKS(ix->flagged[0].ensure(static_cast<size_t>(nb) * 4));
+    CKS(ensure_q_map(ix, static_cast<int64_t>(n_qt) * BM, st));
+    CKS(ix->qstat.ensure(static_cast<size_t>(nb) * sizeof(float4)));
+    CKS(ix->rk.ensure(static_cast<size_t>(nb) * 5 * 4));
+    const size_t lines = static_cast<size_t>(n_lists) * n_qt;
+    CKS(ix->cand.ensure(lines * LKEEP * BM * 8));
+    CKS(ix->cand_cnt.ensure(lines * BM * 4));
+    CKS(ix->cand_theta.ensure(lines * BM * 4));
+    float* rk_st = ix->rk.as<float>();
+    float* rk_lo = rk_st + nb;
+    float* rk_hi = rk_lo + nb;
+    int* rk_t = reinterpret_cast<int*>(rk_hi + nb);
+    int* rk_e = rk_t + nb;
+    {
+      const unsigned blocks = static_cast<unsigned>(std::min<long long>((nb * 32 + 255) / 256, 4096));
+      CKS(launch_k(ix->use_pdl, k_prep_rows, dim3(blocks), dim3(256), 0, st, qp, static_cast<long long>(nb), d,
+                   ix->d_pad, ix->fmt, ix->q_bf16.as<uint16_t>(), ix->qstat.as<float4>(), static_cast<float*>(nullptr),
+                   static_cast<unsigned int*>(nullptr), ix->ctrl.as<unsigned int>(), CTRL_WORDS,
+                   static_cast<unsigned long long*>(nullptr)));
+    }
+    const unsigned wblocks = static_cast<unsigned>((nb * 32 + 255) / 256);
+    CKS(launch_k(ix->use_pdl, k_rank_targets, dim3(wblocks), dim3(256), 0, st, qp, static_cast<long long>(nb), G, d,
+                 tg + q0, ex ? ex + q0 : nullptr, ix->qstat.as<float4>(), ix->dbstat.as<unsigned int>(), ix->eps_scale,
+                 rk_st, rk_lo, rk_hi, rk_t, rk_e));
+    ScoreParams sp;
+    memset(&sp, 0, sizeof sp);
+    sp.n_db = 1;
+    sp.n_qt = n_qt;
+    sp.n_qg = n_qg;
+    sp.S = S;
+    sp.n_items = n_items;
+    sp.kblocks = ix->d_pad / BK;
+    sp.fmt_bits = ix->fmt == FMT_BF16 ? kIdescBf16Bits : 0u;
+    sp.nq = static_cast<int>(nb);
+    sp.n_rows[0] = static_cast<int>(ix->n);
+    sp.n_tiles[0] = T;
+    sp.cand = ix->cand.as<uint2>();
+    sp.cand_cnt = ix->cand_cnt.as<int>();
+    sp.cand_theta = ix->cand_theta.as<float>();
+    sp.err = ix->ctrl.as<uint32_t>() + 2;
+    sp.rk_lo = rk_lo;
+    sp.rk_hi = rk_hi;
+    sp.rk_target = rk_t;
+    sp.rk_exclude = ex ? rk_e : nullptr;
+    if (pair)
+      CKS(launch_kc(ix->use_pdl, 2, k_score_topk<true, true>, dim3(grid), dim3(SCORE_PAIR_THREADS), SCORE_PAIR_SMEM_BYTES,
+                    st, ix->tm_q, ix->tm_xh, ix->tm_xh, sp));
+    else
+      CKS(launch_k(ix->use_pdl, k_score_topk<false, true>, dim3(grid), dim3(SCORE_THREADS), SCORE_SMEM_BYTES, st,
+                   ix->tm_q, ix->tm_x, ix->tm_x, sp));
+    CKS(launch_k(ix->use_pdl, k_rank_finish, dim3(wblocks), dim3(256), 0, st, qp, static_cast<long long>(nb), G, d,
+                 n_lists, n_qt, static_cast<const uint2*>(sp.cand), static_cast<const int*>(sp.cand_cnt),
+                 static_cast<const float*>(sp.cand_theta), static_cast<const float*>(rk_st),
+                 static_cast<const int*>(rk_t), out + q0, ix->flagged[0].as<int>(), ix->ctrl.as<int>()));
+    // exact recount of the queries whose band overflowed a list (none, normally: the blocks leave at once)
+    CKS(launch_k(ix->use_pdl, k_gallery_rank, dim3(static_cast<unsigned>((nb + 7) / 8)), dim3(256), simt_smem, st, qp,
+                 static_cast<long long>(nb), G, static_cast<long long>(ix->n), d, tg + q0, ex ? ex + q0 : nullptr,
+                 out + q0, static_cast<const int*>(ix->flagged[0].as<int>()), static_cast<const int*>(ix->ctrl.as<int>())));
+    ix->stats.launches = 5;
+    ix->stats.slices = S;
+    ix->stats.items = n_items;
+    ix->stats.grid = grid;
+    if (q0 + nb < nq) CKS(finish_sync(ix, st));  // the scratch is reused by the next pass
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
 int keds_gallery_rank(const float* Q, int64_t nq, const float* G, int64_t ng, int d,
                       const int64_t* target, const int64_t* exclude, int64_t* rank_out, void* stream) {
   if (!Q || !G || !target || !rank_out || nq < 0 || ng <= 0 || d <= 0)
@@ -1498,9 +1615,20 @@ int keds_gallery_rank(const float* Q, int64_t nq, const float* G, int64_t ng, in
   if (dev < 0 || device_of(Q) != dev || device_of(G) != dev)
     return fail(KEDS_ERR_ARG, "gallery_rank: Q, G and rank_out must be memory of one device");
   DeviceGuard g(dev);
+  if (ng >= 1024 && nq >= 64) {
+    // worth a tensor-core pass: rank against a temporary index over the gallery (callers that score
+    // many query sets against one gallery keep the index and call keds_index_rank themselves)
+    keds_index_t* tmp = nullptr;
+    CKS(keds_index_create(d, KEDS_METRIC_IP, dev, &tmp));
+    int s = keds_index_add(tmp, G, ng);
+    if (s == 0) s = keds_index_rank(tmp, Q, nq, target, exclude, rank_out, stream);
+    if (s == 0) s = finish_sync(tmp, static_cast<cudaStream_t>(stream));
+    keds_index_free(tmp);
+    return s;
+  }
   k_gallery_rank<<<static_cast<unsigned>((nq + 7) / 8), 256, smem, static_cast<cudaStream_t>(stream)>>>(
       Q, nq, G, ng, d, reinterpret_cast<const long long*>(target),
-      reinterpret_cast<const long long*>(exclude), reinterpret_cast<long long*>(rank_out));
+      reinterpret_cast<const long long*>(exclude), reinterpret_cast<long long*>(rank_out), nullptr, nullptr);
   CK(cudaGetLastError());
   return 0;
 }

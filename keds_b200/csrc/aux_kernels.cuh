@@ -583,7 +583,8 @@ namespace keds {
 
 // ---------------------------------------------------------------------------------------------
 // Merge `parts` per-shard results (part p at Dp + p*stride_d, Ip + p*stride_i, each [nq][k]) into the global top-k (same total order; ids are
-// already global). One block per query. Used after the all-gather of a row-sharded search.
+// already global, every part is sorted best-first the way a search returns it). One block per query.
+// Used behind the exchange of a row-sharded search.
 // With `flags` set (peer-memory exchange, p2p_exchange.cuh) each block first waits until every
 // peer has delivered its part for this `epoch`; Dp/Ip must not be __restrict__/read-only cached.
 struct MergeWait {
@@ -598,12 +599,18 @@ __global__ void k_topk_merge(const float* Dp, const long long* Ip,
                              long long stride_d, long long stride_i, int parts, long long nq, int k,
                              int metric, float* __restrict__ D, long long* __restrict__ I,
                              const MergeWait mw) {
+  // Every part is a search result: sorted by (score desc, label asc), valid entries first, labels
+  // distinct across parts. The global rank of an entry is its position in its own part plus, for
+  // every other part, the number of entries there that precede it -- found by binary search
+  // (parts * log2 k steps per entry). The all-pairs count this replaces was quadratic in parts * k:
+  // 512^2 per query at 8 shards x k = 64, ~150 us, i.e. the whole "exchange cost" of round 1.
   extern __shared__ uint8_t mg_smem[];
-  unsigned long long* key = reinterpret_cast<unsigned long long*>(mg_smem);   // parts*k
-  float* val = reinterpret_cast<float*>(key + parts * k);                     // parts*k
-  long long* idv = reinterpret_cast<long long*>(val + ((parts * k + 1) & ~1)); // parts*k
+  long long* idv = reinterpret_cast<long long*>(mg_smem);     // parts*k
+  float* val = reinterpret_cast<float*>(idv + parts * k);     // parts*k rank scores (IP, or -distance)
+  __shared__ int nvalid;
   const long long q = blockIdx.x;
   const int tot = parts * k;
+  if (threadIdx.x == 0) nvalid = 0;
   griddep_wait();
   if (mw.flags != nullptr) {
     if (threadIdx.x == 0) {
@@ -618,40 +625,44 @@ __global__ void k_topk_merge(const float* Dp, const long long* Ip,
     }
     __syncthreads();
   }
+  int mine = 0;
   for (int i = threadIdx.x; i < tot; i += blockDim.x) {
     const int pt = i / k, j = i % k;
     const long long src = q * k + j;
     const float v = Dp[pt * stride_d + src];
     const long long id = Ip[pt * stride_i + src];
-    val[i] = v;
+    val[i] = metric == METRIC_L2 ? -v : v;
     idv[i] = id;
-    // 64-bit ids do not fit the 32-bit tie-break field in general: compare (score, id) directly
-    key[i] = id < 0 ? 0ull : 1ull;
+    mine += id >= 0;
   }
+  atomicAdd(&nvalid, mine);
   __syncthreads();
   for (int i = threadIdx.x; i < tot; i += blockDim.x) {
-    if (key[i] == 0ull) continue;
-    const float vi = metric == METRIC_L2 ? -val[i] : val[i];
     const long long idi = idv[i];
-    int rank = 0;
-    for (int j = 0; j < tot; ++j) {
-      if (key[j] == 0ull) continue;
-      const float vj = metric == METRIC_L2 ? -val[j] : val[j];
-      rank += (vj > vi) || (vj == vi && idv[j] < idi);
+    if (idi < 0) continue;
+    const float vi = val[i];
+    const int pt = i / k;
+    int rank = i - pt * k;  // its own part is sorted and holds its valid entries first
+    for (int p2 = 0; p2 < parts; ++p2) {
+      if (p2 == pt) continue;
+      const float* v2 = val + p2 * k;
+      const long long* i2 = idv + p2 * k;
+      int lo = 0, hi = k;  // entries [0, lo) of part p2 precede this one
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const long long idm = i2[mid];
+        const float vm = v2[mid];
+        const bool before = idm >= 0 && (vm > vi || (vm == vi && idm < idi));
+        if (before) lo = mid + 1; else hi = mid;
+      }
+      rank += lo;
     }
     if (rank < k) {
-      D[q * k + rank] = val[i];
+      D[q * k + rank] = metric == METRIC_L2 ? -vi : vi;
       I[q * k + rank] = idi;
     }
   }
   // padding when fewer than k valid entries exist
-  __shared__ int nvalid;
-  if (threadIdx.x == 0) nvalid = 0;
-  __syncthreads();
-  int mine = 0;
-  for (int i = threadIdx.x; i < tot; i += blockDim.x) mine += key[i] != 0ull;
-  atomicAdd(&nvalid, mine);
-  __syncthreads();
   for (int r = nvalid + threadIdx.x; r < k; r += blockDim.x) {
     D[q * k + r] = metric == METRIC_L2 ? FLT_MAX : -FLT_MAX;
     I[q * k + r] = -1;
@@ -713,10 +724,12 @@ __global__ void k_weighted_pool(const float* __restrict__ base, long long n_base
 // Gallery ranking by counting (no sort): rank[q] = number of gallery rows, other than the target
 // and the optional excluded row, that beat the target under (score desc, id asc).
 // Covers the argsort-then-find of src/eval_utils.py:1008-1067 (COCO / FashionIQ / CIRR).
+// With `qlist` (device list of query ids, *n_list entries) only those queries are ranked: the
+// exact recount behind the tensor-core ranking; blocks past the end of the list leave at once.
 __global__ void __launch_bounds__(256)
 k_gallery_rank(const float* __restrict__ Q, long long nq, const float* __restrict__ G, long long ng,
                int d, const long long* __restrict__ target, const long long* __restrict__ exclude,
-               long long* __restrict__ rank_out) {
+               long long* __restrict__ rank_out, const int* __restrict__ qlist, const int* __restrict__ n_list) {
   // GR_Q queries per block share every gallery row a warp reads (the row is fetched once for
   // all of them); per (query,row) the arithmetic is that of warp_exact_score.
   constexpr int GR_Q = 8;
@@ -725,17 +738,25 @@ k_gallery_rank(const float* __restrict__ Q, long long nq, const float* __restric
   float* qv = reinterpret_cast<float*>(gr_smem);  // [GR_Q][dq]
   __shared__ int total[GR_Q];
   __shared__ float s_target[GR_Q];
+  __shared__ long long qid[GR_Q];
+  griddep_wait();
+  if (n_list != nullptr) nq = *n_list;
   const long long q0 = static_cast<long long>(blockIdx.x) * GR_Q;
+  if (q0 >= nq) return;
   const int nqb = static_cast<int>(min(static_cast<long long>(GR_Q), nq - q0));
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (threadIdx.x < GR_Q) {
+    total[threadIdx.x] = 0;
+    qid[threadIdx.x] = static_cast<int>(threadIdx.x) < nqb ? (qlist != nullptr ? qlist[q0 + threadIdx.x] : q0 + threadIdx.x) : 0;
+  }
+  __syncthreads();
   for (int i = threadIdx.x; i < GR_Q * dq; i += blockDim.x) {
     const int qi = i / dq, c = i % dq;
-    qv[i] = (qi < nqb && c < d) ? Q[(q0 + qi) * d + c] : 0.f;
+    qv[i] = (qi < nqb && c < d) ? Q[qid[qi] * d + c] : 0.f;
   }
-  if (threadIdx.x < GR_Q) total[threadIdx.x] = 0;
   __syncthreads();
   for (int qi = warp; qi < nqb; qi += nw) {
-    const float st = warp_exact_score(qv + qi * dq, G + target[q0 + qi] * d, d, METRIC_IP, lane);
+    const float st = warp_exact_score(qv + qi * dq, G + target[qid[qi]] * d, d, METRIC_IP, lane);
     if (lane == 0) s_target[qi] = st;
   }
   __syncthreads();
@@ -744,8 +765,8 @@ k_gallery_rank(const float* __restrict__ Q, long long nq, const float* __restric
   int cnt[GR_Q];
 #pragma unroll
   for (int i = 0; i < GR_Q; ++i) {
-    tg[i] = i < nqb ? target[q0 + i] : -1;
-    ex[i] = (i < nqb && exclude) ? exclude[q0 + i] : -1;
+    tg[i] = i < nqb ? target[qid[i]] : -1;
+    ex[i] = (i < nqb && exclude) ? exclude[qid[i]] : -1;
     st[i] = i < nqb ? s_target[i] : 0.f;
     cnt[i] = 0;
   }
@@ -788,7 +809,85 @@ k_gallery_rank(const float* __restrict__ Q, long long nq, const float* __restric
       if (i < nqb) atomicAdd(&total[i], cnt[i]);
   }
   __syncthreads();
-  if (threadIdx.x < nqb) rank_out[q0 + threadIdx.x] = total[threadIdx.x];
+  if (threadIdx.x < nqb) rank_out[qid[threadIdx.x]] = total[threadIdx.x];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Gallery ranking on the tensor cores (k_score_topk<*, true>), the two kernels around it.
+//
+// k_rank_targets: per query (one warp) the exact fp32 score of its target row and the error band
+// around it in approximate-score space: a row with a > s_t + eps beats the target for certain
+// (its exact score is at least a - eps), a row with a < s_t - eps loses for certain, the rows in
+// between are listed and settled exactly by k_rank_finish. eps as in the search certificate.
+__global__ void k_rank_targets(const float* __restrict__ Q, long long nq, const float* __restrict__ G, int d,
+                               const long long* __restrict__ target, const long long* __restrict__ exclude,
+                               const float4* __restrict__ qstat, const unsigned int* __restrict__ dbstat,
+                               float eps_scale, float* __restrict__ s_t, float* __restrict__ lo,
+                               float* __restrict__ hi, int* __restrict__ t32, int* __restrict__ e32) {
+  const int lane = threadIdx.x & 31;
+  const long long q = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  griddep_wait();  // qstat comes from k_prep_rows
+  if (q >= nq) return;
+  const long long t = target[q];
+  const float st = warp_exact_score(Q + q * d, G + t * d, d, METRIC_IP, lane);
+  if (lane == 0) {
+    const float4 qs = qstat[q];
+    const float xb = __uint_as_float(dbstat[0]), xd = __uint_as_float(dbstat[1]);
+    const int d_pad = (d + BK - 1) / BK * BK;
+    float eps = qs.z * xb + sqrtf(qs.x) * xd + (static_cast<float>(d_pad) * 2.4e-7f) * qs.y * xb;
+    eps *= 1.0001f * eps_scale;
+    if (!(eps == eps)) eps = INFINITY;
+    s_t[q] = st;
+    lo[q] = st - eps;
+    hi[q] = st + eps;
+    t32[q] = static_cast<int>(t);
+    e32[q] = exclude != nullptr ? static_cast<int>(exclude[q]) : -1;
+  }
+}
+
+// k_rank_finish: one warp per query. rank = sum over the candidate lists of the certain counts +
+// the band rows that beat the target under the exact rule (fp32 score, then lower row id). A list
+// that overflowed queues the query for the exact recount (k_gallery_rank over the queue).
+__global__ void k_rank_finish(const float* __restrict__ Q, long long nq, const float* __restrict__ G, int d,
+                              int n_lists, int n_qt, const uint2* __restrict__ cand,
+                              const int* __restrict__ cand_cnt, const float* __restrict__ cand_beats,
+                              const float* __restrict__ s_t, const int* __restrict__ t32,
+                              long long* __restrict__ rank_out, int* __restrict__ queue, int* __restrict__ n_queue) {
+  const int lane = threadIdx.x & 31;
+  const long long q = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  griddep_wait();
+  if (q >= nq) return;
+  const int qt = static_cast<int>(q / BM), ql = static_cast<int>(q % BM);
+  const float st = s_t[q];
+  const int t = t32[q];
+  int beats = 0;
+  bool over = false;
+  // certain counts: lanes stride the lists
+  for (int s = lane; s < n_lists; s += 32) {
+    const long long item = static_cast<long long>(s) * n_qt + qt;
+    const int c = cand_cnt[item * BM + ql];
+    over = over || c < 0;
+    beats += __float_as_int(cand_beats[item * BM + ql]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) beats += __shfl_xor_sync(0xffffffffu, beats, o);
+  over = __any_sync(0xffffffffu, over);
+  if (over) {
+    if (lane == 0) queue[atomicAdd(n_queue, 1)] = static_cast<int>(q);
+    return;
+  }
+  // band rows: exact score, exact rule
+  for (int s = 0; s < n_lists; ++s) {
+    const long long item = static_cast<long long>(s) * n_qt + qt;
+    const int c = cand_cnt[item * BM + ql];
+    for (int e = 0; e < c; ++e) {
+      const uint2 en = cand[(item * BM + ql) * LKEEP + e];
+      const int g = static_cast<int>(en.y);
+      const float sg = warp_exact_score(Q + q * d, G + static_cast<long long>(g) * d, d, METRIC_IP, lane);
+      beats += (sg > st) || (sg == st && g < t);
+    }
+  }
+  if (lane == 0) rank_out[q] = beats;
 }
 
 // hits[q][i] = #{ j < ks[i] : labels[I[q][j]] == qlabel[q] }   (ImageNet-domain R@k / P@k,

@@ -90,6 +90,12 @@ struct ScoreParams {
   float* dump;       // debug: full approx scores [n_db][nq][ld_dump], or nullptr
   long long ld_dump;
   unsigned long long* timing;  // nullable: {min start ns, max end ns} of this launch (%globaltimer)
+  // kRank only (gallery ranking by counting, database 0 = the gallery, inner product): per query
+  // the error band [lo, hi] around its target's exact score and the two rows left out of the count
+  const float* rk_lo;
+  const float* rk_hi;
+  const int* rk_target;
+  const int* rk_exclude;     // -1: none
 };
 
 struct ItemCoord {
@@ -176,7 +182,14 @@ __device__ __noinline__ CandState compact_candidates(uint32_t slot0, int cnt, fl
   return r;
 }
 
-template <bool kPair>
+// kRank = false: candidate selection for the top-k search (everything above).
+// kRank = true:  gallery ranking by counting. Per (candidate list, query) the epilogue counts the
+//                rows whose approximate score is above hi = s_target + eps (they beat the target for
+//                certain) and lists the rows inside [lo, hi] (at most LKEEP per list; more sets the
+//                overflow mark and the query is recounted exactly). The target and the excluded row
+//                are skipped by id. Output: the same 128-byte lines (band rows), cand_cnt = band
+//                rows or -1 (overflow), cand_theta = the certain count (as int bits).
+template <bool kPair, bool kRank = false>
 __global__ void __launch_bounds__(ScoreCfg<kPair>::kThreads, 1)
 k_score_topk(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_x0,
              const __grid_constant__ CUtensorMap tm_x1, const ScoreParams p) {
@@ -365,6 +378,18 @@ k_score_topk(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
       const bool active = q_glob < p.nq;
       float theta = active ? -INFINITY : INFINITY;
       int cnt = 0;
+      // rank mode: theta plays "hi", rk_lo_q the lower band edge
+      [[maybe_unused]] float rk_lo_q = INFINITY;
+      [[maybe_unused]] int rk_t = -1, rk_e = -1, beats = 0;
+      [[maybe_unused]] bool overflow = false;
+      if constexpr (kRank) {
+        if (active) {
+          rk_lo_q = p.rk_lo[q_glob];
+          theta = p.rk_hi[q_glob];
+          rk_t = p.rk_target[q_glob];
+          rk_e = p.rk_exclude != nullptr ? p.rk_exclude[q_glob] : -1;
+        }
+      }
       const float* bias = p.bias[c.db];
       const int n_rows = p.n_rows[c.db];
       for (int tile = c.t0; tile < c.t1; ++tile) {
@@ -411,6 +436,25 @@ k_score_topk(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
             for (int j = 0; j < CHUNK; ++j)
               if (static_cast<int>(idx0) + j < n_rows) drow[idx0 + j] = __uint_as_float(v[j]);
           }
+          if constexpr (kRank) {
+            // count the certain winners; rows inside the band are rare and take a plain branch
+#pragma unroll
+            for (int j = 0; j < CHUNK; ++j) {
+              const float sc = __uint_as_float(v[j]);
+              const int id = static_cast<int>(idx0) + j;
+              const bool special = id == rk_t || id == rk_e;
+              beats += (sc > theta && !special) ? 1 : 0;
+              if (sc >= rk_lo_q && !(sc > theta) && !special) {
+                if (cnt < LKEEP) {
+                  sts64(slot0 + static_cast<uint32_t>(cnt) * 256u, v[j], static_cast<uint32_t>(id));
+                  ++cnt;
+                } else {
+                  overflow = true;
+                }
+              }
+            }
+            continue;
+          }
           // APPEND scores at a time, then make sure the next APPEND still fit. (The slot buffers
           // are small on purpose: 32 KB instead of 64 KB buys a fourth TMA stage, and the kernel
           // lives on bytes in flight.)
@@ -453,10 +497,12 @@ k_score_topk(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
       // LKEEP-th best, which becomes theta). They leave as one 128-byte line per (slice, query):
       // [(db, s, qt)][query][LKEEP] {score bits, row id}, padded with {-inf, ~0}; the re-rank
       // kernel reads a slice with a single coalesced half-warp load.
-      if (__any_sync(0xffffffffu, cnt >= LKEEP)) {
-        const CandState st = compact_candidates<CAP>(slot0, cnt, theta);
-        cnt = st.cnt;
-        theta = st.theta;
+      if constexpr (!kRank) {
+        if (__any_sync(0xffffffffu, cnt >= LKEEP)) {
+          const CandState st = compact_candidates<CAP>(slot0, cnt, theta);
+          cnt = st.cnt;
+          theta = st.theta;
+        }
       }
       if (!kPair || qt < p.n_qt) {
         // one candidate line per (slice, column half, query): the re-rank kernel sees S * SUB slices
@@ -470,8 +516,13 @@ k_score_topk(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
           if (e + 1 < cnt) b = lds64(slot0 + (e + 1) * 256);
           *reinterpret_cast<uint4*>(cbase + e) = make_uint4(a.x, a.y, b.x, b.y);
         }
-        p.cand_cnt[oitem * BM + q_local] = cnt;
-        p.cand_theta[oitem * BM + q_local] = theta;
+        if constexpr (kRank) {
+          p.cand_cnt[oitem * BM + q_local] = overflow ? -1 : cnt;
+          p.cand_theta[oitem * BM + q_local] = __int_as_float(beats);
+        } else {
+          p.cand_cnt[oitem * BM + q_local] = cnt;
+          p.cand_theta[oitem * BM + q_local] = theta;
+        }
       }
       __syncwarp();
     }

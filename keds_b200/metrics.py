@@ -34,20 +34,55 @@ def _cuda_device(*tensors) -> torch.device:
     return torch.device("cuda", torch.cuda.current_device())
 
 
+# The evaluation loops score many query sets against ONE gallery (30 checkpoints x 3 feature sets in
+# evaluate_cirr, src/eval_utils.py:617,735): the gallery's native index (device copy of the rows,
+# 16-bit operand, norms, tensor maps) is built once and kept. Entries hold a strong reference to the
+# tensor they were built from, so its storage cannot be recycled under the cache, and are checked by
+# identity + torch's in-place version counter.
+_GALLERY_CACHE: list = []
+_GALLERY_CACHE_SIZE = 3
+
+
+def gallery_index(gallery, device: Optional[torch.device] = None) -> GpuIndexFlat:
+    """The cached inner-product index over `gallery` (a tensor or array [G, d])."""
+    dev = device if device is not None else _cuda_device(gallery)
+    ver = gallery._version if isinstance(gallery, torch.Tensor) else None
+    for i, (obj, v, d_, ix) in enumerate(_GALLERY_CACHE):
+        if obj is gallery and v == ver and d_ == dev and ver is not None:
+            _GALLERY_CACHE.append(_GALLERY_CACHE.pop(i))
+            return ix
+    G = _dev_f32(gallery, dev)
+    if G.dim() != 2:
+        raise ValueError("gallery must be [G, d]")
+    ix = GpuIndexFlat(G.shape[1], METRIC_INNER_PRODUCT, dev.index)
+    ix.add(G)
+    if ver is not None:  # arrays without a version counter are not cached (in-place edits would go unseen)
+        _GALLERY_CACHE.append((gallery, ver, dev, ix))
+        del _GALLERY_CACHE[:-_GALLERY_CACHE_SIZE]
+    return ix
+
+
+def clear_gallery_cache() -> None:
+    _GALLERY_CACHE.clear()
+
+
 def gallery_rank(query: torch.Tensor, gallery: torch.Tensor, target, exclude=None) -> torch.Tensor:
     """rank[q] = number of gallery rows (target and `exclude` left out) that beat the target under
-    (inner product descending, row id ascending). int64 [Q] on the device."""
+    (inner product descending, row id ascending). int64 [Q] on the device. The Q x G contraction
+    runs on the tensor cores against the gallery's cached index (keds_index_rank); the ranks are
+    those of an exact fp32 count."""
     lib = _capi.load()
     dev = _cuda_device(query, gallery)
     Q = _dev_f32(query, dev)
-    G = _dev_f32(gallery, dev)
-    if Q.dim() != 2 or G.dim() != 2 or Q.shape[1] != G.shape[1]:
+    ix = gallery_index(gallery, dev)
+    if Q.dim() != 2 or Q.shape[1] != ix.d:
         raise ValueError("query and gallery must be [*, d] with the same d")
+    n_gallery = ix.ntotal
     t = torch.as_tensor(np.asarray(target) if not isinstance(target, torch.Tensor) else target)
     t = t.to(device=dev, dtype=torch.int64).contiguous()
     if t.numel() != Q.shape[0]:
         raise ValueError("one target per query")
-    if t.numel() and (int(t.min()) < 0 or int(t.max()) >= G.shape[0]):
+    if t.numel() and (int(t.min()) < 0 or int(t.max()) >= n_gallery):
         raise IndexError("target id outside the gallery")
     e_ptr = 0
     if exclude is not None:
@@ -55,15 +90,13 @@ def gallery_rank(query: torch.Tensor, gallery: torch.Tensor, target, exclude=Non
         e = e.to(device=dev, dtype=torch.int64).contiguous()
         if e.numel() != Q.shape[0]:
             raise ValueError("one excluded row (or -1) per query")
-        if e.numel() and (int(e.min()) < -1 or int(e.max()) >= G.shape[0]):
+        if e.numel() and (int(e.min()) < -1 or int(e.max()) >= n_gallery):
             raise IndexError("excluded id outside the gallery")
         e_ptr = e.data_ptr()
     out = torch.empty(Q.shape[0], dtype=torch.int64, device=dev)
     with torch.cuda.device(dev):
-        _capi.check(
-            lib.keds_gallery_rank(Q.data_ptr(), Q.shape[0], G.data_ptr(), G.shape[0], Q.shape[1],
-                                  t.data_ptr(), e_ptr, out.data_ptr(), _stream_ptr(dev.index))
-        )
+        _capi.check(lib.keds_index_rank(ix._h, Q.data_ptr(), Q.shape[0], t.data_ptr(), e_ptr, out.data_ptr(),
+                                        _stream_ptr(dev.index)))
     return out
 
 
@@ -114,13 +147,11 @@ def get_metrics_cirr(image_features, ref_features, reference_names, index_names,
 def get_cirr_testoutput(image_features, ref_features, reference_names, index_names, id_names) -> Dict:
     """src/eval_utils.py:1070-1087: top-50 gallery names per pair id, reference image removed."""
     dev = _cuda_device(image_features, ref_features)
-    G = _dev_f32(image_features, dev)
     Q = _dev_f32(ref_features, dev)
     pos = {n: i for i, n in enumerate(index_names)}
     ref = np.array([pos[n] for n in reference_names], np.int64)
-    ix = GpuIndexFlat(G.shape[1], METRIC_INNER_PRODUCT, dev.index)
-    ix.add(G)
-    if G.shape[0] < 51:  # the reference indexes sorted names [0, 50) after the removal (:1084-1086)
+    ix = gallery_index(image_features, dev)
+    if ix.ntotal < 51:  # the reference indexes sorted names [0, 50) after the removal (:1084-1086)
         raise IndexError("get_cirr_testoutput needs at least 51 gallery images (50 names per pair after "
                          "removing the reference image)")
     _, I = ix.search(Q, 51)
@@ -155,12 +186,11 @@ def get_metrics_imgnet(query_features, image_features, query_labels, target_labe
     P@k = hits_in_top_k / k (:1116), averaged over the queries; k in {1,5,10,50,100,200}."""
     ks = [1, 5, 10, 50, 100, 200]
     dev = _cuda_device(query_features, image_features)
-    G = _dev_f32(image_features, dev)
     Q = _dev_f32(query_features, dev)
     ql = torch.as_tensor(query_labels).to(device=dev, dtype=torch.int64)
     tl = torch.as_tensor(target_labels).to(device=dev, dtype=torch.int64)
-    ix = GpuIndexFlat(G.shape[1], METRIC_INNER_PRODUCT, dev.index)
-    ix.add(G)
+    ix = gallery_index(image_features, dev)
+    n_gallery = ix.ntotal
     kmax = max(ks)
     _, I = ix.search(Q, kmax)
     hits = label_hits(I, tl, ql, ks).to(torch.float32)
@@ -169,5 +199,5 @@ def get_metrics_imgnet(query_features, image_features, query_labels, target_labe
     metrics: Dict[str, float] = {}
     for i, k in enumerate(ks):
         metrics[f"Real2Sketch_R@{k}"] = float((hits[:, i] / (num_total + 1e-5)).mean())
-        metrics[f"Real2Sketch_P@{k}"] = float((hits[:, i] / float(min(k, G.shape[0]))).mean())
+        metrics[f"Real2Sketch_P@{k}"] = float((hits[:, i] / float(min(k, n_gallery))).mean())
     return metrics

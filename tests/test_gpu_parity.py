@@ -586,6 +586,40 @@ def test_gallery_rank_matches_oracle_at_cirr_shape():
         assert np.mean(got < k) == pytest.approx(np.mean(want < k), abs=5e-4)
 
 
+def test_gallery_rank_tensor_core_path_equals_the_exact_count():
+    """keds_index_rank: the tensor-core count + exact settlement of the band rows must give the
+    ranks of the plain fp32 count (keds_gallery_rank's SIMT kernel on the same inputs) bit for bit:
+    mid-ranked random targets (crowded bands), a 50k-row gallery, a batch below one query tile, an
+    inflated error bound that overflows the band lists (exact recount queue), and no exclusions."""
+    lib = _capi.load()
+
+    def simt(q, gal, tgt, ref):
+        out = torch.empty(q.shape[0], dtype=torch.int64, device="cuda")
+        _capi.check(lib.keds_gallery_rank(q.data_ptr(), 60, gal.data_ptr(), gal.shape[0], gal.shape[1],
+                                          tgt.data_ptr(), 0 if ref is None else ref.data_ptr(), out.data_ptr(), None))
+        torch.cuda.synchronize()
+        return out[:60]   # below 64 queries the C entry point keeps to the fp32 SIMT kernel
+
+    for ng, nq, seed in ((2297, 4181, 1), (50000, 1000, 2), (700, 100, 3)):
+        gal = torch.from_numpy(unit(ng, 768, 900 + seed)).cuda()
+        q = torch.from_numpy(unit(nq, 768, 910 + seed)).cuda()
+        rng = np.random.default_rng(seed)
+        tgt = torch.from_numpy(rng.integers(0, ng, nq)).cuda()
+        ref = (tgt + torch.from_numpy(rng.integers(1, ng, nq)).cuda()) % ng
+        got = km.gallery_rank(q, gal, tgt, ref)
+        want = orc.target_ranks(q.cpu().numpy(), gal.cpu().numpy(), tgt.cpu().numpy(), ref.cpu().numpy())
+        assert np.abs(got.cpu().numpy() - want).max() <= 1 and np.mean(got.cpu().numpy() == want) > 0.995
+        assert torch.equal(got[:60], simt(q, gal, tgt, ref))          # the exact fp32 count, bit for bit
+        got2 = km.gallery_rank(q, gal, tgt)                            # cached index, no exclusion
+        assert torch.equal(got2[:60], simt(q, gal, tgt, None))
+        ix = km.gallery_index(gal)
+        ix.set_eps_scale(200.0)                                        # bands overflow: exact recount queue
+        got3 = km.gallery_rank(q, gal, tgt, ref)
+        ix.set_eps_scale(1.0)
+        assert torch.equal(got3, got)
+    km.clear_gallery_cache()
+
+
 def test_imgnet_shaped_recall_50k_gallery():
     """configs[3]: 50k-row gallery with labels < 7000, top-200 label hits."""
     rng = np.random.default_rng(1008)
