@@ -64,6 +64,48 @@ def gallery_index(gallery, device: Optional[torch.device] = None) -> GpuIndexFla
 
 def clear_gallery_cache() -> None:
     _GALLERY_CACHE.clear()
+    _NAME_TABLES.clear()
+
+
+# name -> gallery row tables, kept per names list the same way (identity + length + a fingerprint of
+# a few entries): the eval loops pass the same index_names list for every checkpoint.
+_NAME_TABLES: list = []
+
+
+def _name_table(names, basename: bool) -> Dict[str, int]:
+    n = len(names)
+    probe = (names[0], names[n // 2], names[-1]) if n else ()
+    for i, (obj, m, fp, bn, pos) in enumerate(_NAME_TABLES):
+        if obj is names and m == n and fp == probe and bn == basename:
+            _NAME_TABLES.append(_NAME_TABLES.pop(i))
+            return pos
+    # os.path.basename on POSIX is "everything after the last slash" (src/eval_utils.py:1046-1048)
+    keys = [s.rsplit("/", 1)[-1] for s in names] if basename else names
+    pos = {s: i for i, s in enumerate(keys)}
+    if len(pos) != n:
+        raise AssertionError("gallery names must be unique (the reference asserts one hit per query)")
+    _NAME_TABLES.append((names, n, probe, basename, pos))
+    del _NAME_TABLES[:-4]
+    return pos
+
+
+def _ids(pos: Dict[str, int], names) -> np.ndarray:
+    return np.fromiter(map(pos.__getitem__, names), np.int64, len(names))
+
+
+def _id_tensor(x, n_rows: int, dev: torch.device, what: str, lowest: int = 0) -> torch.Tensor:
+    """int64 ids on the device, range-checked without a device round trip when they arrive as host data"""
+    if isinstance(x, torch.Tensor) and x.is_cuda:
+        t = x.to(device=dev, dtype=torch.int64).contiguous()
+        if t.numel():
+            lo, hi = torch.stack((t.amin(), t.amax())).tolist()
+            if lo < lowest or hi >= n_rows:
+                raise IndexError(f"{what} id outside the gallery")
+        return t
+    a = np.ascontiguousarray(x.numpy() if isinstance(x, torch.Tensor) else np.asarray(x), dtype=np.int64)
+    if a.size and (a.min() < lowest or a.max() >= n_rows):
+        raise IndexError(f"{what} id outside the gallery")
+    return torch.from_numpy(a).to(dev, non_blocking=True)
 
 
 def gallery_rank(query: torch.Tensor, gallery: torch.Tensor, target, exclude=None) -> torch.Tensor:
@@ -78,20 +120,14 @@ def gallery_rank(query: torch.Tensor, gallery: torch.Tensor, target, exclude=Non
     if Q.dim() != 2 or Q.shape[1] != ix.d:
         raise ValueError("query and gallery must be [*, d] with the same d")
     n_gallery = ix.ntotal
-    t = torch.as_tensor(np.asarray(target) if not isinstance(target, torch.Tensor) else target)
-    t = t.to(device=dev, dtype=torch.int64).contiguous()
+    t = _id_tensor(target, n_gallery, dev, "target")
     if t.numel() != Q.shape[0]:
         raise ValueError("one target per query")
-    if t.numel() and (int(t.min()) < 0 or int(t.max()) >= n_gallery):
-        raise IndexError("target id outside the gallery")
     e_ptr = 0
     if exclude is not None:
-        e = torch.as_tensor(np.asarray(exclude) if not isinstance(exclude, torch.Tensor) else exclude)
-        e = e.to(device=dev, dtype=torch.int64).contiguous()
+        e = _id_tensor(exclude, n_gallery, dev, "excluded", lowest=-1)
         if e.numel() != Q.shape[0]:
             raise ValueError("one excluded row (or -1) per query")
-        if e.numel() and (int(e.min()) < -1 or int(e.max()) >= n_gallery):
-            raise IndexError("excluded id outside the gallery")
         e_ptr = e.data_ptr()
     out = torch.empty(Q.shape[0], dtype=torch.int64, device=dev)
     with torch.cuda.device(dev):
@@ -124,23 +160,15 @@ def get_metrics_coco(image_features, ref_features, logit_scale=None) -> Dict[str
 
 def get_metrics_fashion(image_features, ref_features, target_names, answer_names) -> Dict[str, float]:
     """src/eval_utils.py:1025-1037."""
-    pos = {n: i for i, n in enumerate(target_names)}
-    if len(pos) != len(target_names):
-        raise AssertionError("gallery names must be unique (the reference asserts one hit per query)")
-    tgt = np.array([pos[n] for n in answer_names], np.int64)
+    tgt = _ids(_name_table(target_names, False), answer_names)
     r = gallery_rank(ref_features, image_features, tgt).cpu().numpy()
     return {f"R@{k}": float(np.sum(r < k)) / len(r) * 100 for k in [1, 5, 10, 50, 100]}
 
 
 def get_metrics_cirr(image_features, ref_features, reference_names, index_names, target_names) -> Dict[str, float]:
     """src/eval_utils.py:1040-1067: the query's own reference image is removed from its ranking."""
-    names = [os.path.basename(n) for n in index_names]  # G calls instead of Q*G (:1046-1048)
-    pos = {n: i for i, n in enumerate(names)}
-    if len(pos) != len(names):
-        raise AssertionError("gallery names must be unique (the reference asserts one hit per query)")
-    tgt = np.array([pos[n] for n in target_names], np.int64)
-    ref = np.array([pos[n] for n in reference_names], np.int64)
-    r = gallery_rank(ref_features, image_features, tgt, ref).cpu().numpy()
+    pos = _name_table(index_names, True)  # G basenames, once per gallery, instead of Q*G per call (:1046-1048)
+    r = gallery_rank(ref_features, image_features, _ids(pos, target_names), _ids(pos, reference_names)).cpu().numpy()
     return {f"recall_R@{k}": float(np.sum(r < k)) / len(r) * 100 for k in [1, 5, 10, 50, 100]}
 
 
@@ -148,8 +176,7 @@ def get_cirr_testoutput(image_features, ref_features, reference_names, index_nam
     """src/eval_utils.py:1070-1087: top-50 gallery names per pair id, reference image removed."""
     dev = _cuda_device(image_features, ref_features)
     Q = _dev_f32(ref_features, dev)
-    pos = {n: i for i, n in enumerate(index_names)}
-    ref = np.array([pos[n] for n in reference_names], np.int64)
+    ref = _ids(_name_table(index_names, False), reference_names)
     ix = gallery_index(image_features, dev)
     if ix.ntotal < 51:  # the reference indexes sorted names [0, 50) after the removal (:1084-1086)
         raise IndexError("get_cirr_testoutput needs at least 51 gallery images (50 names per pair after "
