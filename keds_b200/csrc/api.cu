@@ -225,6 +225,7 @@ struct keds_index {
   bool attrs_set = false;
   bool use_pdl = true;
   int rerank_threads_large = 128;  // block size of the throughput re-rank variant (KEDS_RERANK_THREADS)
+  int rerank_variant = 0;          // 0: by batch size; 1 / 2: force the latency / throughput variant
   // in-kernel timing of the scoring kernel (bench.py's roofline leg): {min start, max end} ns
   bool timing_on = false;
   DevBuf timing;
@@ -255,6 +256,10 @@ int set_kernel_attrs(keds_index* ix) {
   CK(cudaFuncSetAttribute(k_exact_fallback, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   const char* no_pdl = getenv("KEDS_NO_PDL");
   ix->use_pdl = !(no_pdl && no_pdl[0] == '1');
+  if (const char* rv = getenv("KEDS_RERANK_VARIANT")) {
+    if (!strcmp(rv, "latency")) ix->rerank_variant = 1;
+    if (!strcmp(rv, "throughput")) ix->rerank_variant = 2;
+  }
   if (const char* rt = getenv("KEDS_RERANK_THREADS")) {
     const int v = atoi(rt);
     if (v == 32 || v == 64 || v == 128 || v == 256) ix->rerank_threads_large = v;
@@ -604,7 +609,9 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
     rp.eps_scale = a->eps_scale;
     rp.band_max = a->ctrl.as<unsigned int>() + CTRL_BAND;
     // one wave of blocks (two per SM): the latency variant; more: the four-per-SM throughput variant
-    const bool small_batch = nq * n_db <= 2ll * a->num_sms;
+    bool small_batch = nq * n_db <= 2ll * a->num_sms;
+    if (a->rerank_variant == 1) small_batch = true;   // experiments: KEDS_RERANK_VARIANT=latency|throughput
+    if (a->rerank_variant == 2) small_batch = false;
     // Candidate capacity. A single wave has the shared memory to spare: full size. Large batches
     // live on blocks per SM, so they start small and follow the band a recent search reported (a
     // query that does not fit is answered by the exact fallback and raises the next call's figure).

@@ -66,6 +66,27 @@ def test_tensor_core_scores_match_the_rounded_operand_reference(n, b, d, fmt):
     check(ix, db, q, min(16, n), "ip")
 
 
+def test_fp16_subnormal_operands_are_multiplied_not_flushed():
+    """The certificate's bound is stated for the operands as rounded to fp16, subnormals included
+    (|x| < 6.1e-5: about one element in 800 of a unit-norm 768-d row). If the tensor cores flushed
+    them the approximate score would miss their products: check a row set made almost entirely of
+    fp16 subnormals against float64 products of the rounded operands."""
+    rng = np.random.default_rng(5)
+    n, b, d = 512, 128, 256
+    db = (rng.uniform(1e-6, 5e-5, size=(n, d)) * rng.choice([-1.0, 1.0], size=(n, d))).astype(np.float32)
+    db[:, 0] = 0.5                                     # one normal element per row keeps fp16 the better format
+    q = rng.uniform(0.5, 1.0, size=(b, d)).astype(np.float32)
+    ix = build(db, "ip")
+    ix.set_operand_format("fp16")
+    got = ix.debug_scores(torch.from_numpy(q).cuda()).cpu().double()
+    h = lambda a: torch.from_numpy(a).to(torch.float16).double()
+    ref = h(q) @ h(db).t()
+    sub = (h(q)[:, 1:] @ h(db)[:, 1:].t()).abs().mean().item()      # what the subnormal part contributes
+    assert sub > 1e-4
+    assert (got - ref).abs().max().item() < 2e-6, ((got - ref).abs().max().item(), sub)
+    check(ix, db, q, 16, "ip")
+
+
 def test_operand_format_follows_the_data():
     """fp16 for data inside its range, bf16 when a value would overflow or flush; a later add that
     breaks the fp16 assumption re-rounds the rows already held; a mixed pair of databases settles
