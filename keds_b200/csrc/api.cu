@@ -214,7 +214,8 @@ struct keds_index {
   bool tm_x_ok = false;
   bool use_pair = true;
   // per-call scratch (one search in flight per handle)
-  DevBuf q_f32, q_bf16, qstat, cand, cand_cnt, cand_theta, flagged[2], ctrl, exact_scratch, rk;
+  DevBuf q_f32, q_bf16, qstat, cand, cand_cnt, cand_theta, flagged[2], ctrl, exact_scratch, rk, theta0;
+  bool warm_start = true;  // lists start at a finished list's threshold (KEDS_NO_WARM_START=1: every list cold)
   DevBuf D_stage[2], I_stage[2];
   HostBuf h_q, h_out;  // pinned staging for host-pointer calls
   CUtensorMap tm_q;
@@ -256,6 +257,7 @@ int set_kernel_attrs(keds_index* ix) {
   CK(cudaFuncSetAttribute(k_exact_fallback, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   const char* no_pdl = getenv("KEDS_NO_PDL");
   ix->use_pdl = !(no_pdl && no_pdl[0] == '1');
+  if (const char* ws = getenv("KEDS_NO_WARM_START")) ix->warm_start = !(ws[0] == '1');
   if (const char* rv = getenv("KEDS_RERANK_VARIANT")) {
     if (!strcmp(rv, "latency")) ix->rerank_variant = 1;
     if (!strcmp(rv, "throughput")) ix->rerank_variant = 2;
@@ -346,10 +348,13 @@ Plan make_plan(const keds_index* ix, int n_db, int64_t nq, int k, int64_t n_min,
     const long long G = std::min<long long>(items, units);
     const long long per_cta = (items + G - 1) / G;
     double cost = static_cast<double>(per_cta) * ((T_max + S - 1) / S) + 0.35 * per_cta;
-    // expected fallbacks: a query is flagged when one slice holds LKEEP or more of the ~2k rows at
-    // or above tau (Poisson tail, five-fold margin) -- large k wants more slices than the SM count
+    // expected fallbacks: a query is flagged when one list holds LKEEP or more of the rows at or
+    // above tau (Poisson tail, five-fold margin) -- large k wants more lists than the SM count.
+    // Rows at or above tau on i.i.d. data: ~2.4k with bf16 operands (wide band), k plus a few with
+    // fp16 (measured 18-24 at k = 16, ~215 at k = 200); crowded bands arrive through band_hint.
     {
-      const double lam = std::max(2.0 * k, 1.25 * static_cast<double>(band_hint)) / (S * pl.sub);
+      const double band = ix->fmt == FMT_FP16 ? 1.15 * k + 12.0 : 2.0 * k;
+      const double lam = std::max(band, 1.25 * static_cast<double>(band_hint)) / (S * pl.sub);
       double term = std::exp(-lam), tail = 0.0;  // term_i = e^-lam lam^i / i!
       for (int i = 1; i <= LKEEP + 40; ++i) {
         term *= lam / i;
@@ -531,6 +536,8 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
     const int64_t q_rows = static_cast<int64_t>(pl.n_qt) * BM;
     CKS(ensure_q_map(a, q_rows, st));
     CKS(a->qstat.ensure(static_cast<size_t>(nq) * sizeof(float4)));
+    const int64_t theta_ld = q_rows;
+    CKS(a->theta0.ensure(static_cast<size_t>(n_db) * theta_ld * 4));
     {
       CKS(prof_mark(a, st, 0));
       const int threads = 256;
@@ -540,7 +547,8 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
       CKS(launch_k(a->use_pdl, k_prep_rows, dim3(blocks), dim3(threads), 0, st, q_dev,
                    static_cast<long long>(nq), a->d, a->d_pad, a->fmt, a->q_bf16.as<uint16_t>(),
                    a->qstat.as<float4>(), static_cast<float*>(nullptr), static_cast<unsigned int*>(nullptr),
-                   a->ctrl.as<unsigned int>(), CTRL_WORDS, tchain));
+                   a->ctrl.as<unsigned int>(), CTRL_WORDS, a->theta0.as<float>(), static_cast<int>(n_db * theta_ld),
+                   tchain));
       a->stats.launches++;
     }
     // candidate lines are indexed by (db, slice, query tile) whatever the work-item grouping
@@ -567,6 +575,8 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
     sp.cand = a->cand.as<uint2>();
     sp.cand_cnt = a->cand_cnt.as<int>();
     sp.cand_theta = a->cand_theta.as<float>();
+    sp.theta0 = a->warm_start ? a->theta0.as<float>() : nullptr;
+    sp.theta_ld = static_cast<int>(theta_ld);
     sp.err = a->ctrl.as<uint32_t>() + 2;
     sp.dump = dump;
     sp.ld_dump = ld_dump;
@@ -883,7 +893,7 @@ int keds_index_create(int d, int metric, int device, keds_index_t** out) {
   DevBuf* tracked[] = {&ix->x_f32, &ix->x_bf16, &ix->bias, &ix->q_f32, &ix->q_bf16, &ix->qstat, &ix->cand,
                        &ix->cand_cnt, &ix->cand_theta, &ix->flagged[0], &ix->flagged[1], &ix->ctrl,
                        &ix->exact_scratch, &ix->D_stage[0], &ix->D_stage[1], &ix->I_stage[0], &ix->I_stage[1],
-                       &ix->rk};
+                       &ix->rk, &ix->theta0};
   for (DevBuf* b : tracked) b->gen = &ix->generation;
   *out = ix;
   return 0;
@@ -895,7 +905,7 @@ void keds_index_free(keds_index_t* ix) {
   DevBuf* bufs[] = {&ix->x_f32, &ix->x_bf16, &ix->bias, &ix->dbstat, &ix->q_f32, &ix->q_bf16,
                     &ix->qstat, &ix->cand, &ix->cand_cnt, &ix->cand_theta, &ix->flagged[0],
                     &ix->flagged[1], &ix->ctrl, &ix->exact_scratch, &ix->D_stage[0], &ix->D_stage[1],
-                    &ix->I_stage[0], &ix->I_stage[1], &ix->timing, &ix->probe, &ix->rk};
+                    &ix->I_stage[0], &ix->I_stage[1], &ix->timing, &ix->probe, &ix->rk, &ix->theta0};
   for (DevBuf* b : bufs) b->release();
   ix->h_q.release();
   ix->h_out.release();
@@ -932,7 +942,7 @@ static int prep_db_rows(keds_index* ix, int64_t r0, int64_t r1) {
   const unsigned blocks = static_cast<unsigned>(std::min<int64_t>((n * 32 + 255) / 256, ix->num_sms * 16));
   k_prep_rows<<<blocks, 256>>>(ix->x_f32.as<float>() + r0 * d, n, ix->d, ix->d_pad, ix->fmt,
                                ix->x_bf16.as<uint16_t>() + r0 * dp, nullptr, ix->bias.as<float>() + r0,
-                               ix->dbstat.as<unsigned int>(), nullptr, 0, nullptr);
+                               ix->dbstat.as<unsigned int>(), nullptr, 0, nullptr, 0, nullptr);
   CK(cudaGetLastError());
   return 0;
 }
@@ -1561,7 +1571,7 @@ int keds_index_rank(keds_index_t* ix, const float* q, int64_t nq, const int64_t*
       CKS(launch_k(ix->use_pdl, k_prep_rows, dim3(blocks), dim3(256), 0, st, qp, static_cast<long long>(nb), d,
                    ix->d_pad, ix->fmt, ix->q_bf16.as<uint16_t>(), ix->qstat.as<float4>(), static_cast<float*>(nullptr),
                    static_cast<unsigned int*>(nullptr), ix->ctrl.as<unsigned int>(), CTRL_WORDS,
-                   static_cast<unsigned long long*>(nullptr)));
+                   static_cast<float*>(nullptr), 0, static_cast<unsigned long long*>(nullptr)));
     }
     const unsigned wblocks = static_cast<unsigned>((nb * 32 + 255) / 256);
     CKS(launch_k(ix->use_pdl, k_rank_targets, dim3(wblocks), dim3(256), 0, st, qp, static_cast<long long>(nb), G, d,

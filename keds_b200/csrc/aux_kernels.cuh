@@ -170,14 +170,18 @@ __global__ void k_prep_rows(const float* __restrict__ x, long long n, int d, int
                             uint16_t* __restrict__ out, float4* __restrict__ stat,
                             float* __restrict__ bias, unsigned int* __restrict__ gmax,
                             unsigned int* __restrict__ zero_words, int n_zero,
+                            float* __restrict__ neg_inf_words, int n_neg_inf,
                             unsigned long long* timing) {
   const int lane = threadIdx.x & 31;
   griddep_wait();               // earlier kernels of the stream may still read what is rewritten here
   griddep_launch_dependents();  // the scoring kernel may start its prologue
   const unsigned long long t_start = ktimer_begin(timing);
   // per-call control words (flag counters, error word) are cleared here instead of by a separate
-  // memset node in front of every search
+  // memset node in front of every search; the shared per-query thresholds start at -inf
   if (zero_words != nullptr && blockIdx.x == 0 && threadIdx.x < n_zero) zero_words[threadIdx.x] = 0u;
+  if (neg_inf_words != nullptr)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_neg_inf; i += gridDim.x * blockDim.x)
+      neg_inf_words[i] = -INFINITY;
   const long long warp0 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
   float mx_b = 0.f, mx_d = 0.f, mx_n = 0.f;

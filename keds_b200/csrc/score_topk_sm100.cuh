@@ -86,6 +86,8 @@ struct ScoreParams {
   uint2* cand;       // [n_db * S * kSub * n_qt][BM][LKEEP] {approx score bits, row id}, padded {-inf, ~0}
   int* cand_cnt;     // [..][BM]
   float* cand_theta; // [..][BM]  everything the slice dropped scored <= theta
+  float* theta0;     // [n_db][theta_ld] running per-query drop threshold shared by all lists of a query (see epilogue)
+  int theta_ld;
   uint32_t* err;     // device error word (0 = ok)
   float* dump;       // debug: full approx scores [n_db][nq][ld_dump], or nullptr
   long long ld_dump;
@@ -378,6 +380,20 @@ k_score_topk(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
       const bool active = q_glob < p.nq;
       float theta = active ? -INFINITY : INFINITY;
       int cnt = 0;
+      // Warm start: a list may begin at the final threshold of ANY list of the same query that has
+      // already finished. That threshold is the 16th best score of its list, and the certificate
+      // needs every list's threshold below tau anyway, so rows at or below it can be dropped here
+      // as well (the list's reported threshold only rises from there). Without it every work item
+      // starts cold -- every score of its first columns is appended and the list compacted every
+      // eight appends -- which is what made short slices (k = 200 galleries: two tiles per item)
+      // spend more time warming lists than scoring. Any stale value is still a valid start.
+      float* th0 = nullptr;
+      if constexpr (!kRank) {
+        if (active && p.theta0 != nullptr) {
+          th0 = p.theta0 + static_cast<long long>(c.db) * p.theta_ld + q_glob;
+          theta = __ldcg(th0);
+        }
+      }
       // rank mode: theta plays "hi", rk_lo_q the lower band edge
       [[maybe_unused]] float rk_lo_q = INFINITY;
       [[maybe_unused]] int rk_t = -1, rk_e = -1, beats = 0;
@@ -522,6 +538,11 @@ k_score_topk(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
         } else {
           p.cand_cnt[oitem * BM + q_local] = cnt;
           p.cand_theta[oitem * BM + q_local] = theta;
+          // publish for the lists that start later (float max through the sign-split integer trick)
+          if (th0 != nullptr && theta > -INFINITY) {
+            if (theta >= 0.f) atomicMax(reinterpret_cast<int*>(th0), __float_as_int(theta));
+            else atomicMin(reinterpret_cast<unsigned int*>(th0), __float_as_uint(theta));
+          }
         }
       }
       __syncwarp();
