@@ -224,7 +224,7 @@ int keds_label_hits(const int64_t* I, int64_t nq, int kmax, const int64_t* label
                     const int64_t* qlabel, const int32_t* ks, int nks, int32_t* hits,
                     void* cuda_stream);
 
-/* ---- neighbour consumer (forward only) ----------------------------------------
+/* ---- neighbour consumer (eval forward here, training entry points below) ------
  * The modules that consume the retrieved neighbours, evaluated in one launch sequence:
  *   mapped = img2text(feat); nb_img = img2text(base_img[I_img]); nb_txt = img2text(base_txt[I_txt])
  *   tokens[:,0,:] = retrieval_fuse(mapped[:,None], nb_img, nb_img)   (CrossFormer, image stack = 0)
@@ -232,8 +232,7 @@ int keds_label_hits(const int64_t* I, int64_t nq, int kmax, const int64_t* label
  *   tokens[:,2,:] = mapped
  * i.e. src/trainer.py:59-69 and src/eval_utils.py:378-383,515-519,661-668,806-810,943-947 with
  * IM2TEXT / CrossFormer / CrossAttention of src/model/model.py:37-123 in eval mode (dropout off).
- * Arithmetic: tf32 tensor-core products with fp32 accumulation, fp32 everywhere else. No backward
- * pass: training keeps the PyTorch modules.
+ * Arithmetic: tf32 tensor-core products with fp32 accumulation, fp32 everywhere else.
  *
  * create: d_in = feature width (768), d_mid = IM2TEXT middle_dim (512), d_tok = IM2TEXT output_dim =
  *   CrossFormer q/k/v_dim (768), n_hidden = IM2TEXT n_layer (2), n_layers = CrossFormer num_layers
@@ -266,6 +265,36 @@ int keds_consumer_forward(keds_consumer_t* c, const float* feat, const float* ba
 /* synchronise the stream and report a device-side pipeline error, if any; launches (nullable) =
  * kernels launched by this handle so far */
 int keds_consumer_check(keds_consumer_t* c, void* cuda_stream, int64_t* launches);
+
+/* ---- the same modules while they are being trained (src/trainer.py:59-69, backward at :462-474) --
+ * Parameters live in ONE flat caller-owned device buffer (e.g. a torch Parameter) that the optimiser
+ * updates in place; the handle reads through it and nothing is copied per step. Layout (floats,
+ * every block padded to a multiple of 4): IM2TEXT W_i, b_i for i = 0 .. n_hidden (fc_out last); then
+ * per stack (image, text): to_k / to_v of all layers stacked as [L][k | v][inner] x d_tok with their
+ * biases, then per layer to_q W, b and to_out W, b. param_offset gives any slot's offsets and shape.
+ *   bind_params     adopt the buffer (replaces set_linear + finalize; set_linear afterwards writes
+ *                   into the buffer).
+ *   forward_train   keds_consumer_forward that keeps the activations the backward needs. masks:
+ *                   NULL or n_hidden device pointers (entries nullable) to float [B(1+2k)][d_mid]
+ *                   dropout multipliers (0 or 1/(1-p); rows ordered queries | image neighbours |
+ *                   text neighbours), applied between Linear and ReLU as in IM2TEXT
+ *                   (src/model/model.py:110-116); they must stay alive until the backward.
+ *   backward        dtokens [B][3][d_tok] -> grads (param_count floats, same layout, overwritten).
+ *                   One backward per forward_train. tf32 tensor-core products, fp32 accumulation. */
+int64_t keds_consumer_param_count(const keds_consumer_t* c);
+int keds_consumer_param_offset(const keds_consumer_t* c, int kind, int stack, int layer, int64_t* w_off,
+                               int64_t* b_off, int64_t* rows, int64_t* cols);
+int keds_consumer_bind_params(keds_consumer_t* c, float* params);
+int keds_consumer_forward_train(keds_consumer_t* c, const float* feat, const float* base_img, int64_t n_img,
+                                const float* base_txt, int64_t n_txt, const int64_t* I_img,
+                                const int64_t* I_txt, const int32_t* perm, int64_t B, int k,
+                                const float* const* masks, float* tokens, void* cuda_stream);
+int keds_consumer_backward(keds_consumer_t* c, const float* dtokens, float* grads, void* cuda_stream);
+/* Test hook: hidden activations [B(1+2k)][d_mid] of IM2TEXT layer `layer` as the last forward_train
+ * left them (after dropout and ReLU). Their signs are the ReLU gates the backward uses; a tf32
+ * forward and a float64 one disagree on them for pre-activations within rounding of zero, so a
+ * gradient comparison has to take the gates from here. Synchronises. */
+int keds_consumer_debug_hidden(keds_consumer_t* c, int layer, float* out, int64_t n, void* cuda_stream);
 /* Diagnostics: with debug on, every k_linear_tf32 launch of a forward records per CTA
  * {start, prologue done, dependency met, accumulator ready, end} (%globaltimer ns).
  * debug_timeline copies launch `launch` (index within the last forward) of n_ctas CTAs to

@@ -109,6 +109,17 @@ SIGNATURES = {
         [_vp, _vp, _vp, C.c_int64, _vp, C.c_int64, _vp, _vp, _vp, C.c_int64, C.c_int, _vp, _vp],
     ),
     "keds_consumer_check": (C.c_int, [_vp, _vp, C.POINTER(C.c_int64)]),
+    "keds_consumer_param_count": (C.c_int64, [_vp]),
+    "keds_consumer_param_offset": (
+        C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                  C.POINTER(C.c_int64)]),
+    "keds_consumer_bind_params": (C.c_int, [_vp, _vp]),
+    "keds_consumer_forward_train": (
+        C.c_int,
+        [_vp, _vp, _vp, C.c_int64, _vp, C.c_int64, _vp, _vp, _vp, C.c_int64, C.c_int, C.POINTER(_vp), _vp, _vp],
+    ),
+    "keds_consumer_backward": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "keds_consumer_debug_hidden": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, _vp]),
     "keds_consumer_set_debug": (C.c_int, [_vp, C.c_int]),
     "keds_consumer_debug_timeline": (C.c_int, [_vp, C.c_int, _vp, C.c_int64]),
     "keds_clip_loss_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),

@@ -12,8 +12,12 @@ The reference evaluates, per batch (src/trainer.py:59-69; src/eval_utils.py:378-
 
 as ~60 small PyTorch kernels on `[B, k, 768]` tensors that first travelled GPU -> CPU -> GPU.
 `NeighbourConsumer` takes the three modules' weights once and produces `tokens` from the query
-features and the neighbour *ids* (the rows are gathered from the resident databases).  Forward
-only: training, where the modules learn, keeps the PyTorch modules.
+features and the neighbour *ids* (the rows are gathered from the resident databases): the eval
+loops.  `TrainableNeighbourConsumer` is the same block while the modules learn (src/trainer.py:59-69,
+backward at :462-474): its parameters live in one flat torch Parameter that the optimiser updates
+in place and the native handle reads through, forward and backward are native launch sequences
+(tf32 tcgen05 GEMMs with the operand roles turned for dX and dW), and the gradients arrive through
+torch.autograd like any module's.
 
 Weights are taken from `state_dict()`s with the reference's own parameter names, so
 `NeighbourConsumer.from_modules(img2text, retrieval_fuse, text_condition)` works on the reference's
@@ -173,5 +177,163 @@ class NeighbourConsumer:
     def __del__(self) -> None:  # pragma: no cover
         try:
             self.close()
+        except Exception:
+            pass
+
+
+class _ConsumerFn(torch.autograd.Function):
+    """tokens = consumer(feature, ids) with the gradient of the flat parameter vector."""
+
+    @staticmethod
+    def forward(ctx, mod, feature, image_index, text_index, I_img, I_txt, perm, masks, flat):
+        B, k = I_img.shape
+        tokens = torch.empty((B, 3, mod.d_tok), dtype=torch.float32, device=feature.device)
+        mp = None
+        if masks is not None:
+            mp = (C.c_void_p * mod.n_hidden)(*[0 if m is None else m.data_ptr() for m in masks])
+        pp = 0 if perm is None else perm.data_ptr()
+        _capi.check(mod._lib.keds_consumer_forward_train(
+            mod._h, feature.data_ptr(), image_index.rows_ptr(), image_index.ntotal, text_index.rows_ptr(),
+            text_index.ntotal, I_img.data_ptr(), I_txt.data_ptr(), pp, B, k, mp, tokens.data_ptr(),
+            _stream_ptr(mod.device)))
+        ctx.mod, ctx.keep = mod, (masks, feature, I_img, I_txt, perm)   # alive until the backward has run
+        return tokens
+
+    @staticmethod
+    def backward(ctx, dtokens):
+        mod = ctx.mod
+        grads = torch.zeros_like(mod.flat)
+        dt = dtokens.contiguous().to(torch.float32)
+        _capi.check(mod._lib.keds_consumer_backward(mod._h, dt.data_ptr(), grads.data_ptr(), _stream_ptr(mod.device)))
+        return None, None, None, None, None, None, None, None, grads
+
+
+class TrainableNeighbourConsumer(torch.nn.Module):
+    """img2text + retrieval_fuse + text_condition as ONE trainable module on the native path.
+
+        consumer = TrainableNeighbourConsumer.from_modules(img2text, retrieval_fuse, text_condition, device=gpu)
+        optimizer = torch.optim.AdamW(consumer.parameters(), ...)
+        tokens = consumer(image_features, image_index, text_index, I_img, I_txt)      # [B, 3, d_tok], differentiable
+        ...
+        loss.backward(); optimizer.step()
+
+    `flat` holds every weight and bias (layout: keds_consumer_param_offset); `state_dicts()` hands them
+    back under the reference's parameter names (views), `load_state_dicts` takes them in. In train()
+    mode IM2TEXT's dropout (src/model/model.py:110-116, p = `dropout`) is applied with masks drawn
+    by torch's generator; eval() runs the plain forward."""
+
+    def __init__(self, img2text_sd: Mapping[str, torch.Tensor], retrieval_fuse_sd: Mapping[str, torch.Tensor],
+                 text_condition_sd: Mapping[str, torch.Tensor], heads: int = 8, device: int = 0,
+                 dropout: float = 0.1) -> None:
+        super().__init__()
+        self._lib = _capi.load()
+        self._h = C.c_void_p()
+        self.device = int(device)
+        self.dropout = float(dropout)
+        n_hidden = _count_prefix(img2text_sd, "layers.{}.0.weight")
+        n_layers = _count_prefix(retrieval_fuse_sd, "cross_layers.{}.to_q.weight")
+        if n_hidden < 1 or n_layers < 1 or "fc_out.weight" not in img2text_sd:
+            raise ValueError("state_dicts do not look like IM2TEXT / CrossFormer (src/model/model.py:81-123)")
+        w0 = img2text_sd["layers.0.0.weight"]
+        self.d_mid, self.d_in = int(w0.shape[0]), int(w0.shape[1])
+        self.d_tok = int(img2text_sd["fc_out.weight"].shape[0])
+        inner = int(retrieval_fuse_sd["cross_layers.0.to_q.weight"].shape[0])
+        self.n_hidden, self.n_layers, self.heads, self.dim_head = n_hidden, n_layers, int(heads), inner // int(heads)
+        _capi.check(self._lib.keds_consumer_create(self.d_in, self.d_mid, self.d_tok, n_hidden, n_layers, self.heads,
+                                                   self.dim_head, self.device, C.byref(self._h)))
+        n = int(self._lib.keds_consumer_param_count(self._h))
+        self.flat = torch.nn.Parameter(torch.zeros(n, dtype=torch.float32, device=torch.device("cuda", self.device)))
+        self._slots = {}   # (module prefix, reference parameter name) -> (offset, shape)
+        for i in range(n_hidden + 1):
+            name = f"layers.{i}.0" if i < n_hidden else "fc_out"
+            self._slot("img2text", name, KIND_MLP, 0, i)
+        for stack, prefix in ((STACK_IMAGE, "retrieval_fuse"), (STACK_TEXT, "text_condition")):
+            for l in range(n_layers):
+                for kind, nm in ((KIND_TO_Q, "to_q"), (KIND_TO_K, "to_k"), (KIND_TO_V, "to_v"), (KIND_TO_OUT, "to_out.0")):
+                    self._slot(prefix, f"cross_layers.{l}.{nm}", kind, stack, l)
+        self.load_state_dicts(img2text_sd, retrieval_fuse_sd, text_condition_sd)
+        self._bind()
+
+    @classmethod
+    def from_modules(cls, img2text, retrieval_fuse, text_condition, device: int = 0,
+                     dropout: Optional[float] = None) -> "TrainableNeighbourConsumer":
+        heads = int(retrieval_fuse.cross_layers[0].heads)
+        if dropout is None:  # IM2TEXT's own rate: layers[i] = Sequential(Linear, Dropout, ReLU)
+            dropout = float(img2text.layers[0][1].p)
+        return cls(img2text.state_dict(), retrieval_fuse.state_dict(), text_condition.state_dict(), heads=heads,
+                   device=device, dropout=dropout)
+
+    def _slot(self, prefix: str, name: str, kind: int, stack: int, layer: int) -> None:
+        wo, bo, r, c_ = C.c_int64(0), C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        _capi.check(self._lib.keds_consumer_param_offset(self._h, kind, stack, layer, C.byref(wo), C.byref(bo),
+                                                         C.byref(r), C.byref(c_)))
+        self._slots[(prefix, name + ".weight")] = (int(wo.value), (int(r.value), int(c_.value)))
+        self._slots[(prefix, name + ".bias")] = (int(bo.value), (int(r.value),))
+
+    def _bind(self) -> None:
+        torch.cuda.current_stream(self.flat.device).synchronize()
+        _capi.check(self._lib.keds_consumer_bind_params(self._h, self.flat.data_ptr()))
+        self._bound_ptr = self.flat.data_ptr()
+
+    def _view(self, t: torch.Tensor, prefix: str, name: str) -> torch.Tensor:
+        off, shape = self._slots[(prefix, name)]
+        return t[off:off + int(torch.Size(shape).numel())].view(shape)
+
+    def state_dicts(self, grads: bool = False):
+        """(img2text_sd, retrieval_fuse_sd, text_condition_sd): views of `flat` (or of `flat.grad`)
+        under the reference's parameter names."""
+        src = self.flat.grad if grads else self.flat.detach()
+        out = {"img2text": {}, "retrieval_fuse": {}, "text_condition": {}}
+        for (prefix, name) in self._slots:
+            out[prefix][name] = self._view(src, prefix, name)
+        return out["img2text"], out["retrieval_fuse"], out["text_condition"]
+
+    def load_state_dicts(self, img2text_sd, retrieval_fuse_sd, text_condition_sd) -> None:
+        with torch.no_grad():
+            for prefix, sd in (("img2text", img2text_sd), ("retrieval_fuse", retrieval_fuse_sd),
+                               ("text_condition", text_condition_sd)):
+                for (pf, name) in self._slots:
+                    if pf != prefix:
+                        continue
+                    if name not in sd:
+                        raise KeyError(f"{prefix}: parameter {name} missing")
+                    self._view(self.flat, prefix, name).copy_(torch.as_tensor(sd[name]).to(self.flat.device, torch.float32))
+
+    def forward(self, feature: torch.Tensor, image_index: GpuIndexFlat, text_index: GpuIndexFlat,
+                I_img: torch.Tensor, I_txt: torch.Tensor, perm: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if self.flat.data_ptr() != self._bound_ptr:   # the parameter was re-created (.to(), load): adopt the new storage
+            self._bind()
+        feature = feature.detach().to(device=self.flat.device, dtype=torch.float32).contiguous()
+        I_img, I_txt = I_img.contiguous(), I_txt.contiguous()
+        if I_img.shape != I_txt.shape or I_img.shape[0] != feature.shape[0] or feature.shape[1] != self.d_in:
+            raise ValueError("feature, I_img and I_txt disagree on B, k or d_in")
+        B, k = I_img.shape
+        if perm is not None:
+            perm = perm.to(device=feature.device, dtype=torch.int32).contiguous()
+        masks = None
+        if self.training and self.dropout > 0.0:
+            M = B * (1 + 2 * k)
+            keep = 1.0 - self.dropout
+            masks = [(torch.rand((M, self.d_mid), device=feature.device) < keep).to(torch.float32) / keep
+                     for _ in range(self.n_hidden)]
+        return _ConsumerFn.apply(self, feature, image_index, text_index, I_img, I_txt, perm, masks, self.flat)
+
+    def check(self) -> int:
+        n = C.c_int64(0)
+        _capi.check(self._lib.keds_consumer_check(self._h, _stream_ptr(self.device), C.byref(n)))
+        return int(n.value)
+
+    def debug_hidden(self, layer: int, rows: int) -> torch.Tensor:
+        """hidden activations [rows, d_mid] of IM2TEXT layer `layer` from the last forward (test hook)"""
+        out = torch.empty((rows, self.d_mid), dtype=torch.float32, device=self.flat.device)
+        _capi.check(self._lib.keds_consumer_debug_hidden(self._h, int(layer), out.data_ptr(), out.numel(),
+                                                         _stream_ptr(self.device)))
+        return out
+
+    def __del__(self) -> None:  # pragma: no cover
+        try:
+            if getattr(self, "_h", None) is not None and self._h:
+                self._lib.keds_consumer_free(self._h)
+                self._h = C.c_void_p()
         except Exception:
             pass

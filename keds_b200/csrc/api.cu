@@ -51,12 +51,25 @@ struct DevBuf {
   // Bumped whenever the buffer moves: a CUDA graph captured over a handle bakes these addresses in,
   // and its owner compares keds_index_generation() before every replay (RetrievalStep.run()).
   uint64_t* gen = nullptr;
+  bool borrowed = false;  // p points into memory owned by the caller (bound training parameters): never freed here
   void moved() {
     if (gen) ++*gen;
   }
+  // view of caller-owned memory (replaces whatever was held)
+  void borrow(void* ptr, size_t bytes) {
+    release();
+    p = ptr;
+    cap = bytes;
+    borrowed = true;
+  }
   // grow without keeping contents
   int ensure(size_t bytes) {
-    if (bytes <= cap) return 0;
+    if (bytes <= cap && !borrowed) return 0;
+    if (borrowed) {
+      p = nullptr;
+      cap = 0;
+      borrowed = false;
+    }
     if (p) cudaFree(p);
     p = nullptr;
     cap = 0;
@@ -78,12 +91,13 @@ struct DevBuf {
     return 0;
   }
   void release() {
-    if (p) {
+    if (p && !borrowed) {
       cudaFree(p);
       moved();
     }
     p = nullptr;
     cap = 0;
+    borrowed = false;
   }
   template <class T>
   T* as() const { return static_cast<T*>(p); }
@@ -1671,3 +1685,5 @@ int keds_label_hits(const int64_t* I, int64_t nq, int kmax, const int64_t* label
 #include "consumer_host.cuh"
 // keds_clip_loss_*: the contrastive loss over the gathered features
 #include "clip_loss_host.cuh"
+// keds_consumer_bind_params / _forward_train / _backward: the consumer while it is being trained
+#include "consumer_train_host.cuh"

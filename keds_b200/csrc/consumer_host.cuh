@@ -58,6 +58,19 @@ struct keds_consumer {
   bool debug = false;
   DevBuf tdump;
   int dbg_launch = 0;
+  // ---- training (consumer_train_host.cuh) ----
+  float* bound = nullptr;  // caller-owned flat parameter buffer (keds_consumer_bind_params)
+  LinearW mlpT[CONS_MAX_MLP + 1], wqT[2][CONS_MAX_LAYERS], woT[2][CONS_MAX_LAYERS], wkvT[2];  // W^T: the weight operand of dX = dY W
+  bool t_ready = false;
+  struct Train {
+    bool valid = false;
+    int64_t B = 0;
+    int k = 0;
+    const float* masks[CONS_MAX_MLP] = {nullptr};
+    DevBuf h[CONS_MAX_MLP];                                              // hidden activations [M][d_mid]
+    DevBuf q[CONS_MAX_LAYERS], o[CONS_MAX_LAYERS], qin[CONS_MAX_LAYERS];  // per layer, both stacks side by side
+    DevBuf dq[2], dO, dQ, dkv, dy, dh[2], ta, tb, dtok;                   // backward scratch
+  } tr;
 };
 constexpr int CONS_DBG_LAUNCHES = 32;
 constexpr int CONS_DBG_CTAS = 1024;
@@ -226,6 +239,23 @@ void keds_consumer_free(keds_consumer_t* c) {
   }
   for (DevBuf* b : {&c->xin, &c->hid[0], &c->hid[1], &c->xm, &c->kv, &c->qb, &c->ob, &c->qn[0], &c->qn[1], &c->err, &c->tdump})
     b->release();
+  for (auto& l : c->mlpT) l.w.release();
+  for (int z = 0; z < 2; ++z) {
+    for (int l = 0; l < CONS_MAX_LAYERS; ++l) {
+      c->wqT[z][l].w.release();
+      c->woT[z][l].w.release();
+    }
+    c->wkvT[z].w.release();
+  }
+  for (int i = 0; i < CONS_MAX_MLP; ++i) c->tr.h[i].release();
+  for (int l = 0; l < CONS_MAX_LAYERS; ++l) {
+    c->tr.q[l].release();
+    c->tr.o[l].release();
+    c->tr.qin[l].release();
+  }
+  for (DevBuf* b : {&c->tr.dq[0], &c->tr.dq[1], &c->tr.dO, &c->tr.dQ, &c->tr.dkv, &c->tr.dy, &c->tr.dh[0], &c->tr.dh[1],
+                    &c->tr.ta, &c->tr.tb, &c->tr.dtok})
+    b->release();
   delete c;
 }
 
@@ -242,8 +272,10 @@ int keds_consumer_set_linear(keds_consumer_t* c, int kind, int stack, int layer,
   DeviceGuard g(c->device);
   if (!g.ok) return fail(KEDS_ERR_CUDA, "cudaSetDevice(%d) failed", c->device);
   const size_t wb = static_cast<size_t>(eo) * ei * 4;
-  CKS(s->w.ensure(wb));
-  CKS(s->b.ensure(static_cast<size_t>(eo) * 4));
+  if (!s->w.borrowed) {  // (bound parameters: the values go into the caller's flat buffer)
+    CKS(s->w.ensure(wb));
+    CKS(s->b.ensure(static_cast<size_t>(eo) * 4));
+  }
   CK(cudaMemcpy(s->w.p, W, wb, cudaMemcpyDefault));
   if (b) CK(cudaMemcpy(s->b.p, b, static_cast<size_t>(eo) * 4, cudaMemcpyDefault));
   else CK(cudaMemset(s->b.p, 0, static_cast<size_t>(eo) * 4));
@@ -285,9 +317,11 @@ int keds_consumer_finalize(keds_consumer_t* c) {
     LinearW& kv = c->wkv[z];
     kv.out = c->n_layers * 2 * c->inner;
     kv.in = c->d_tok;
-    CKS(kv.w.ensure(static_cast<size_t>(kv.out) * kv.in * 4));
-    CKS(kv.b.ensure(static_cast<size_t>(kv.out) * 4));
-    for (int l = 0; l < c->n_layers; ++l) {
+    if (c->bound == nullptr) {  // (bound parameters already live stacked in the caller's buffer)
+      CKS(kv.w.ensure(static_cast<size_t>(kv.out) * kv.in * 4));
+      CKS(kv.b.ensure(static_cast<size_t>(kv.out) * 4));
+    }
+    for (int l = 0; l < c->n_layers && c->bound == nullptr; ++l) {
       CK(cudaMemcpy(kv.w.as<float>() + (2 * l) * wl, c->wk[z][l].w.p, wl * 4, cudaMemcpyDeviceToDevice));
       CK(cudaMemcpy(kv.w.as<float>() + (2 * l + 1) * wl, c->wv[z][l].w.p, wl * 4, cudaMemcpyDeviceToDevice));
       CK(cudaMemcpy(kv.b.as<float>() + (2 * l) * c->inner, c->wk[z][l].b.p, c->inner * 4, cudaMemcpyDeviceToDevice));
@@ -312,9 +346,17 @@ int keds_consumer_finalize(keds_consumer_t* c) {
   return 0;
 }
 
-int keds_consumer_forward(keds_consumer_t* c, const float* q, const float* base_img, int64_t n_img,
+}  // extern "C"
+
+namespace {
+
+// The forward pass. train = false: eval (dropout is the identity), scratch reused across layers.
+// train = true: hidden activations, per-layer queries / attention outputs and layer inputs are
+// kept for keds_consumer_backward; masks[i] (nullable) is hidden layer i's dropout multiplier.
+int consumer_forward_impl(keds_consumer_t* c, const float* q, const float* base_img, int64_t n_img,
                           const float* base_txt, int64_t n_txt, const int64_t* I_img, const int64_t* I_txt,
-                          const int32_t* perm, int64_t B, int k, float* tokens, void* stream) {
+                          const int32_t* perm, int64_t B, int k, float* tokens, void* stream, bool train,
+                          const float* const* masks) {
   if (!c || !q || !base_img || !base_txt || !I_img || !I_txt || !tokens)
     return fail(KEDS_ERR_ARG, "consumer_forward: NULL argument");
   if (!c->finalized) return fail(KEDS_ERR_ARG, "consumer_forward: call keds_consumer_finalize first");
@@ -333,8 +375,23 @@ int keds_consumer_forward(keds_consumer_t* c, const float* q, const float* base_
   const int L = c->n_layers, inner = c->inner, dt = c->d_tok;
   const int64_t kvw = static_cast<int64_t>(L) * 2 * inner;
   CKS(c->xin.ensure(static_cast<size_t>(M) * c->d_in * 4));
-  CKS(c->hid[0].ensure(static_cast<size_t>(M) * c->d_mid * 4));
-  CKS(c->hid[1].ensure(static_cast<size_t>(M) * c->d_mid * 4));
+  if (train) {
+    c->tr.valid = false;
+    for (int i = 0; i < c->n_hidden; ++i) {
+      CKS(c->tr.h[i].ensure(static_cast<size_t>(M) * c->d_mid * 4));
+      c->tr.masks[i] = masks ? masks[i] : nullptr;
+      if (c->tr.masks[i] && !is_device_ptr(c->tr.masks[i]))
+        return fail(KEDS_ERR_ARG, "consumer_forward_train: dropout masks must be device memory");
+    }
+    for (int l = 0; l < L; ++l) {
+      CKS(c->tr.q[l].ensure(static_cast<size_t>(2) * B * inner * 4));
+      CKS(c->tr.o[l].ensure(static_cast<size_t>(2) * B * inner * 4));
+      if (l > 0) CKS(c->tr.qin[l].ensure(static_cast<size_t>(2) * B * dt * 4));
+    }
+  } else {
+    CKS(c->hid[0].ensure(static_cast<size_t>(M) * c->d_mid * 4));
+    CKS(c->hid[1].ensure(static_cast<size_t>(M) * c->d_mid * 4));
+  }
   CKS(c->xm.ensure(static_cast<size_t>(M) * dt * 4));
   CKS(c->kv.ensure(static_cast<size_t>(2) * Bk * kvw * 4));
   CKS(c->qb.ensure(static_cast<size_t>(2) * B * inner * 4));
@@ -365,8 +422,14 @@ int keds_consumer_forward(keds_consumer_t* c, const float* q, const float* base_
   const float* cur = xin;
   int cur_w = c->d_in;
   for (int i = 0; i < c->n_hidden; ++i) {
-    float* h = c->hid[i & 1].as<float>();
-    CKS(consumer_linear(c, cur, nullptr, cur_w, M, &c->mlp[i], nullptr, 1, h, nullptr, c->d_mid, 1, st));
+    float* h = train ? c->tr.h[i].as<float>() : c->hid[i & 1].as<float>();
+    const float* mask = train ? c->tr.masks[i] : nullptr;
+    CKS(consumer_linear(c, cur, nullptr, cur_w, M, &c->mlp[i], nullptr, mask ? 0 : 1, h, nullptr, c->d_mid, 1, st));
+    if (mask) {  // Linear -> Dropout -> ReLU (src/model/model.py:110-116)
+      const long long n = static_cast<long long>(M) * c->d_mid;
+      CKS(launch_k(true, k_mask_relu, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, st, h, mask, n));
+      c->launches++;
+    }
     cur = h;
     cur_w = c->d_mid;
   }
@@ -387,6 +450,12 @@ int keds_consumer_forward(keds_consumer_t* c, const float* q, const float* base_
   const float* qc1 = xm;
   int64_t ldq = dt;
   for (int l = 0; l < L; ++l) {
+    if (train) {  // every layer keeps its own query and attention output for the backward
+      qb0 = c->tr.q[l].as<float>();
+      qb1 = qb0 + B * inner;
+      ob0 = c->tr.o[l].as<float>();
+      ob1 = ob0 + B * inner;
+    }
     CKS(consumer_linear(c, qc0, qc1, ldq, B, &c->wq[0][l], &c->wq[1][l], 0, qb0, qb1, inner, 2, st));
     AttendParams ap;
     memset(&ap, 0, sizeof ap);
@@ -416,7 +485,7 @@ int keds_consumer_forward(keds_consumer_t* c, const float* q, const float* base_
       o1 = tokens + dt;
       ldo = 3 * static_cast<int64_t>(dt);
     } else {
-      o0 = c->qn[l & 1].as<float>();
+      o0 = train ? c->tr.qin[l + 1].as<float>() : c->qn[l & 1].as<float>();
       o1 = o0 + B * dt;
       ldo = dt;
     }
@@ -428,7 +497,23 @@ int keds_consumer_forward(keds_consumer_t* c, const float* q, const float* base_
   // tokens[:, 2, :] = img2text(query features)
   CK(cudaMemcpy2DAsync(tokens + 2 * dt, static_cast<size_t>(3) * dt * 4, xm, static_cast<size_t>(dt) * 4,
                        static_cast<size_t>(dt) * 4, static_cast<size_t>(B), cudaMemcpyDeviceToDevice, st));
+  if (train) {
+    c->tr.B = B;
+    c->tr.k = k;
+    c->tr.valid = true;
+  }
   return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int keds_consumer_forward(keds_consumer_t* c, const float* q, const float* base_img, int64_t n_img,
+                          const float* base_txt, int64_t n_txt, const int64_t* I_img, const int64_t* I_txt,
+                          const int32_t* perm, int64_t B, int k, float* tokens, void* stream) {
+  return consumer_forward_impl(c, q, base_img, n_img, base_txt, n_txt, I_img, I_txt, perm, B, k, tokens, stream, false,
+                               nullptr);
 }
 
 int keds_consumer_set_debug(keds_consumer_t* c, int enable) {

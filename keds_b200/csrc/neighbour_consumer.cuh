@@ -690,4 +690,146 @@ __global__ void k_cross_attend(const AttendParams p) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Training: the backward pass of the same modules (src/trainer.py:59-69 with the modules being
+// optimised, backward at :462-474). The products are the same tf32 tcgen05 GEMMs with the operand
+// roles turned (dX = dY W, dW = dY^T X); these kernels are what lies between them.
+
+// Linear -> Dropout -> ReLU of IM2TEXT (src/model/model.py:110-116) behind the GEMM, in place:
+// h = max(z * mask, 0), mask = 0 or 1 / (1 - p) per element (drawn by the caller).
+__global__ void k_mask_relu(float* __restrict__ z, const float* __restrict__ mask, long long n) {
+  griddep_wait();
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) z[i] = fmaxf(z[i] * mask[i], 0.f);
+}
+
+// dz = dh * [h > 0] * mask   (mask nullable: no dropout)
+__global__ void k_relu_bwd(const float* dh, const float* __restrict__ h, const float* __restrict__ mask, float* dz,
+                           long long n) {  // dz may alias dh
+  griddep_wait();
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) dz[i] = h[i] > 0.f ? dh[i] * (mask != nullptr ? mask[i] : 1.f) : 0.f;
+}
+
+// Bias gradient: out[c] = sum_r in[r][c]. One block per 32 columns (32 x 8 threads), rows summed in
+// a fixed order: deterministic.
+__global__ void __launch_bounds__(256)
+k_colsum(const float* __restrict__ in, long long ld, long long rows, int cols, float* __restrict__ out) {
+  griddep_wait();
+  __shared__ float part[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  float acc = 0.f;
+  if (c < cols)
+    for (long long r = ry; r < rows; r += 8) acc += in[r * ld + c];
+  part[ry][cx] = acc;
+  __syncthreads();
+  if (ry == 0 && c < cols) {
+    float t = part[0][cx];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) t += part[i][cx];
+    out[c] = t;
+  }
+}
+
+// out[r][:] = a[r][:] + b[r][:] + c[r][:] over `cols` columns (row strides lda / ldb / ldc / ldo)
+__global__ void k_add3_rows(const float* __restrict__ a, long long lda, const float* __restrict__ b, long long ldb,
+                            const float* __restrict__ c, long long ldc, float* __restrict__ out, long long ldo,
+                            long long rows, int cols) {
+  griddep_wait();
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  const long long r = i / cols;
+  const int x = static_cast<int>(i % cols);
+  out[r * ldo + x] = a[r * lda + x] + b[r * ldb + x] + c[r * ldc + x];
+}
+
+// Backward of k_cross_attend for one query token: with s_j = scale q.k_j, p = softmax(s),
+// o = sum_j p_j v_j and the incoming dO:
+//   dv_j = p_j dO,  dp_j = dO.v_j,  ds_j = p_j (dp_j - sum_i p_i dp_i),
+//   dq = scale sum_j ds_j k_j,  dk_j = scale ds_j q.
+// The probabilities are recomputed from Q and K (nothing is kept from the forward but Q).
+// grid (B, problems), one warp per head, dynamic smem = heads * (2 dim_head + 2 k) floats.
+struct AttendBwdParams {
+  int B, k, heads, dim_head;
+  const float* Q[2];     // [B][inner]
+  const float* KV[2];    // [B * k][ld_kv]
+  const float* dO[2];    // [B][inner]
+  float* dQ[2];          // [B][inner]
+  float* dKV[2];         // [B * k][ld_kv]: dK at k_off, dV at v_off of this layer
+  long long ld_kv;
+  int k_off, v_off;
+  float scale;
+};
+
+__global__ void k_cross_attend_bwd(const AttendBwdParams p) {
+  extern __shared__ float atb_sm[];
+  griddep_wait();
+  const int b = blockIdx.x, z = blockIdx.y;
+  const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int dh = p.dim_head, inner = p.heads * dh;
+  float* qs = atb_sm + h * (2 * dh + 2 * p.k);
+  float* gs = qs + dh;          // dO of this head
+  float* pr = gs + dh;          // scores -> probabilities
+  float* ds = pr + p.k;         // dp -> ds
+  const float* q = p.Q[z] + static_cast<long long>(b) * inner + h * dh;
+  const float* go = p.dO[z] + static_cast<long long>(b) * inner + h * dh;
+  const long long row0 = static_cast<long long>(b) * p.k;
+  const float* kv = p.KV[z] + row0 * p.ld_kv + h * dh;
+  float* dkv = p.dKV[z] + row0 * p.ld_kv + h * dh;
+  for (int d = lane; d < dh; d += 32) {
+    qs[d] = q[d];
+    gs[d] = go[d];
+  }
+  __syncwarp();
+  float mx = -INFINITY;
+  for (int j = lane; j < p.k; j += 32) {
+    const float* kr = kv + j * p.ld_kv + p.k_off;
+    const float* vr = kv + j * p.ld_kv + p.v_off;
+    float s = 0.f, dp = 0.f;
+    for (int d = 0; d < dh; ++d) {
+      s = fmaf(__ldg(kr + d), qs[d], s);
+      dp = fmaf(__ldg(vr + d), gs[d], dp);
+    }
+    s *= p.scale;
+    pr[j] = s;
+    ds[j] = dp;
+    mx = fmaxf(mx, s);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float den = 0.f;
+  for (int j = lane; j < p.k; j += 32) {
+    const float e = expf(pr[j] - mx);
+    pr[j] = e;
+    den += e;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) den += __shfl_xor_sync(0xffffffffu, den, o);
+  const float inv = 1.f / den;
+  float dot = 0.f;
+  for (int j = lane; j < p.k; j += 32) {
+    const float pj = pr[j] * inv;
+    pr[j] = pj;
+    dot = fmaf(pj, ds[j], dot);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+  for (int j = lane; j < p.k; j += 32) ds[j] = pr[j] * (ds[j] - dot);
+  __syncwarp();
+  // one lane per column: coalesced over the key / value rows
+  float* dq = p.dQ[z] + static_cast<long long>(b) * inner + h * dh;
+  for (int d = lane; d < dh; d += 32) {
+    float acc = 0.f;
+    const float qd = qs[d], gd = gs[d];
+    for (int j = 0; j < p.k; ++j) {
+      const float dsj = ds[j];
+      acc = fmaf(dsj, __ldg(kv + j * p.ld_kv + p.k_off + d), acc);
+      dkv[j * p.ld_kv + p.k_off + d] = p.scale * dsj * qd;
+      dkv[j * p.ld_kv + p.v_off + d] = pr[j] * gd;
+    }
+    dq[d] = p.scale * acc;
+  }
+}
+
 }  // namespace keds

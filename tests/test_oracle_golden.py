@@ -146,3 +146,28 @@ def test_cirr_testoutput_matches_reference(golden_dir):
     assert got == e["output"]
     with pytest.raises(IndexError):   # fewer than 51 gallery images: the reference's [t] for t < 50 runs out
         orc.cirr_testoutput(z["gal"][:40], z["qf"][:3], e["index_names"][:3], e["index_names"][:40], [1, 2, 3])
+
+
+def test_consumer_training_oracle_matches_reference_modules(golden_dir):
+    """oracle/consumer_train_oracle.py against tokens and parameter gradients computed by the
+    reference's own IM2TEXT / CrossFormer classes in train mode (oracle/make_golden_consumer_train.py)."""
+    from oracle import consumer_train_oracle as cto
+    g = np.load(os.path.join(golden_dir, "consumer_train.npz"))
+    sds = [{k.split("/", 1)[1]: g[k] for k in g.files if k.startswith(p + "/")}
+           for p in ("img2text", "retrieval_fuse", "text_condition")]
+    tok, grads = cto.tokens_and_grads(sds[0], sds[1], sds[2], int(g["dims"][5]), g["feat"], g["topk_image"],
+                                      g["topk_text"], g["dtokens"])
+    assert np.abs(tok - g["tokens"]).max() < 1e-12
+    assert len(grads) == 54
+    for name, v in grads.items():
+        assert np.abs(v - g["grad/" + name]).max() < 1e-12, name
+    # a dropout mask of ones is no dropout; a mask of zeros on a hidden layer kills that layer's weight gradient
+    M = g["feat"].shape[0] * (1 + 2 * g["topk_image"].shape[1])
+    ones = [np.ones((M, int(g["dims"][1]))), None]
+    tok1, grads1 = cto.tokens_and_grads(sds[0], sds[1], sds[2], int(g["dims"][5]), g["feat"], g["topk_image"],
+                                        g["topk_text"], g["dtokens"], ones)
+    assert np.abs(tok1 - tok).max() < 1e-12
+    zeros = [np.zeros((M, int(g["dims"][1]))), None]
+    _, grads0 = cto.tokens_and_grads(sds[0], sds[1], sds[2], int(g["dims"][5]), g["feat"], g["topk_image"],
+                                     g["topk_text"], g["dtokens"], zeros)
+    assert np.abs(grads0["img2text/layers.0.0.weight"]).max() == 0.0
