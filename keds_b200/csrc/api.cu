@@ -230,7 +230,6 @@ struct keds_index {
   // per-call scratch (one search in flight per handle)
   DevBuf q_f32, q_bf16, qstat, cand, cand_cnt, cand_theta, flagged[2], ctrl, exact_scratch, rk, theta0;
   bool warm_start = true;  // lists start at a finished list's threshold (KEDS_NO_WARM_START=1: every list cold)
-  bool split_q = false;    // single-CTA scoring kernel with separate row / query rings (KEDS_SPLIT_Q=0|1)
   DevBuf D_stage[2], I_stage[2];
   HostBuf h_q, h_out;  // pinned staging for host-pointer calls
   CUtensorMap tm_q;
@@ -263,11 +262,7 @@ int set_kernel_attrs(keds_index* ix) {
                           (int)SCORE_PAIR_SMEM_BYTES));
   CK(cudaFuncSetAttribute(k_score_topk<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)SCORE_SMEM_BYTES));
-  CK(cudaFuncSetAttribute(k_score_topk<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                          (int)SCORE_SMEM_BYTES));
-  CK(cudaFuncSetAttribute(k_score_topk<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                          (int)SCORE_SMEM_BYTES));
-  if (const char* sq = getenv("KEDS_SPLIT_Q")) ix->split_q = sq[0] == '1';
+
   CK(cudaFuncSetAttribute(k_score_topk<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)SCORE_PAIR_SMEM_BYTES));
   const char* no_pair = getenv("KEDS_NO_PAIR");
@@ -605,9 +600,6 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
     if (pl.pair)
       CKS(launch_kc(a->use_pdl, 2, k_score_topk<true>, dim3(pl.grid), dim3(SCORE_PAIR_THREADS), SCORE_PAIR_SMEM_BYTES,
                     st, a->tm_q, ix[0]->tm_xh, n_db > 1 ? ix[1]->tm_xh : ix[0]->tm_xh, sp));
-    else if (a->split_q)
-      CKS(launch_k(a->use_pdl, k_score_topk<false, false, true>, dim3(pl.grid), dim3(SCORE_SPLITQ_THREADS),
-                   SCORE_SMEM_BYTES, st, a->tm_q, ix[0]->tm_x, n_db > 1 ? ix[1]->tm_x : ix[0]->tm_x, sp));
     else
       CKS(launch_k(a->use_pdl, k_score_topk<false>, dim3(pl.grid), dim3(SCORE_THREADS), SCORE_SMEM_BYTES, st,
                    a->tm_q, ix[0]->tm_x, n_db > 1 ? ix[1]->tm_x : ix[0]->tm_x, sp));
@@ -1623,9 +1615,6 @@ int keds_index_rank(keds_index_t* ix, const float* q, int64_t nq, const int64_t*
     if (pair)
       CKS(launch_kc(ix->use_pdl, 2, k_score_topk<true, true>, dim3(grid), dim3(SCORE_PAIR_THREADS), SCORE_PAIR_SMEM_BYTES,
                     st, ix->tm_q, ix->tm_xh, ix->tm_xh, sp));
-    else if (ix->split_q)
-      CKS(launch_k(ix->use_pdl, k_score_topk<false, true, true>, dim3(grid), dim3(SCORE_SPLITQ_THREADS), SCORE_SMEM_BYTES,
-                   st, ix->tm_q, ix->tm_x, ix->tm_x, sp));
     else
       CKS(launch_k(ix->use_pdl, k_score_topk<false, true>, dim3(grid), dim3(SCORE_THREADS), SCORE_SMEM_BYTES, st,
                    ix->tm_q, ix->tm_x, ix->tm_x, sp));

@@ -44,39 +44,31 @@ constexpr int SCORE_PAIR_THREADS = 320;  // CTA-pair variant: 8 epilogue warps
 constexpr uint32_t Q_STAGE_BYTES = BM * BK * 2;
 constexpr uint32_t TMEM_COLS = 512;
 
-template <bool kPair, bool kSplitQ = false>
+template <bool kPair>
 struct ScoreCfg {
-  static_assert(!(kPair && kSplitQ), "the split query ring belongs to the single-CTA variant");
   // Single CTA (HBM-bound, one query tile): the kernel lives on bytes in flight, so the candidate
-  // slots are cut to 32 per query (32 KB, checked every 8 scores) in favour of staging memory.
-  //   kSplitQ = false: four 48-KB stages, each holding a query k-block and a row k-block.
-  //   kSplitQ = true:  the two operands get rings of their own -- FIVE 32-KB row stages (a quarter
-  //                    more database bytes in flight: what the kernel's time follows when the power
-  //                    cap pulls the SM clock, and with it every latency, down) and two 16-KB query
-  //                    buffers refilled from L2 by a producer warp of their own. Same 227 KB.
+  // slots are cut to 32 per query (32 KB) to make room for a fourth 48-KB stage; the slot count
+  // is then checked every 8 scores. CTA pair (compute-bound): 64 slots, checked every 32 scores --
+  // compactions are what its epilogue can least afford.
   // CTA pair (compute-bound): 8 epilogue warps of 32 slots each (the same 64 KB as 4 x 64 before)
   // and, with 32-KB stages, room for a fifth stage.
-  static constexpr int kStages = (kPair || kSplitQ) ? 5 : 4;
-  static constexpr int kQBufs = kSplitQ ? 2 : 0;
+  static constexpr int kStages = kPair ? 5 : 4;
   static constexpr int kEpiWarps = kPair ? 8 : 4;
   static constexpr int kSub = kEpiWarps / 4;                        // candidate lists ("sub-slices") per (slice, query)
-  static constexpr int kThreads = 64 + 32 * kEpiWarps + (kSplitQ ? 32 : 0);
+  static constexpr int kThreads = 64 + 32 * kEpiWarps;
   static constexpr int kCap = 32;
   static constexpr int kAppend = 8;
   static constexpr uint32_t kCandWarpBytes = kCap * 32 * 8;
   static constexpr int kRowsPerCta = kPair ? BN / 2 : BN;           // row-tile rows this CTA loads
   static constexpr uint32_t kXBytes = kRowsPerCta * BK * 2;
-  static constexpr uint32_t kStageBytes = (kSplitQ ? 0u : Q_STAGE_BYTES) + kXBytes;  // 48 KB / 32 KB
+  static constexpr uint32_t kStageBytes = Q_STAGE_BYTES + kXBytes;  // 48 KB / 32 KB
   // dynamic shared memory map (offsets from a 1024-aligned base)
-  static constexpr uint32_t kOffQ = kStages * kStageBytes;          // query buffers (kSplitQ only)
-  static constexpr uint32_t kOffCand = kOffQ + kQBufs * Q_STAGE_BYTES;
+  static constexpr uint32_t kOffCand = kStages * kStageBytes;
   static constexpr uint32_t kOffBias = kOffCand + kEpiWarps * kCandWarpBytes;
   static constexpr uint32_t kOffBars = kOffBias + 2 * BN * 4;
-  static constexpr uint32_t kSmemBytes = kOffBars + 256 + 768;      // barriers + alignment slack (227 KB exactly)
+  static constexpr uint32_t kSmemBytes = kOffBars + 256 + 768;      // barriers + alignment slack (227 KB exactly for the single-CTA variant)
 };
 constexpr uint32_t SCORE_SMEM_BYTES = ScoreCfg<false>::kSmemBytes;
-static_assert(ScoreCfg<false, true>::kSmemBytes == ScoreCfg<false>::kSmemBytes, "both single-CTA layouts fill the same 227 KB");
-constexpr int SCORE_SPLITQ_THREADS = ScoreCfg<false, true>::kThreads;
 constexpr uint32_t SCORE_PAIR_SMEM_BYTES = ScoreCfg<true>::kSmemBytes;
 
 struct ScoreParams {
@@ -199,11 +191,11 @@ __device__ __noinline__ CandState compact_candidates(uint32_t slot0, int cnt, fl
 //                overflow mark and the query is recounted exactly). The target and the excluded row
 //                are skipped by id. Output: the same 128-byte lines (band rows), cand_cnt = band
 //                rows or -1 (overflow), cand_theta = the certain count (as int bits).
-template <bool kPair, bool kRank = false, bool kSplitQ = false>
-__global__ void __launch_bounds__(ScoreCfg<kPair, kSplitQ>::kThreads, 1)
+template <bool kPair, bool kRank = false>
+__global__ void __launch_bounds__(ScoreCfg<kPair>::kThreads, 1)
 k_score_topk(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_x0,
              const __grid_constant__ CUtensorMap tm_x1, const ScoreParams p) {
-  using Cfg = ScoreCfg<kPair, kSplitQ>;
+  using Cfg = ScoreCfg<kPair>;
   constexpr int NSTAGE = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -224,8 +216,6 @@ k_score_topk(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
   auto empty_bar = [&](int s) { return bars + 8u * (NSTAGE + s); };
   auto tfull_bar = [&](int a) { return bars + 8u * (2 * NSTAGE + a); };
   auto tempty_bar = [&](int a) { return bars + 8u * (2 * NSTAGE + 2 + a); };
-  auto qfull_bar = [&](int b) { return bars + 8u * (2 * NSTAGE + 4 + b); };    // kSplitQ: the query ring's own pair
-  auto qempty_bar = [&](int b) { return bars + 8u * (2 * NSTAGE + 6 + b); };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + Cfg::kOffBars + 200);
   volatile uint32_t* dead = reinterpret_cast<volatile uint32_t*>(gbase + Cfg::kOffBars + 204);
 
@@ -246,12 +236,6 @@ k_score_topk(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), kPair ? 2 * Cfg::kEpiWarps : Cfg::kEpiWarps);  // pair: the leader collects both CTAs' epilogue warps
-    }
-    if constexpr (kSplitQ) {
-      for (int b = 0; b < Cfg::kQBufs; ++b) {
-        mbar_init(qfull_bar(b), 1);
-        mbar_init(qempty_bar(b), 1);
-      }
     }
     *dead = 0;
     fence_mbar_init();
@@ -274,7 +258,7 @@ k_score_topk(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
   // synchronises the device): the producer sends the row half of its first stages now, under
   // k_prep_rows, and the query half once the wait below has passed.
   int pre_rows = 0;
-  if constexpr (!kPair && !kSplitQ) {
+  if constexpr (!kPair) {
     if (warp == 0 && lane == 0 && unit < p.n_items) {
       const ItemCoord c = decode_item(p, unit);
       if (c.t0 < c.t1) {
@@ -292,59 +276,11 @@ k_score_topk(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
   // Programmatic dependent launch: everything above overlapped the tail of the previous kernel
   // (k_prep_rows); from here on its outputs (bf16 queries) are needed. Let the next kernel
   // (k_select_rerank) be scheduled as soon as SMs free up.
-  // kSplitQ: warp 6 streams database rows only -- nothing it touches depends on the previous kernel
-  // (rows change in add() alone, which synchronises the device), so it never waits: by the time
-  // the queries are ready its whole ring is in flight.
-  const bool row_warp = kSplitQ && warp == 6;
-  if (!row_warp) {
-    griddep_wait();
-    griddep_launch_dependents();
-  }
+  griddep_wait();
+  griddep_launch_dependents();
   const unsigned long long t_start = ktimer_begin(p.timing);
 
-  if (row_warp) {
-    // ------------------------------------------------------------ TMA producer: database rows (kSplitQ)
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int item = unit; item < p.n_items; item += n_units) {
-        const ItemCoord c = decode_item(p, item);
-        const CUtensorMap* tmx = c.db == 0 ? &tm_x0 : &tm_x1;
-        for (int tile = c.t0; tile < c.t1; ++tile) {
-          for (int kb = 0; kb < p.kblocks; ++kb) {
-            mbar_wait(empty_bar(stage), phase ^ 1u, dead, p.err, 0x100u + stage);
-            mbar_arrive_expect_tx(full_bar(stage), Cfg::kXBytes);
-            tma_load_2d(sbase + stage * Cfg::kStageBytes, tmx, full_bar(stage), kb * BK, tile * BN,
-                        p.n_qt > 1 ? kEvictNormal : kEvictFirst);
-            if (++stage == NSTAGE) {
-              stage = 0;
-              phase ^= 1u;
-            }
-          }
-        }
-      }
-    }
-  } else if (kSplitQ && warp == 0) {
-    // ------------------------------------------------------------ TMA producer: query k-blocks (kSplitQ)
-    if (lane == 0) {
-      int qb = 0;
-      uint32_t qphase = 0;
-      for (int item = unit; item < p.n_items; item += n_units) {
-        const ItemCoord c = decode_item(p, item);
-        for (int tile = c.t0; tile < c.t1; ++tile) {
-          for (int kb = 0; kb < p.kblocks; ++kb) {
-            mbar_wait(qempty_bar(qb), qphase ^ 1u, dead, p.err, 0x140u + qb);
-            mbar_arrive_expect_tx(qfull_bar(qb), Q_STAGE_BYTES);
-            tma_load_2d(sbase + Cfg::kOffQ + qb * Q_STAGE_BYTES, &tm_q, qfull_bar(qb), kb * BK, c.qg * BM, kEvictLast);
-            if (++qb == Cfg::kQBufs) {
-              qb = 0;
-              qphase ^= 1u;
-            }
-          }
-        }
-      }
-    }
-  } else if (warp == 0) {
+  if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0;
@@ -388,8 +324,6 @@ k_score_topk(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
       const uint32_t idesc = idesc_f16_base(kPair ? 2 * BM : BM, BN) | p.fmt_bits;
       int stage = 0;
       uint32_t phase = 0;
-      [[maybe_unused]] int qb = 0;
-      [[maybe_unused]] uint32_t qphase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int item = unit; item < p.n_items; item += n_units) {
@@ -400,16 +334,10 @@ k_score_topk(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
           const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
           for (int kb = 0; kb < p.kblocks; ++kb) {
             mbar_wait(full_bar(stage), phase, dead, p.err, 0x300u + stage);
-            uint32_t sq = sbase + stage * Cfg::kStageBytes;   // query k-block (combined stage: in front of the rows)
-            uint32_t sx = sq + Q_STAGE_BYTES;
-            if constexpr (kSplitQ) {
-              mbar_wait(qfull_bar(qb), qphase, dead, p.err, 0x340u + qb);
-              sx = sq;
-              sq = sbase + Cfg::kOffQ + qb * Q_STAGE_BYTES;
-            }
             tc_fence_after();
+            const uint32_t sq = sbase + stage * Cfg::kStageBytes;
             const uint64_t adesc = smem_desc_sw128(sq);
-            const uint64_t bdesc = smem_desc_sw128(sx);
+            const uint64_t bdesc = smem_desc_sw128(sq + Q_STAGE_BYTES);
 #pragma unroll
             for (int k = 0; k < BK / UK; ++k) {
               // +32 bytes per K=16 step inside the 128-byte swizzle row: +2 in 16-byte units
@@ -419,13 +347,6 @@ k_score_topk(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
                 umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
             }
             if constexpr (kPair) umma_commit_2sm(empty_bar(stage), 0x3); else umma_commit(empty_bar(stage));
-            if constexpr (kSplitQ) {
-              umma_commit(qempty_bar(qb));
-              if (++qb == Cfg::kQBufs) {
-                qb = 0;
-                qphase ^= 1u;
-              }
-            }
             if (++stage == NSTAGE) {
               stage = 0;
               phase ^= 1u;
