@@ -642,7 +642,8 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
     // query that does not fit is answered by the exact fallback and raises the next call's figure).
     int rmax = R_MAX;
     if (!small_batch) {
-      const unsigned int want = std::max<unsigned int>(static_cast<unsigned int>(4 * k), band_hint + band_hint / 2);
+      const unsigned int want =
+          std::max<unsigned int>(static_cast<unsigned int>(k + k / 2 + 64), band_hint + band_hint / 2);
       rmax = 256;
       while (rmax < static_cast<int>(std::min<unsigned int>(want, R_MAX))) rmax *= 2;
     }

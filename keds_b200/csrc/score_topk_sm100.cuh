@@ -50,9 +50,10 @@ struct ScoreCfg {
   // slots are cut to 32 per query (32 KB) to make room for a fourth 48-KB stage; the slot count
   // is then checked every 8 scores. CTA pair (compute-bound): 64 slots, checked every 32 scores --
   // compactions are what its epilogue can least afford.
-  // CTA pair (compute-bound): 8 epilogue warps of 32 slots each (the same 64 KB as 4 x 64 before)
-  // and, with 32-KB stages, room for a fifth stage.
-  static constexpr int kStages = kPair ? 5 : 4;
+  // CTA pair (compute-bound): 8 epilogue warps of 32 slots each (the same 64 KB as 4 x 64 before).
+  // Four 32-KB stages: 195 KB, which leaves an SM room for re-rank blocks of another sub-pass next
+  // to a scoring CTA (api.cu: pipelined sub-passes); a fifth stage measured no faster.
+  static constexpr int kStages = 4;
   static constexpr int kEpiWarps = kPair ? 8 : 4;
   static constexpr int kSub = kEpiWarps / 4;                        // candidate lists ("sub-slices") per (slice, query)
   static constexpr int kThreads = 64 + 32 * kEpiWarps;
