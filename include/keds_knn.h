@@ -47,6 +47,8 @@ typedef struct keds_search_stats {
   int32_t exact_only;    /* 1 if the planner chose the fp32 scan for the whole batch */
   int32_t launches;      /* kernels launched by the last search call */
   uint32_t err_word;     /* device watchdog word, 0 = clean */
+  int32_t streamed;      /* 0: every re-rank block waited for the whole scoring grid; W > 0: the re-rank
+                            was streamed behind waves of W query groups (256 queries each) */
 } keds_search_stats;
 
 /* ---- index lifecycle ------------------------------------------------------------------------
@@ -332,6 +334,10 @@ int keds_debug_plan(int n_db, int64_t nq, int k, int64_t n_rows, int num_sms, in
 /* Programmatic dependent launch between the kernels of a search (default on; env KEDS_NO_PDL=1
  * turns the default off). Tuning/diagnostic switch; results do not depend on it. */
 int keds_index_set_pdl(keds_index_t* idx, int enable);
+/* Streamed re-rank for large batches (default on; env KEDS_NO_STREAM_RERANK=1 turns the default
+ * off): the scoring kernel finishes query tiles wave by wave and the re-rank blocks of a tile start
+ * on the tile's completion counter instead of the scoring grid's end. Results do not depend on it. */
+int keds_index_set_stream_rerank(keds_index_t* idx, int enable);
 /* Scale the certificate's error bound (1.0 = rigorous bound). Test hook for the fallback. */
 int keds_index_set_eps_scale(keds_index_t* idx, float scale);
 

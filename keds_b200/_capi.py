@@ -25,6 +25,7 @@ class SearchStats(C.Structure):
         ("exact_only", C.c_int32),
         ("launches", C.c_int32),
         ("err_word", C.c_uint32),
+        ("streamed", C.c_int32),
     ]
 
 
@@ -133,6 +134,7 @@ SIGNATURES = {
     "keds_debug_plan": (C.c_int, [C.c_int, C.c_int64, C.c_int, C.c_int64, C.c_int, C.POINTER(C.c_int32)]),
     "keds_index_set_eps_scale": (C.c_int, [_vp, C.c_float]),
     "keds_index_set_pdl": (C.c_int, [_vp, C.c_int]),
+    "keds_index_set_stream_rerank": (C.c_int, [_vp, C.c_int]),
     "keds_last_error": (C.c_char_p, []),
     "keds_device_count": (C.c_int, []),
     "keds_version": (C.c_char_p, []),

@@ -195,9 +195,13 @@ int device_of(const void* p) {
 // candidate band |C| of the search (planner feedback), [7] spare
 constexpr int CTRL_WORDS = 8;
 constexpr int CTRL_BAND = 6;
+// behind the status words: the streamed re-rank's per-(database, query tile) counters. One such
+// block per pass of a multi-pass call, so that no pass has to be read back before the next starts.
+constexpr int CTRL_STRIDE = CTRL_WORDS + 2 * 128;  // Q_PASS_MAX / BM query tiles x two databases
 constexpr int S_MAX = 192;
 constexpr size_t CAND_BUDGET = size_t(1) << 30;
 constexpr int64_t Q_PASS_MAX = 16384;
+static_assert(CTRL_STRIDE >= CTRL_WORDS + 2 * (Q_PASS_MAX / 128), "one counter per (database, query tile) of a pass");
 constexpr size_t TIMING_RING = 8192;
 constexpr size_t TIMING_PAIRS = 5;  // k_prep_rows, k_score_topk, k_select_rerank, k_exact_fallback, (reserved)
 
@@ -206,6 +210,9 @@ struct Plan {
   bool pair = false;  // CTA-pair scoring kernel (two query tiles per work item)
   int sub = 1;        // candidate lines per (slice, query): 2 in the pair kernel (one per column half)
   int S = 1, n_qt = 1, n_qg = 1, n_items = 0, grid = 0;
+  bool small_batch = true;  // one wave of re-rank blocks: the latency variant
+  bool streamed = false;    // re-rank blocks wait for their query tile, not for the scoring grid
+  int W = 1;                // query groups per wave of the scoring kernel's item order (streamed only)
 };
 
 }  // namespace
@@ -239,6 +246,9 @@ struct keds_index {
   keds_search_stats stats;
   bool attrs_set = false;
   bool use_pdl = true;
+  bool stream_rerank = true;       // KEDS_NO_STREAM_RERANK=1: every re-rank block waits for the whole scoring grid
+  unsigned int* ctrl_cur = nullptr;  // status block of the pass being launched
+  int ctrl_passes = 1;             // status blocks the last call used (finish_sync reads them all)
   int rerank_threads_large = 128;  // block size of the throughput re-rank variant (KEDS_RERANK_THREADS)
   int rerank_variant = 0;          // 0: by batch size; 1 / 2: force the latency / throughput variant
   // in-kernel timing of the scoring kernel (bench.py's roofline leg): {min start, max end} ns
@@ -273,6 +283,7 @@ int set_kernel_attrs(keds_index* ix) {
   const char* no_pdl = getenv("KEDS_NO_PDL");
   ix->use_pdl = !(no_pdl && no_pdl[0] == '1');
   if (const char* ws = getenv("KEDS_NO_WARM_START")) ix->warm_start = !(ws[0] == '1');
+  if (const char* sr = getenv("KEDS_NO_STREAM_RERANK")) ix->stream_rerank = !(sr[0] == '1');
   if (const char* rv = getenv("KEDS_RERANK_VARIANT")) {
     if (!strcmp(rv, "latency")) ix->rerank_variant = 1;
     if (!strcmp(rv, "throughput")) ix->rerank_variant = 2;
@@ -355,6 +366,25 @@ Plan make_plan(const keds_index* ix, int n_db, int64_t nq, int k, int64_t n_min,
     pl.exact_only = 1;
     return pl;
   }
+  // Re-rank variant and streaming. One wave of re-rank blocks (two per SM): the latency variant
+  // behind the whole scoring grid. Large batches on the pair kernel: the scoring kernel walks the
+  // query groups wave by wave and the re-rank of a finished wave runs under the scoring of the next
+  // (rerank.cuh). A database that stays in L2 is walked one query group at a time; a larger one four
+  // at a time, which keeps the row traffic from HBM at a quarter of the tensor time.
+  pl.small_batch = nq * n_db <= 2ll * ix->num_sms;
+  if (ix->rerank_variant == 1) pl.small_batch = true;   // experiments: KEDS_RERANK_VARIANT=latency|throughput
+  if (ix->rerank_variant == 2) pl.small_batch = false;
+  pl.streamed = ix->stream_rerank && pl.pair && !pl.small_batch && pl.n_qg >= 2;
+  pl.W = pl.n_qg;
+  if (pl.streamed) {
+    const double db_bytes = static_cast<double>(n_db) * static_cast<double>(n_max) * std::max(ix->d_pad, 64) * 2.0;
+    pl.W = std::min(pl.n_qg, db_bytes <= 80e6 ? 1 : 4);
+  }
+  if (const char* dbg = getenv("KEDS_DEBUG_WAVE")) {  // experiments only: force the wave size
+    const int v = atoi(dbg);
+    if (pl.streamed && v >= 1) pl.W = std::min(pl.n_qg, v);
+  }
+  const int waves = (pl.n_qg + pl.W - 1) / pl.W;
   double best = 1e300;
   // one exact scan of every fp32 row, in the cost unit below (one bf16 row tile per work unit)
   const double scan_cost = 2.0 * T_max / units;
@@ -363,6 +393,15 @@ Plan make_plan(const keds_index* ix, int n_db, int64_t nq, int k, int64_t n_min,
     const long long G = std::min<long long>(items, units);
     const long long per_cta = (items + G - 1) / G;
     double cost = static_cast<double>(per_cta) * ((T_max + S - 1) / S) + 0.35 * per_cta;
+    if (pl.streamed) {
+      // what stays exposed of the re-rank (measured: ~1.1e-4 row tiles per query and neighbour, a
+      // little more per candidate list): the queries that finish in the last round of work items,
+      // or whatever half-rate blocks next to the scoring CTAs cannot absorb
+      const double r_est = static_cast<double>(nq) * n_db * (k + 8) * 1.1e-4 * (1.0 + 0.0022 * S * pl.sub);
+      const double frac_last = std::max(1.0 / static_cast<double>(per_cta), 1.0 / waves);
+      const double absorb = 0.5 * cost * static_cast<double>(per_cta - 1) / static_cast<double>(per_cta);
+      cost += std::max(r_est * frac_last, r_est - absorb);
+    }
     // expected fallbacks: a query is flagged when one list holds LKEEP or more of the rows at or
     // above tau (Poisson tail, five-fold margin) -- large k wants more lists than the SM count.
     // Rows at or above tau on i.i.d. data: ~2.4k with bf16 operands (wide band), k plus a few with
@@ -467,7 +506,7 @@ int launch_exact(keds_index* ix, keds_index* dbs[2], int n_db, const float* q_de
     e.x_f32 = dbs[i]->x_f32.as<float>();
     e.n_rows = dbs[i]->n;
     e.flagged = ix->flagged[i].as<int>();
-    e.n_flagged = ix->ctrl.as<int>() + i;
+    e.n_flagged = reinterpret_cast<int*>(ix->ctrl_cur) + i;
     e.scratch = scratch;
     scratch += static_cast<size_t>(fc) * dbs[i]->n;
     e.cmax = scratch;
@@ -485,10 +524,10 @@ int launch_exact(keds_index* ix, keds_index* dbs[2], int n_db, const float* q_de
   if (smem > 160 * 1024) return fail(KEDS_ERR_ARG, "d=%d / k=%d too large for the exact fallback", ix->d, k);
   const unsigned blocks = blocks_;
   // status words [3..5]: work counters of the fallback, zero at the start of every search
-  ep.work = ix->ctrl.as<unsigned int>() + 3;
-  ep.done = ix->ctrl.as<unsigned int>() + 5;
-  ep.err = ix->ctrl.as<unsigned int>() + 2;
-  ep.band_dev = ix->ctrl.as<unsigned int>() + CTRL_BAND;
+  ep.work = ix->ctrl_cur + 3;
+  ep.done = ix->ctrl_cur + 5;
+  ep.err = ix->ctrl_cur + 2;
+  ep.band_dev = ix->ctrl_cur + CTRL_BAND;
   const int passes = static_cast<int>((nq + fc - 1) / fc);
   for (int pass = 0; pass < passes; ++pass) {
     ep.pass = pass;
@@ -498,7 +537,7 @@ int launch_exact(keds_index* ix, keds_index* dbs[2], int n_db, const float* q_de
       ep.peer.publish = peer->publish && pass == passes - 1;  // only the step's very last launch publishes
     }
     ep.timing = pass == 0 ? timing : nullptr;
-    if (pass > 0) CK(cudaMemsetAsync(ix->ctrl.as<unsigned int>() + 3, 0, 12, st));
+    if (pass > 0) CK(cudaMemsetAsync(ix->ctrl_cur + 3, 0, 12, st));
     CKS(launch_k(ix->use_pdl, k_exact_fallback, dim3(blocks), dim3(EXACT_THREADS), smem, st, ep));
     ix->stats.launches += 1;
   }
@@ -509,7 +548,7 @@ int launch_exact(keds_index* ix, keds_index* dbs[2], int n_db, const float* q_de
 // cons_in (nullable): neighbour-consumer outputs for this pass, already offset to its first query.
 int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int k, float* D[2],
                 long long* I[2], uint32_t flags, cudaStream_t st, float* dump, int64_t ld_dump,
-                const ConsumeParams* cons_in, const PeerOut* peer = nullptr) {
+                const ConsumeParams* cons_in, const PeerOut* peer = nullptr, int pass_idx = 0) {
   keds_index* a = ix[0];
   const int metric = (flags & KEDS_SEARCH_FORCE_IP) ? METRIC_IP : a->metric;
   CKS(set_kernel_attrs(a));
@@ -523,7 +562,10 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
     tchain = a->timing.as<unsigned long long>() + TIMING_PAIRS * 2 * a->timing_launches;
     a->timing_launches++;
   }
-  CKS(a->ctrl.ensure(CTRL_WORDS * 4));
+  // (a multi-pass call sizes the status blocks of all its passes before the first launch)
+  CKS(a->ctrl.ensure(static_cast<size_t>(pass_idx + 1) * CTRL_STRIDE * 4));
+  a->ctrl_cur = a->ctrl.as<unsigned int>() + static_cast<size_t>(pass_idx) * CTRL_STRIDE;
+  a->ctrl_passes = pass_idx + 1;
   for (int i = 0; i < n_db; ++i) CKS(a->flagged[i].ensure(static_cast<size_t>(nq) * 4));
 
   int64_t n_min = ix[0]->n, n_max = ix[0]->n;
@@ -538,12 +580,14 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
   a->stats.slices = pl.S;
   a->stats.items = pl.n_items;
   a->stats.grid = pl.grid;
+  const bool streamed = pl.streamed && !dump;
+  a->stats.streamed = streamed ? pl.W : 0;
 
   if (pl.exact_only) {
-    CK(cudaMemsetAsync(a->ctrl.p, 0, CTRL_WORDS * 4, st));
+    CK(cudaMemsetAsync(a->ctrl_cur, 0, CTRL_WORDS * 4, st));
     for (int i = 0; i < n_db; ++i) {
       k_flag_all<<<static_cast<unsigned>((nq + 255) / 256), 256, 0, st>>>(
-          a->flagged[i].as<int>(), a->ctrl.as<int>() + i, static_cast<int>(nq));
+          a->flagged[i].as<int>(), reinterpret_cast<int*>(a->ctrl_cur) + i, static_cast<int>(nq));
       a->stats.launches++;
     }
   } else {
@@ -562,8 +606,8 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
       CKS(launch_k(a->use_pdl, k_prep_rows, dim3(blocks), dim3(threads), 0, st, q_dev,
                    static_cast<long long>(nq), a->d, a->d_pad, a->fmt, a->q_bf16.as<uint16_t>(),
                    a->qstat.as<float4>(), static_cast<float*>(nullptr), static_cast<unsigned int*>(nullptr),
-                   a->ctrl.as<unsigned int>(), CTRL_WORDS, a->theta0.as<float>(), static_cast<int>(n_db * theta_ld),
-                   tchain));
+                   a->ctrl_cur, CTRL_WORDS + (streamed ? n_db * pl.n_qt : 0), a->theta0.as<float>(),
+                   static_cast<int>(n_db * theta_ld), tchain));
       a->stats.launches++;
     }
     // candidate lines are indexed by (db, slice, query tile) whatever the work-item grouping
@@ -579,6 +623,8 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
     sp.n_qg = pl.n_qg;
     sp.S = pl.S;
     sp.n_items = pl.n_items;
+    sp.W = streamed ? pl.W : pl.n_qg;
+    sp.qt_done = streamed ? a->ctrl_cur + CTRL_WORDS : nullptr;
     sp.kblocks = a->d_pad / BK;
     sp.fmt_bits = a->fmt == FMT_BF16 ? kIdescBf16Bits : 0u;
     sp.nq = static_cast<int>(nq);
@@ -592,7 +638,7 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
     sp.cand_theta = a->cand_theta.as<float>();
     sp.theta0 = a->warm_start ? a->theta0.as<float>() : nullptr;
     sp.theta_ld = static_cast<int>(theta_ld);
-    sp.err = a->ctrl.as<uint32_t>() + 2;
+    sp.err = a->ctrl_cur + 2;
     sp.dump = dump;
     sp.ld_dump = ld_dump;
     sp.timing = tchain ? tchain + 2 : nullptr;
@@ -629,14 +675,15 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
       rp.I[i] = I[i];
       rp.id_offset[i] = ix[i]->id_offset;
       rp.flagged[i] = a->flagged[i].as<int>();
-      rp.n_flagged[i] = a->ctrl.as<int>() + i;
+      rp.n_flagged[i] = reinterpret_cast<int*>(a->ctrl_cur) + i;
     }
     rp.eps_scale = a->eps_scale;
-    rp.band_max = a->ctrl.as<unsigned int>() + CTRL_BAND;
+    rp.band_max = a->ctrl_cur + CTRL_BAND;
+    rp.qt_done = sp.qt_done;
+    rp.done_target = static_cast<unsigned int>(pl.S) * ScoreCfg<true>::kEpiWarps;
+    rp.err = a->ctrl_cur + 2;
     // one wave of blocks (two per SM): the latency variant; more: the four-per-SM throughput variant
-    bool small_batch = nq * n_db <= 2ll * a->num_sms;
-    if (a->rerank_variant == 1) small_batch = true;   // experiments: KEDS_RERANK_VARIANT=latency|throughput
-    if (a->rerank_variant == 2) small_batch = false;
+    const bool small_batch = pl.small_batch;
     // Candidate capacity. A single wave has the shared memory to spare: full size. Large batches
     // live on blocks per SM, so they start small and follow the band a recent search reported (a
     // query that does not fit is answered by the exact fallback and raises the next call's figure).
@@ -660,6 +707,9 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
     if (small_batch)
       CKS(launch_k(a->use_pdl, k_select_rerank<3, 2>, dim3(static_cast<unsigned>(nq), n_db),
                    dim3(RERANK_THREADS), smem, st, rp));
+    else if (streamed)
+      CKS(launch_k(a->use_pdl, k_select_rerank<1, 4>, dim3(static_cast<unsigned>(pl.n_qg * 2 * BM * n_db)),
+                   dim3(a->rerank_threads_large), smem, st, rp));
     else
       CKS(launch_k(a->use_pdl, k_select_rerank<1, 4>, dim3(static_cast<unsigned>(nq), n_db),
                    dim3(a->rerank_threads_large), smem, st, rp));
@@ -683,10 +733,26 @@ __global__ void k_fill_pad(float* D, long long* I, long long n, float dv) {
   }
 }
 
+// Status of a call = its passes' status blocks folded: flagged queries summed, first error word.
+void read_status(const keds_index* a, const uint32_t* blocks, uint32_t h[CTRL_WORDS]) {
+  for (int i = 0; i < CTRL_WORDS; ++i) h[i] = 0;
+  if (!blocks) return;
+  for (int p = 0; p < a->ctrl_passes; ++p) {
+    const uint32_t* b = blocks + static_cast<size_t>(p) * CTRL_STRIDE;
+    h[0] += b[0];
+    h[1] += b[1];
+    if (h[2] == 0) h[2] = b[2];
+  }
+}
+
 int finish_sync(keds_index* a, cudaStream_t st) {
   CK(cudaStreamSynchronize(st));
   uint32_t h[CTRL_WORDS] = {0};
-  if (a->ctrl.p) CK(cudaMemcpy(h, a->ctrl.p, sizeof h, cudaMemcpyDeviceToHost));
+  if (a->ctrl.p) {
+    std::vector<uint32_t> all(static_cast<size_t>(a->ctrl_passes) * CTRL_STRIDE);
+    CK(cudaMemcpy(all.data(), a->ctrl.p, all.size() * 4, cudaMemcpyDeviceToHost));
+    read_status(a, all.data(), h);
+  }
   a->stats.n_flagged[0] = static_cast<int32_t>(h[0]);
   a->stats.n_flagged[1] = static_cast<int32_t>(h[1]);
   a->stats.err_word = h[2];
@@ -755,6 +821,10 @@ int search_impl(keds_index* ix[2], int n_db, const float* q, int64_t nq, int k, 
       Id[i] = a->I_stage[i].as<long long>();
     }
   }
+  // status blocks of every pass, sized before the first launch (growing them later would free
+  // memory that kernels of an earlier pass still write)
+  const int n_passes = static_cast<int>((nq + Q_PASS_MAX - 1) / Q_PASS_MAX);
+  CKS(a->ctrl.ensure(static_cast<size_t>(n_passes) * CTRL_STRIDE * 4));
   // empty databases answer with padding only
   bool any_empty = false;
   for (int i = 0; i < n_db; ++i) any_empty = any_empty || ix[i]->n == 0;
@@ -769,8 +839,10 @@ int search_impl(keds_index* ix[2], int n_db, const float* q, int64_t nq, int k, 
           const int64_t nb = std::min<int64_t>(Q_PASS_MAX, nq - q0);
           float* Dp[2] = {D1[0] + q0 * k, nullptr};
           long long* Ip[2] = {I1[0] + q0 * k, nullptr};
-          CKS(search_pass(one, 1, qd + q0 * a->d, nb, k, Dp, Ip, flags, st, nullptr, 0, nullptr));
-          if (q0 + nb < nq) CKS(finish_sync(one[0], st));
+          // (stream order keeps the passes apart: every kernel of a chain waits for its predecessor)
+          CKS(one[0]->ctrl.ensure(static_cast<size_t>(n_passes) * CTRL_STRIDE * 4));
+          CKS(search_pass(one, 1, qd + q0 * a->d, nb, k, Dp, Ip, flags, st, nullptr, 0, nullptr, nullptr,
+                          static_cast<int>(q0 / Q_PASS_MAX)));
         }
       } else {
         const long long tot = static_cast<long long>(nq) * k;
@@ -801,10 +873,10 @@ int search_impl(keds_index* ix[2], int n_db, const float* q, int64_t nq, int k, 
         }
         pp.publish = q0 + nb >= nq;  // the flags go out behind the step's last pass
       }
+      // every pass has its own status block and the scratch is reused in stream order (each kernel
+      // of a chain waits for its predecessor to complete), so the passes queue without a host round trip
       CKS(search_pass(ix, n_db, qd + q0 * a->d, nb, k, Dp, Ip, flags, st, nullptr, 0, cons ? &cp : nullptr,
-                      peer ? &pp : nullptr));
-      // the per-call status words are rewritten by the next pass: read this pass's first
-      if (q0 + nb < nq) CKS(finish_sync(a, st));
+                      peer ? &pp : nullptr, static_cast<int>(q0 / Q_PASS_MAX)));
     }
   }
   if (!out_dev) {
@@ -820,16 +892,19 @@ int search_impl(keds_index* ix[2], int n_db, const float* q, int64_t nq, int k, 
       }
       return finish_sync(a, st);
     }
-    CKS(a->h_out.ensure(per * n_db + CTRL_WORDS * 4));
+    const size_t ctrl_bytes = static_cast<size_t>(a->ctrl_passes) * CTRL_STRIDE * 4;
+    CKS(a->h_out.ensure(per * n_db + ctrl_bytes));
     uint8_t* h = static_cast<uint8_t*>(a->h_out.p);
     for (int i = 0; i < n_db; ++i) {
       CK(cudaMemcpyAsync(h + per * i, Dd[i], db_, cudaMemcpyDeviceToHost, st));
       CK(cudaMemcpyAsync(h + per * i + db_, Id[i], ib_, cudaMemcpyDeviceToHost, st));
     }
-    uint32_t* hc = reinterpret_cast<uint32_t*>(h + per * n_db);
-    memset(hc, 0, CTRL_WORDS * 4);
-    if (a->ctrl.p) CK(cudaMemcpyAsync(hc, a->ctrl.p, CTRL_WORDS * 4, cudaMemcpyDeviceToHost, st));
+    uint32_t* hall = reinterpret_cast<uint32_t*>(h + per * n_db);
+    memset(hall, 0, ctrl_bytes);
+    if (a->ctrl.p) CK(cudaMemcpyAsync(hall, a->ctrl.p, ctrl_bytes, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    uint32_t hc[CTRL_WORDS];
+    read_status(a, hall, hc);
     for (int i = 0; i < n_db; ++i) {
       memcpy(D[i], h + per * i, db_);
       memcpy(I[i], h + per * i + db_, ib_);
@@ -1074,6 +1149,14 @@ int keds_index_set_pdl(keds_index_t* ix, int enable) {
   return 0;
 }
 
+int keds_index_set_stream_rerank(keds_index_t* ix, int enable) {
+  if (!ix) return fail(KEDS_ERR_ARG, "set_stream_rerank: null handle");
+  DeviceGuard g(ix->device);
+  CKS(set_kernel_attrs(ix));
+  ix->stream_rerank = enable != 0;
+  return 0;
+}
+
 int keds_index_set_eps_scale(keds_index_t* ix, float scale) {
   if (!ix || !(scale >= 0.f)) return fail(KEDS_ERR_ARG, "set_eps_scale: bad argument");
   ix->eps_scale = scale;
@@ -1260,6 +1343,7 @@ int keds_debug_plan(int n_db, int64_t nq, int k, int64_t n_rows, int num_sms, in
     return fail(KEDS_ERR_ARG, "debug_plan: bad argument");
   keds_index ix;  // never touches the device: only the planner's inputs are read
   ix.num_sms = num_sms;
+  ix.d = ix.d_pad = 768;  // the planner weighs the database's bytes against L2: the reference's 768-d rows
   const char* no_pair = getenv("KEDS_NO_PAIR");
   ix.use_pair = !(no_pair && no_pair[0] == '1');
   const Plan pl = make_plan(&ix, n_db, nq, k, n_rows, n_rows, 0u);

@@ -178,7 +178,8 @@ __global__ void k_prep_rows(const float* __restrict__ x, long long n, int d, int
   const unsigned long long t_start = ktimer_begin(timing);
   // per-call control words (flag counters, error word) are cleared here instead of by a separate
   // memset node in front of every search; the shared per-query thresholds start at -inf
-  if (zero_words != nullptr && blockIdx.x == 0 && threadIdx.x < n_zero) zero_words[threadIdx.x] = 0u;
+  if (zero_words != nullptr && blockIdx.x == 0)
+    for (int i = threadIdx.x; i < n_zero; i += blockDim.x) zero_words[i] = 0u;
   if (neg_inf_words != nullptr)
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_neg_inf; i += gridDim.x * blockDim.x)
       neg_inf_words[i] = -INFINITY;

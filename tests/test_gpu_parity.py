@@ -179,6 +179,73 @@ def test_config1_4096_queries_vs_50k_rows():
     assert st["exact_only"] == 0 and st["n_flagged"][0] < 64   # the tensor-core path answered
 
 
+def _plain_rerank_index(db, metric):
+    """an index whose re-rank blocks wait for the whole scoring grid"""
+    ix = build(db, metric)
+    ix.set_stream_rerank(False)
+    return ix
+
+
+@pytest.mark.parametrize("metric", ["ip", "l2"])
+@pytest.mark.parametrize("n,b,k", [(50000, 4096, 16), (30000, 1000, 16), (20000, 1408, 64), (70000, 2049, 16)])
+def test_streamed_rerank_equals_the_plain_chain_and_the_oracle(n, b, k, metric):
+    """Large batches: the scoring kernel finishes query tiles wave by wave and the re-rank blocks of
+    a tile start on its counter instead of the scoring grid's completion (rerank.cuh). Same lists,
+    same arithmetic: the answer must equal the plain chain's bit for bit, ragged batches (1000
+    queries: the last CTA pair works on one tile; 2049: a tile with a single query) included, and
+    both must satisfy the oracle."""
+    db, q = unit(n, 768, 4000 + n % 97), unit(b, 768, 4100 + b % 89)
+    ix = build(db, metric)
+    qd = torch.from_numpy(q).cuda()
+    D, I = ix.search(qd, k)
+    ix.sync()
+    st = ix.last_stats()
+    assert st["streamed"] >= 1 and st["exact_only"] == 0 and st["err_word"] == 0, st
+    ref = _plain_rerank_index(db, metric)
+    D0, I0 = ref.search(qd, k)
+    ref.sync()
+    assert ref.last_stats()["streamed"] == 0
+    assert torch.equal(I, I0) and torch.equal(D, D0)
+    sub = np.linspace(0, b - 1, 96).astype(np.int64)
+    Dr, Ir = orc.search(db, q[sub], k, metric)
+    c = orc.compare_topk(Dr, Ir, D.cpu().numpy()[sub], I.cpu().numpy()[sub], db, q[sub], metric, TIE_GAP, D_TOL)
+    assert c["ok"], (c, st)
+    for _ in range(3):   # the counters are re-armed by every search
+        D2, I2 = ix.search(qd, k)
+    ix.sync()
+    assert torch.equal(I2, I) and torch.equal(D2, D) and ix.last_stats()["err_word"] == 0
+
+
+def test_streamed_rerank_two_databases_with_the_consumer_and_several_passes():
+    """The streamed chain under the fused two-database retrieval (gather + pool inside the re-rank
+    blocks) and across the passes of a 17,000-query call, which now queue without a host round trip
+    (one status block per pass): flagged counts add up over the passes."""
+    a, b = unit(40000, 768, 4200), unit(40000, 768, 4201)
+    q = unit(17000, 768, 4202)
+    ia, ib = build(a, "ip"), build(b, "ip")
+    qd = torch.from_numpy(q).cuda()
+    perm = torch.randperm(16, generator=torch.Generator().manual_seed(6))
+    o = kr.retrieve2(ia, ib, qd, 16, perm_img=perm, want_feats=True, pool_mode=kr.POOL_SOFTMAX, tau=50.0)
+    ia.sync()
+    st = ia.last_stats()
+    assert st["streamed"] >= 1 and st["err_word"] == 0, st
+    sub = np.concatenate([np.arange(0, 17000, 173), [16383, 16384, 16385, 16999]])
+    for name, db, ix_perm in (("img", a, perm.numpy()), ("txt", b, None)):
+        D, I = o[f"D_{name}"].cpu().numpy()[sub], o[f"I_{name}"].cpu().numpy()[sub]
+        Dr, Ir = orc.search(db, q[sub], 16, "ip")
+        assert orc.compare_topk(Dr, Ir, D, I, db, q[sub], "ip", TIE_GAP, D_TOL)["ok"]
+        assert np.array_equal(o[f"feat_{name}"][torch.from_numpy(sub).cuda()].cpu().numpy(), orc.gather(db, I, ix_perm))
+        W = orc.softmax_weights(D, 50.0)
+        assert np.abs(o[f"pool_{name}"].cpu().numpy()[sub] - orc.weighted_pool(db, I, W)[:, 0]).max() < 2e-5
+    # an inflated error bound flags every query: the per-pass flag counters must add up to the batch
+    ia.set_eps_scale(1e4)
+    D1, I1 = ia.search(qd, 16)
+    ia.sync()
+    assert ia.last_stats()["n_flagged"][0] == 17000
+    ia.set_eps_scale(1.0)
+    assert torch.equal(I1, o["I_img"])
+
+
 def test_more_queries_than_one_pass_holds():
     """Batches above 16,384 queries (config 3 has 65,536) are cut into passes inside one call: the
     seams must not show, for one database and for the fused two-database search."""
