@@ -47,8 +47,6 @@ typedef struct keds_search_stats {
   int32_t exact_only;    /* 1 if the planner chose the fp32 scan for the whole batch */
   int32_t launches;      /* kernels launched by the last search call */
   uint32_t err_word;     /* device watchdog word, 0 = clean */
-  int32_t streamed;      /* 0: every re-rank block waited for the whole scoring grid; W > 0: the re-rank
-                            was streamed behind waves of W query groups (256 queries each) */
 } keds_search_stats;
 
 /* ---- index lifecycle ------------------------------------------------------------------------
@@ -117,6 +115,21 @@ int keds_retrieve2(keds_index_t* img, keds_index_t* txt, const float* q, int64_t
                    float* D_img, int64_t* I_img, float* D_txt, int64_t* I_txt, float* feat_img,
                    float* feat_txt, float* pool_img, float* pool_txt, uint32_t flags,
                    void* cuda_stream);
+/* The same operator for a caller whose queries and results live on the HOST, as the reference's do
+ * (q.cpu().numpy() in, numpy (D, I) out, src/trainer.py:207-221), without copies around the search:
+ *   q        may be page-locked host memory (cudaHostAlloc / cudaHostRegister / torch pin_memory):
+ *            the first kernel of the chain reads it through the device mapping, once;
+ *   Dh_x, Ih_x (nullable, in pairs) page-locked host blocks [nq][k]: the block that finishes a query's
+ *            row stores it there as well as into D_x, I_x (posted writes that travel while the
+ *            neighbour gather of that query runs).
+ * Stream-ordered and asynchronous like keds_retrieve2: the host blocks are complete once the stream
+ * has been synchronised (or the graph that captured the call has finished). */
+int keds_retrieve2_hostio(keds_index_t* img, keds_index_t* txt, const float* q, int64_t nq, int k,
+                          const int32_t* perm_img, const int32_t* perm_txt, int pool_mode, float tau,
+                          float* D_img, int64_t* I_img, float* D_txt, int64_t* I_txt, float* Dh_img,
+                          int64_t* Ih_img, float* Dh_txt, int64_t* Ih_txt, float* feat_img,
+                          float* feat_txt, float* pool_img, float* pool_txt, uint32_t flags,
+                          void* cuda_stream);
 /* Wait for the last asynchronous search on idx and report its device status. */
 int keds_index_sync(keds_index_t* idx, void* cuda_stream);
 int keds_index_last_stats(const keds_index_t* idx, keds_search_stats* out);
@@ -334,10 +347,6 @@ int keds_debug_plan(int n_db, int64_t nq, int k, int64_t n_rows, int num_sms, in
 /* Programmatic dependent launch between the kernels of a search (default on; env KEDS_NO_PDL=1
  * turns the default off). Tuning/diagnostic switch; results do not depend on it. */
 int keds_index_set_pdl(keds_index_t* idx, int enable);
-/* Streamed re-rank for large batches (default on; env KEDS_NO_STREAM_RERANK=1 turns the default
- * off): the scoring kernel finishes query tiles wave by wave and the re-rank blocks of a tile start
- * on the tile's completion counter instead of the scoring grid's end. Results do not depend on it. */
-int keds_index_set_stream_rerank(keds_index_t* idx, int enable);
 /* Scale the certificate's error bound (1.0 = rigorous bound). Test hook for the fallback. */
 int keds_index_set_eps_scale(keds_index_t* idx, float scale);
 

@@ -25,7 +25,6 @@ class SearchStats(C.Structure):
         ("exact_only", C.c_int32),
         ("launches", C.c_int32),
         ("err_word", C.c_uint32),
-        ("streamed", C.c_int32),
     ]
 
 
@@ -69,6 +68,11 @@ SIGNATURES = {
         C.c_int,
         [_vp, _vp, _vp, C.c_int64, C.c_int, _vp, _vp, C.c_int, C.c_float,
          _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_uint32, _vp],
+    ),
+    "keds_retrieve2_hostio": (
+        C.c_int,
+        [_vp, _vp, _vp, C.c_int64, C.c_int, _vp, _vp, C.c_int, C.c_float,
+         _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_uint32, _vp],
     ),
     "keds_index_sync": (C.c_int, [_vp, _vp]),
     "keds_index_last_stats": (C.c_int, [_vp, C.POINTER(SearchStats)]),
@@ -134,7 +138,6 @@ SIGNATURES = {
     "keds_debug_plan": (C.c_int, [C.c_int, C.c_int64, C.c_int, C.c_int64, C.c_int, C.POINTER(C.c_int32)]),
     "keds_index_set_eps_scale": (C.c_int, [_vp, C.c_float]),
     "keds_index_set_pdl": (C.c_int, [_vp, C.c_int]),
-    "keds_index_set_stream_rerank": (C.c_int, [_vp, C.c_int]),
     "keds_last_error": (C.c_char_p, []),
     "keds_device_count": (C.c_int, []),
     "keds_version": (C.c_char_p, []),

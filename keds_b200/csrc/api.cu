@@ -195,13 +195,12 @@ int device_of(const void* p) {
 // candidate band |C| of the search (planner feedback), [7] spare
 constexpr int CTRL_WORDS = 8;
 constexpr int CTRL_BAND = 6;
-// behind the status words: the streamed re-rank's per-(database, query tile) counters. One such
-// block per pass of a multi-pass call, so that no pass has to be read back before the next starts.
-constexpr int CTRL_STRIDE = CTRL_WORDS + 2 * 128;  // Q_PASS_MAX / BM query tiles x two databases
+// one block of status words per pass of a multi-pass call, so that no pass has to be read back
+// before the next one starts
+constexpr int CTRL_STRIDE = CTRL_WORDS;
 constexpr int S_MAX = 192;
 constexpr size_t CAND_BUDGET = size_t(1) << 30;
 constexpr int64_t Q_PASS_MAX = 16384;
-static_assert(CTRL_STRIDE >= CTRL_WORDS + 2 * (Q_PASS_MAX / 128), "one counter per (database, query tile) of a pass");
 constexpr size_t TIMING_RING = 8192;
 constexpr size_t TIMING_PAIRS = 5;  // k_prep_rows, k_score_topk, k_select_rerank, k_exact_fallback, (reserved)
 
@@ -211,8 +210,6 @@ struct Plan {
   int sub = 1;        // candidate lines per (slice, query): 2 in the pair kernel (one per column half)
   int S = 1, n_qt = 1, n_qg = 1, n_items = 0, grid = 0;
   bool small_batch = true;  // one wave of re-rank blocks: the latency variant
-  bool streamed = false;    // re-rank blocks wait for their query tile, not for the scoring grid
-  int W = 1;                // query groups per wave of the scoring kernel's item order (streamed only)
 };
 
 }  // namespace
@@ -246,7 +243,6 @@ struct keds_index {
   keds_search_stats stats;
   bool attrs_set = false;
   bool use_pdl = true;
-  bool stream_rerank = true;       // KEDS_NO_STREAM_RERANK=1: every re-rank block waits for the whole scoring grid
   unsigned int* ctrl_cur = nullptr;  // status block of the pass being launched
   int ctrl_passes = 1;             // status blocks the last call used (finish_sync reads them all)
   int rerank_threads_large = 128;  // block size of the throughput re-rank variant (KEDS_RERANK_THREADS)
@@ -283,7 +279,6 @@ int set_kernel_attrs(keds_index* ix) {
   const char* no_pdl = getenv("KEDS_NO_PDL");
   ix->use_pdl = !(no_pdl && no_pdl[0] == '1');
   if (const char* ws = getenv("KEDS_NO_WARM_START")) ix->warm_start = !(ws[0] == '1');
-  if (const char* sr = getenv("KEDS_NO_STREAM_RERANK")) ix->stream_rerank = !(sr[0] == '1');
   if (const char* rv = getenv("KEDS_RERANK_VARIANT")) {
     if (!strcmp(rv, "latency")) ix->rerank_variant = 1;
     if (!strcmp(rv, "throughput")) ix->rerank_variant = 2;
@@ -366,25 +361,11 @@ Plan make_plan(const keds_index* ix, int n_db, int64_t nq, int k, int64_t n_min,
     pl.exact_only = 1;
     return pl;
   }
-  // Re-rank variant and streaming. One wave of re-rank blocks (two per SM): the latency variant
-  // behind the whole scoring grid. Large batches on the pair kernel: the scoring kernel walks the
-  // query groups wave by wave and the re-rank of a finished wave runs under the scoring of the next
-  // (rerank.cuh). A database that stays in L2 is walked one query group at a time; a larger one four
-  // at a time, which keeps the row traffic from HBM at a quarter of the tensor time.
+  // re-rank variant: one wave of blocks (two per SM) runs the latency variant, more the
+  // four-per-SM throughput variant
   pl.small_batch = nq * n_db <= 2ll * ix->num_sms;
   if (ix->rerank_variant == 1) pl.small_batch = true;   // experiments: KEDS_RERANK_VARIANT=latency|throughput
   if (ix->rerank_variant == 2) pl.small_batch = false;
-  pl.streamed = ix->stream_rerank && pl.pair && !pl.small_batch && pl.n_qg >= 2;
-  pl.W = pl.n_qg;
-  if (pl.streamed) {
-    const double db_bytes = static_cast<double>(n_db) * static_cast<double>(n_max) * std::max(ix->d_pad, 64) * 2.0;
-    pl.W = std::min(pl.n_qg, db_bytes <= 80e6 ? 1 : 4);
-  }
-  if (const char* dbg = getenv("KEDS_DEBUG_WAVE")) {  // experiments only: force the wave size
-    const int v = atoi(dbg);
-    if (pl.streamed && v >= 1) pl.W = std::min(pl.n_qg, v);
-  }
-  const int waves = (pl.n_qg + pl.W - 1) / pl.W;
   double best = 1e300;
   // one exact scan of every fp32 row, in the cost unit below (one bf16 row tile per work unit)
   const double scan_cost = 2.0 * T_max / units;
@@ -393,15 +374,6 @@ Plan make_plan(const keds_index* ix, int n_db, int64_t nq, int k, int64_t n_min,
     const long long G = std::min<long long>(items, units);
     const long long per_cta = (items + G - 1) / G;
     double cost = static_cast<double>(per_cta) * ((T_max + S - 1) / S) + 0.35 * per_cta;
-    if (pl.streamed) {
-      // what stays exposed of the re-rank (measured: ~1.1e-4 row tiles per query and neighbour, a
-      // little more per candidate list): the queries that finish in the last round of work items,
-      // or whatever half-rate blocks next to the scoring CTAs cannot absorb
-      const double r_est = static_cast<double>(nq) * n_db * (k + 8) * 1.1e-4 * (1.0 + 0.0022 * S * pl.sub);
-      const double frac_last = std::max(1.0 / static_cast<double>(per_cta), 1.0 / waves);
-      const double absorb = 0.5 * cost * static_cast<double>(per_cta - 1) / static_cast<double>(per_cta);
-      cost += std::max(r_est * frac_last, r_est - absorb);
-    }
     // expected fallbacks: a query is flagged when one list holds LKEEP or more of the rows at or
     // above tau (Poisson tail, five-fold margin) -- large k wants more lists than the SM count.
     // Rows at or above tau on i.i.d. data: ~2.4k with bf16 operands (wide band), k plus a few with
@@ -548,7 +520,10 @@ int launch_exact(keds_index* ix, keds_index* dbs[2], int n_db, const float* q_de
 // cons_in (nullable): neighbour-consumer outputs for this pass, already offset to its first query.
 int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int k, float* D[2],
                 long long* I[2], uint32_t flags, cudaStream_t st, float* dump, int64_t ld_dump,
-                const ConsumeParams* cons_in, const PeerOut* peer = nullptr, int pass_idx = 0) {
+                const ConsumeParams* cons_in, const PeerOut* peer = nullptr, int pass_idx = 0,
+                const float* q_src = nullptr) {
+  // q_src (nullable): the queries in page-locked host memory, addressed through the mapping;
+  // k_prep_rows reads them there once and leaves the fp32 copy the other kernels use in q_dev
   keds_index* a = ix[0];
   const int metric = (flags & KEDS_SEARCH_FORCE_IP) ? METRIC_IP : a->metric;
   CKS(set_kernel_attrs(a));
@@ -580,10 +555,9 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
   a->stats.slices = pl.S;
   a->stats.items = pl.n_items;
   a->stats.grid = pl.grid;
-  const bool streamed = pl.streamed && !dump;
-  a->stats.streamed = streamed ? pl.W : 0;
 
   if (pl.exact_only) {
+    if (q_src) CK(cudaMemcpyAsync(const_cast<float*>(q_dev), q_src, static_cast<size_t>(nq) * a->d * 4, cudaMemcpyDefault, st));
     CK(cudaMemsetAsync(a->ctrl_cur, 0, CTRL_WORDS * 4, st));
     for (int i = 0; i < n_db; ++i) {
       k_flag_all<<<static_cast<unsigned>((nq + 255) / 256), 256, 0, st>>>(
@@ -603,11 +577,11 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
       const long long warps_needed = nq;
       const unsigned blocks =
           static_cast<unsigned>(std::min<long long>((warps_needed * 32 + threads - 1) / threads, 4096));
-      CKS(launch_k(a->use_pdl, k_prep_rows, dim3(blocks), dim3(threads), 0, st, q_dev,
+      CKS(launch_k(a->use_pdl, k_prep_rows, dim3(blocks), dim3(threads), 0, st, q_src ? q_src : q_dev,
                    static_cast<long long>(nq), a->d, a->d_pad, a->fmt, a->q_bf16.as<uint16_t>(),
                    a->qstat.as<float4>(), static_cast<float*>(nullptr), static_cast<unsigned int*>(nullptr),
-                   a->ctrl_cur, CTRL_WORDS + (streamed ? n_db * pl.n_qt : 0), a->theta0.as<float>(),
-                   static_cast<int>(n_db * theta_ld), tchain));
+                   a->ctrl_cur, CTRL_WORDS, a->theta0.as<float>(), static_cast<int>(n_db * theta_ld), tchain,
+                   q_src ? const_cast<float*>(q_dev) : static_cast<float*>(nullptr)));
       a->stats.launches++;
     }
     // candidate lines are indexed by (db, slice, query tile) whatever the work-item grouping
@@ -623,8 +597,6 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
     sp.n_qg = pl.n_qg;
     sp.S = pl.S;
     sp.n_items = pl.n_items;
-    sp.W = streamed ? pl.W : pl.n_qg;
-    sp.qt_done = streamed ? a->ctrl_cur + CTRL_WORDS : nullptr;
     sp.kblocks = a->d_pad / BK;
     sp.fmt_bits = a->fmt == FMT_BF16 ? kIdescBf16Bits : 0u;
     sp.nq = static_cast<int>(nq);
@@ -679,9 +651,6 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
     }
     rp.eps_scale = a->eps_scale;
     rp.band_max = a->ctrl_cur + CTRL_BAND;
-    rp.qt_done = sp.qt_done;
-    rp.done_target = static_cast<unsigned int>(pl.S) * ScoreCfg<true>::kEpiWarps;
-    rp.err = a->ctrl_cur + 2;
     // one wave of blocks (two per SM): the latency variant; more: the four-per-SM throughput variant
     const bool small_batch = pl.small_batch;
     // Candidate capacity. A single wave has the shared memory to spare: full size. Large batches
@@ -707,9 +676,6 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
     if (small_batch)
       CKS(launch_k(a->use_pdl, k_select_rerank<3, 2>, dim3(static_cast<unsigned>(nq), n_db),
                    dim3(RERANK_THREADS), smem, st, rp));
-    else if (streamed)
-      CKS(launch_k(a->use_pdl, k_select_rerank<1, 4>, dim3(static_cast<unsigned>(pl.n_qg * 2 * BM * n_db)),
-                   dim3(a->rerank_threads_large), smem, st, rp));
     else
       CKS(launch_k(a->use_pdl, k_select_rerank<1, 4>, dim3(static_cast<unsigned>(nq), n_db),
                    dim3(a->rerank_threads_large), smem, st, rp));
@@ -731,6 +697,20 @@ __global__ void k_fill_pad(float* D, long long* I, long long n, float dv) {
     D[i] = dv;
     I[i] = -1;
   }
+}
+
+// device alias of a page-locked host result block (nullptr in: nullptr out)
+template <class T>
+int mapped_alias(T* host, T** out) {
+  *out = nullptr;
+  if (!host) return 0;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, host) != cudaSuccess || at.type != cudaMemoryTypeHost || !at.devicePointer) {
+    cudaGetLastError();
+    return fail(KEDS_ERR_ARG, "retrieve2_hostio: a host result pointer is not page-locked (cudaHostAlloc / pin_memory)");
+  }
+  *out = static_cast<T*>(at.devicePointer);
+  return 0;
 }
 
 // Status of a call = its passes' status blocks folded: flagged queries summed, first error word.
@@ -763,7 +743,7 @@ int finish_sync(keds_index* a, cudaStream_t st) {
 
 int search_impl(keds_index* ix[2], int n_db, const float* q, int64_t nq, int k, float* D[2],
                 int64_t* I[2], uint32_t flags, void* stream, const ConsumeParams* cons = nullptr,
-                const PeerOut* peer = nullptr) {
+                const PeerOut* peer = nullptr, bool q_mapped = false) {
   keds_index* a = ix[0];
   if (!a || !q || nq < 0 || k <= 0) return fail(KEDS_ERR_ARG, "search: null handle/query or bad nq/k");
   if (k > K_MAX) return fail(KEDS_ERR_ARG, "search: k=%d exceeds the maximum %d", k, K_MAX);
@@ -784,7 +764,19 @@ int search_impl(keds_index* ix[2], int n_db, const float* q, int64_t nq, int k, 
     for (int i = 0; i < 2; ++i)
       if (ix[i]->fmt != FMT_BF16) CKS(keds_index_set_operand_format(ix[i], FMT_BF16));
 
-  const bool q_dev = is_device_ptr(q);
+  // q_mapped: the queries sit in page-locked host memory and the first kernel of the chain reads
+  // them through the mapping (no copy in front of the search); it leaves an fp32 copy in q_f32
+  const float* q_map = nullptr;
+  if (q_mapped && !is_device_ptr(q)) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, q) != cudaSuccess || at.type != cudaMemoryTypeHost || !at.devicePointer) {
+      cudaGetLastError();
+      return fail(KEDS_ERR_ARG, "retrieve2_hostio: q is neither device memory nor page-locked host memory");
+    }
+    q_map = static_cast<const float*>(at.devicePointer);
+    CKS(a->q_f32.ensure(static_cast<size_t>(nq) * a->d * 4));
+  }
+  const bool q_dev = q_map != nullptr || is_device_ptr(q);
   bool out_dev = true;
   for (int i = 0; i < n_db; ++i) {
     const bool dd = is_device_ptr(D[i]), di = is_device_ptr(I[i]);
@@ -793,19 +785,48 @@ int search_impl(keds_index* ix[2], int n_db, const float* q, int64_t nq, int k, 
     if (i > 0 && dd != is_device_ptr(D[0]))
       return fail(KEDS_ERR_ARG, "search2: outputs must all be host or all be device memory");
   }
-  const float* qd = q;
+  const float* qd = q_map ? a->q_f32.as<float>() : q;
+  bool any_empty = false;
+  for (int i = 0; i < n_db; ++i) any_empty = any_empty || ix[i]->n == 0;
+  // Host in, host out (the reference's numpy call): the call synchronises before it returns, so
+  // page-locked staging buffers can be reused call after call -- and the kernels work on them
+  // through the mapping: k_prep_rows reads the staged queries, the ranking blocks store their rows
+  // into the staged result block. No copy in front of the search and none behind it.
+  // one database's I (8 B) and D (4 B) blocks in the staged result, labels first (8-byte aligned)
+  const size_t res_per = (static_cast<size_t>(nq) * k * 12 + 15) & ~size_t(15);
+  ConsumeParams host_cons;
+  bool staged_io = false;
   if (!q_dev) {
     const size_t qb = static_cast<size_t>(nq) * a->d * 4;
     CKS(a->q_f32.ensure(qb));
     const void* src = q;
     if (!out_dev && qb <= (size_t(64) << 20)) {
-      // host in, host out: the call synchronises before it returns, so a pinned staging buffer can
-      // be reused call after call (one real DMA instead of the driver's chunked pageable copy)
       CKS(a->h_q.ensure(qb));
       memcpy(a->h_q.p, q, qb);
       src = a->h_q.p;
+      // (without the fallback a flagged query keeps the re-rank's provisional row, which only the
+      // device block holds: that diagnostic mode takes the copies)
+      staged_io = !cons && !peer && !any_empty && !(flags & KEDS_SEARCH_NO_FALLBACK) &&
+                  res_per * n_db <= (size_t(256) << 20);
     }
-    CK(cudaMemcpyAsync(a->q_f32.p, src, qb, cudaMemcpyHostToDevice, st));
+    if (staged_io) {
+      const size_t ctrl_bytes = static_cast<size_t>((nq + Q_PASS_MAX - 1) / Q_PASS_MAX) * CTRL_STRIDE * 4;
+      CKS(a->h_out.ensure(res_per * n_db + ctrl_bytes));
+      float* qalias = nullptr;
+      uint8_t* oalias = nullptr;
+      CKS(mapped_alias(static_cast<float*>(a->h_q.p), &qalias));
+      CKS(mapped_alias(static_cast<uint8_t*>(a->h_out.p), &oalias));
+      q_map = qalias;
+      memset(&host_cons, 0, sizeof host_cons);
+      host_cons.enabled = 1;
+      for (int i = 0; i < n_db; ++i) {
+        host_cons.host_I[i] = reinterpret_cast<long long*>(oalias + res_per * i);
+        host_cons.host_D[i] = reinterpret_cast<float*>(oalias + res_per * i + static_cast<size_t>(nq) * k * 8);
+      }
+      cons = &host_cons;
+    } else {
+      CK(cudaMemcpyAsync(a->q_f32.p, src, qb, cudaMemcpyHostToDevice, st));
+    }
     qd = a->q_f32.as<float>();
   }
   float* Dd[2] = {nullptr, nullptr};
@@ -826,10 +847,11 @@ int search_impl(keds_index* ix[2], int n_db, const float* q, int64_t nq, int k, 
   const int n_passes = static_cast<int>((nq + Q_PASS_MAX - 1) / Q_PASS_MAX);
   CKS(a->ctrl.ensure(static_cast<size_t>(n_passes) * CTRL_STRIDE * 4));
   // empty databases answer with padding only
-  bool any_empty = false;
-  for (int i = 0; i < n_db; ++i) any_empty = any_empty || ix[i]->n == 0;
   if (any_empty) {
     if (cons) return fail(KEDS_ERR_ARG, "retrieve2: both databases must hold rows");
+    // no kernel of a chain may run on this handle: its status blocks read as clean
+    CK(cudaMemsetAsync(a->ctrl.p, 0, static_cast<size_t>(n_passes) * CTRL_STRIDE * 4, st));
+    a->ctrl_passes = n_passes;
     for (int i = 0; i < n_db; ++i) {
       if (ix[i]->n != 0) {
         keds_index* one[2] = {ix[i], nullptr};
@@ -862,6 +884,8 @@ int search_impl(keds_index* ix[2], int n_db, const float* q, int64_t nq, int k, 
         for (int s = 0; s < 2; ++s) {
           if (cp.feat[s]) cp.feat[s] += q0 * k * a->d;
           if (cp.pool[s]) cp.pool[s] += q0 * a->d;
+          if (cp.host_D[s]) cp.host_D[s] += q0 * k;
+          if (cp.host_I[s]) cp.host_I[s] += q0 * k;
         }
       }
       PeerOut pp;
@@ -876,14 +900,14 @@ int search_impl(keds_index* ix[2], int n_db, const float* q, int64_t nq, int k, 
       // every pass has its own status block and the scratch is reused in stream order (each kernel
       // of a chain waits for its predecessor to complete), so the passes queue without a host round trip
       CKS(search_pass(ix, n_db, qd + q0 * a->d, nb, k, Dp, Ip, flags, st, nullptr, 0, cons ? &cp : nullptr,
-                      peer ? &pp : nullptr, static_cast<int>(q0 / Q_PASS_MAX)));
+                      peer ? &pp : nullptr, static_cast<int>(q0 / Q_PASS_MAX), q_map ? q_map + q0 * a->d : nullptr));
     }
   }
   if (!out_dev) {
     // results and status words into pinned memory with asynchronous copies, ONE synchronisation,
     // then plain memcpy into the caller's arrays
     const size_t db_ = static_cast<size_t>(nq) * k * 4, ib_ = static_cast<size_t>(nq) * k * 8;
-    const size_t per = db_ + ib_;
+    const size_t per = res_per;
     if (per * n_db > (size_t(256) << 20)) {
       // very large result blocks: not worth pinning that much host memory, copy straight out
       for (int i = 0; i < n_db; ++i) {
@@ -895,9 +919,11 @@ int search_impl(keds_index* ix[2], int n_db, const float* q, int64_t nq, int k, 
     const size_t ctrl_bytes = static_cast<size_t>(a->ctrl_passes) * CTRL_STRIDE * 4;
     CKS(a->h_out.ensure(per * n_db + ctrl_bytes));
     uint8_t* h = static_cast<uint8_t*>(a->h_out.p);
-    for (int i = 0; i < n_db; ++i) {
-      CK(cudaMemcpyAsync(h + per * i, Dd[i], db_, cudaMemcpyDeviceToHost, st));
-      CK(cudaMemcpyAsync(h + per * i + db_, Id[i], ib_, cudaMemcpyDeviceToHost, st));
+    if (!staged_io) {  // (staged_io: the kernels have written the rows here themselves)
+      for (int i = 0; i < n_db; ++i) {
+        CK(cudaMemcpyAsync(h + per * i, Id[i], ib_, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(h + per * i + ib_, Dd[i], db_, cudaMemcpyDeviceToHost, st));
+      }
     }
     uint32_t* hall = reinterpret_cast<uint32_t*>(h + per * n_db);
     memset(hall, 0, ctrl_bytes);
@@ -906,8 +932,8 @@ int search_impl(keds_index* ix[2], int n_db, const float* q, int64_t nq, int k, 
     uint32_t hc[CTRL_WORDS];
     read_status(a, hall, hc);
     for (int i = 0; i < n_db; ++i) {
-      memcpy(D[i], h + per * i, db_);
-      memcpy(I[i], h + per * i + db_, ib_);
+      memcpy(I[i], h + per * i, ib_);
+      memcpy(D[i], h + per * i + ib_, db_);
     }
     a->stats.n_flagged[0] = static_cast<int32_t>(hc[0]);
     a->stats.n_flagged[1] = static_cast<int32_t>(hc[1]);
@@ -1033,7 +1059,7 @@ static int prep_db_rows(keds_index* ix, int64_t r0, int64_t r1) {
   const unsigned blocks = static_cast<unsigned>(std::min<int64_t>((n * 32 + 255) / 256, ix->num_sms * 16));
   k_prep_rows<<<blocks, 256>>>(ix->x_f32.as<float>() + r0 * d, n, ix->d, ix->d_pad, ix->fmt,
                                ix->x_bf16.as<uint16_t>() + r0 * dp, nullptr, ix->bias.as<float>() + r0,
-                               ix->dbstat.as<unsigned int>(), nullptr, 0, nullptr, 0, nullptr);
+                               ix->dbstat.as<unsigned int>(), nullptr, 0, nullptr, 0, nullptr, nullptr);
   CK(cudaGetLastError());
   return 0;
 }
@@ -1149,14 +1175,6 @@ int keds_index_set_pdl(keds_index_t* ix, int enable) {
   return 0;
 }
 
-int keds_index_set_stream_rerank(keds_index_t* ix, int enable) {
-  if (!ix) return fail(KEDS_ERR_ARG, "set_stream_rerank: null handle");
-  DeviceGuard g(ix->device);
-  CKS(set_kernel_attrs(ix));
-  ix->stream_rerank = enable != 0;
-  return 0;
-}
-
 int keds_index_set_eps_scale(keds_index_t* ix, float scale) {
   if (!ix || !(scale >= 0.f)) return fail(KEDS_ERR_ARG, "set_eps_scale: bad argument");
   ix->eps_scale = scale;
@@ -1184,16 +1202,23 @@ int keds_index_search2(keds_index_t* a, keds_index_t* b, const float* q, int64_t
   return search_impl(v, 2, q, nq, k, Dv, Iv, flags, stream);
 }
 
-int keds_retrieve2(keds_index_t* img, keds_index_t* txt, const float* q, int64_t nq, int k,
+}  // extern "C"
+
+namespace {
+
+int retrieve2_impl(keds_index_t* img, keds_index_t* txt, const float* q, int64_t nq, int k,
                    const int32_t* perm_img, const int32_t* perm_txt, int pool_mode, float tau,
                    float* D_img, int64_t* I_img, float* D_txt, int64_t* I_txt, float* feat_img,
-                   float* feat_txt, float* pool_img, float* pool_txt, uint32_t flags, void* stream) {
+                   float* feat_txt, float* pool_img, float* pool_txt, uint32_t flags, void* stream,
+                   bool hostio, float* Dh_img, int64_t* Ih_img, float* Dh_txt, int64_t* Ih_txt) {
   if (!img || !txt || !q || !D_img || !I_img || !D_txt || !I_txt)
     return fail(KEDS_ERR_ARG, "retrieve2: null handle, query or result pointer");
   if (pool_mode < 0 || pool_mode > 2) return fail(KEDS_ERR_ARG, "retrieve2: pool_mode must be 0, 1 or 2");
-  if (!is_device_ptr(q) || !is_device_ptr(D_img) || !is_device_ptr(I_img) || !is_device_ptr(D_txt) ||
+  if ((!hostio && !is_device_ptr(q)) || !is_device_ptr(D_img) || !is_device_ptr(I_img) || !is_device_ptr(D_txt) ||
       !is_device_ptr(I_txt))
     return fail(KEDS_ERR_ARG, "retrieve2: device pointers only");
+  if ((Dh_img == nullptr) != (Ih_img == nullptr) || (Dh_txt == nullptr) != (Ih_txt == nullptr))
+    return fail(KEDS_ERR_ARG, "retrieve2_hostio: a host mirror needs both its D and its I block");
   if (k > 1024) return fail(KEDS_ERR_ARG, "retrieve2: k=%d too large for the fused consumer", k);
   keds_index* v[2] = {img, txt};
   float* Dv[2] = {D_img, D_txt};
@@ -1201,7 +1226,18 @@ int keds_retrieve2(keds_index_t* img, keds_index_t* txt, const float* q, int64_t
   const bool want_pool = pool_mode != 0 && (pool_img || pool_txt);
   ConsumeParams cp;
   memset(&cp, 0, sizeof cp);
-  cp.enabled = (feat_img || feat_txt || want_pool) ? 1 : 0;
+  {
+    DeviceGuard g(img->device);
+    if (!g.ok) return fail(KEDS_ERR_NO_GPU, "cannot select CUDA device %d", img->device);
+    long long* ih[2] = {nullptr, nullptr};
+    CKS(mapped_alias(Dh_img, &cp.host_D[0]));
+    CKS(mapped_alias(reinterpret_cast<long long*>(Ih_img), &ih[0]));
+    CKS(mapped_alias(Dh_txt, &cp.host_D[1]));
+    CKS(mapped_alias(reinterpret_cast<long long*>(Ih_txt), &ih[1]));
+    cp.host_I[0] = ih[0];
+    cp.host_I[1] = ih[1];
+  }
+  cp.enabled = (feat_img || feat_txt || want_pool || Dh_img || Dh_txt) ? 1 : 0;
   cp.mode = want_pool ? pool_mode : 0;
   cp.tau = tau;
   cp.perm[0] = perm_img;
@@ -1213,7 +1249,28 @@ int keds_retrieve2(keds_index_t* img, keds_index_t* txt, const float* q, int64_t
   // one warp per neighbour row; per-warp partial pools meet in shared memory ([warps][d/4] float4)
   static_assert(RERANK_THREADS == EXACT_THREADS, "the consumer scratch is sized for one block shape");
   cp.part4 = (img->d & 3) == 0 ? (RERANK_THREADS / 32) * (img->d >> 2) : 0;
-  return search_impl(v, 2, q, nq, k, Dv, Iv, flags, stream, cp.enabled ? &cp : nullptr);
+  return search_impl(v, 2, q, nq, k, Dv, Iv, flags, stream, cp.enabled ? &cp : nullptr, nullptr, hostio);
+}
+
+}  // namespace
+
+extern "C" {
+
+int keds_retrieve2(keds_index_t* img, keds_index_t* txt, const float* q, int64_t nq, int k,
+                   const int32_t* perm_img, const int32_t* perm_txt, int pool_mode, float tau,
+                   float* D_img, int64_t* I_img, float* D_txt, int64_t* I_txt, float* feat_img,
+                   float* feat_txt, float* pool_img, float* pool_txt, uint32_t flags, void* stream) {
+  return retrieve2_impl(img, txt, q, nq, k, perm_img, perm_txt, pool_mode, tau, D_img, I_img, D_txt, I_txt, feat_img,
+                        feat_txt, pool_img, pool_txt, flags, stream, false, nullptr, nullptr, nullptr, nullptr);
+}
+
+int keds_retrieve2_hostio(keds_index_t* img, keds_index_t* txt, const float* q, int64_t nq, int k,
+                          const int32_t* perm_img, const int32_t* perm_txt, int pool_mode, float tau,
+                          float* D_img, int64_t* I_img, float* D_txt, int64_t* I_txt, float* Dh_img,
+                          int64_t* Ih_img, float* Dh_txt, int64_t* Ih_txt, float* feat_img, float* feat_txt,
+                          float* pool_img, float* pool_txt, uint32_t flags, void* stream) {
+  return retrieve2_impl(img, txt, q, nq, k, perm_img, perm_txt, pool_mode, tau, D_img, I_img, D_txt, I_txt, feat_img,
+                        feat_txt, pool_img, pool_txt, flags, stream, true, Dh_img, Ih_img, Dh_txt, Ih_txt);
 }
 
 int keds_index_sync(keds_index_t* ix, void* stream) {
@@ -1343,7 +1400,6 @@ int keds_debug_plan(int n_db, int64_t nq, int k, int64_t n_rows, int num_sms, in
     return fail(KEDS_ERR_ARG, "debug_plan: bad argument");
   keds_index ix;  // never touches the device: only the planner's inputs are read
   ix.num_sms = num_sms;
-  ix.d = ix.d_pad = 768;  // the planner weighs the database's bytes against L2: the reference's 768-d rows
   const char* no_pair = getenv("KEDS_NO_PAIR");
   ix.use_pair = !(no_pair && no_pair[0] == '1');
   const Plan pl = make_plan(&ix, n_db, nq, k, n_rows, n_rows, 0u);
@@ -1671,7 +1727,8 @@ int keds_index_rank(keds_index_t* ix, const float* q, int64_t nq, const int64_t*
       CKS(launch_k(ix->use_pdl, k_prep_rows, dim3(blocks), dim3(256), 0, st, qp, static_cast<long long>(nb), d,
                    ix->d_pad, ix->fmt, ix->q_bf16.as<uint16_t>(), ix->qstat.as<float4>(), static_cast<float*>(nullptr),
                    static_cast<unsigned int*>(nullptr), ix->ctrl.as<unsigned int>(), CTRL_WORDS,
-                   static_cast<float*>(nullptr), 0, static_cast<unsigned long long*>(nullptr)));
+                   static_cast<float*>(nullptr), 0, static_cast<unsigned long long*>(nullptr),
+                   static_cast<float*>(nullptr)));
     }
     const unsigned wblocks = static_cast<unsigned>((nb * 32 + 255) / 256);
     CKS(launch_k(ix->use_pdl, k_rank_targets, dim3(wblocks), dim3(256), 0, st, qp, static_cast<long long>(nb), G, d,

@@ -171,7 +171,7 @@ __global__ void k_prep_rows(const float* __restrict__ x, long long n, int d, int
                             float* __restrict__ bias, unsigned int* __restrict__ gmax,
                             unsigned int* __restrict__ zero_words, int n_zero,
                             float* __restrict__ neg_inf_words, int n_neg_inf,
-                            unsigned long long* timing) {
+                            unsigned long long* timing, float* __restrict__ copy_f32) {
   const int lane = threadIdx.x & 31;
   griddep_wait();               // earlier kernels of the stream may still read what is rewritten here
   griddep_launch_dependents();  // the scoring kernel may start its prologue
@@ -199,6 +199,9 @@ __global__ void k_prep_rows(const float* __restrict__ x, long long n, int d, int
 #pragma unroll 4
       for (int c = lane; c < dp4; c += 32) {
         const float4 v = c < d4 ? __ldg(x4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        // x in page-locked host memory (read through the mapping, once): the kernels behind this
+        // one take the fp32 rows from this device copy
+        if (copy_f32 != nullptr && c < d4) reinterpret_cast<float4*>(copy_f32 + r * d)[c] = v;
         float4 f;
         uint2 pk;
         pk.x = round_pair(fmt, v.x, v.y, f.x, f.y, bad);
@@ -215,6 +218,7 @@ __global__ void k_prep_rows(const float* __restrict__ x, long long n, int d, int
     } else {
       for (int c = lane; c < d_pad; c += 32) {
         const float v = c < d ? xr[c] : 0.f;
+        if (copy_f32 != nullptr && c < d) copy_f32[r * d + c] = v;
         float bf, unused;
         const unsigned int pk = round_pair(fmt, v, 0.f, bf, unused, bad);
         orow[c] = static_cast<uint16_t>(pk & 0xFFFFu);
@@ -329,7 +333,27 @@ struct ConsumeParams {
   const int* perm[2];
   float* feat[2];   // [nq][k][d]
   float* pool[2];   // [nq][d]
+  // Host mirror of the result rows ([nq][k] each, page-locked host memory addressed through its
+  // device mapping, nullable): the block that has a query's final row stores it there as well, so
+  // the (D, I) the reference reads on the host need no copy behind the search.
+  float* host_D[2];
+  long long* host_I[2];
 };
+
+// One query's final row to the host mirror (called by every thread of the block, row complete in
+// shared memory). Posted writes: they are on their way while the block goes on to the consumer.
+__device__ __forceinline__ void mirror_row_to_host(const ConsumeParams& c, int s, long long q, int k,
+                                                   const unsigned int* top_id, const float* top_d,
+                                                   long long id_offset, int metric) {
+  float* Dh = c.host_D[s] + q * k;
+  long long* Ih = c.host_I[s] + q * k;
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    const unsigned int id = top_id[j];
+    const bool pad = id == 0xFFFFFFFFu;
+    Dh[j] = pad ? (metric == METRIC_L2 ? FLT_MAX : -FLT_MAX) : top_d[j];
+    Ih[j] = pad ? -1ll : static_cast<long long>(id) + id_offset;
+  }
+}
 
 // Row-sharded exchange fused into the search (p2p_exchange.cuh): the block that has ranked query b
 // also stores that [k] result row into every peer's receive buffer (NVLink P2P stores), and the

@@ -380,6 +380,8 @@ __device__ __forceinline__ void exact_select(const ExactParams& p, uint8_t* ex_s
     if (p.cons.enabled || (p.peer.n > 1 && dbi == 0)) {
       __syncthreads();
       if (p.peer.n > 1 && dbi == 0) push_row_to_peers(p.peer, q, p.k, top_id, top_d, e.id_offset, p.metric);
+      if (p.cons.enabled && p.cons.host_D[dbi] != nullptr)
+        mirror_row_to_host(p.cons, dbi, q, p.k, top_id, top_d, e.id_offset, p.metric);
       if (p.cons.enabled)
         consume_query<1>(p.cons, e.x_f32, dbi, q, p.k, p.d, p.metric, top_id, top_d, top_w, part);
     }

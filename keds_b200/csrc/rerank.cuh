@@ -36,14 +36,6 @@ struct RerankParams {
   unsigned int* band_max;    // status word: largest |C| of this search (feeds the planner's next slice count)
   PeerOut peer;              // row-sharded exchange (database 0 only); n == 0: off
   unsigned long long* timing;  // nullable in-kernel launch timer
-  // Streamed re-rank (large batches on the CTA-pair scoring kernel): the scoring kernel finishes
-  // query tiles one wave after the other and counts the finished epilogue warps per (database,
-  // tile) in qt_done; a block here does not wait for the whole scoring grid (griddepcontrol.wait)
-  // but for its own tile's counter, so the re-rank of early tiles runs on the shared memory and
-  // issue slots the scoring CTAs leave free while later tiles are still being scored.
-  const unsigned int* qt_done;  // nullptr: off (2-D grid {query, database}, griddepcontrol.wait)
-  unsigned int done_target;     // arrivals that complete a tile: slices * epilogue warps
-  unsigned int* err;            // device error word (bounded spin)
 };
 
 constexpr unsigned int PAD_ID = 0xFFFFFFFFu;
@@ -55,20 +47,7 @@ template <int R, int MINB>
 __global__ void __launch_bounds__(RERANK_THREADS, MINB)
 k_select_rerank(const RerankParams p) {
   extern __shared__ uint8_t rr_smem[];
-  int q = blockIdx.x, db = blockIdx.y;
-  const bool streamed = p.qt_done != nullptr;
-  if (streamed) {
-    // 1-D grid in the order the scoring kernel finishes its work: (pair of query tiles, database, query)
-    const int per_g = 2 * BM * p.n_db;
-    const int g = blockIdx.x / per_g, r = blockIdx.x - g * per_g;
-    db = r / (2 * BM);
-    q = g * 2 * BM + (r - db * 2 * BM);
-    if (q >= p.nq) {
-      // (see the end of the kernel: the grid's last block ties this grid's completion to the scoring grid's)
-      if (blockIdx.x == gridDim.x - 1) griddep_wait();
-      return;
-    }
-  }
+  const int q = blockIdx.x, db = blockIdx.y;
   const int qt = q / BM, ql = q % BM;
   const int slots = p.S * LKEEP;
   // shared layout
@@ -98,36 +77,7 @@ k_select_rerank(const RerankParams p) {
   const float xb = __uint_as_float(p.dbstat[db][0]);
   const float xd = __uint_as_float(p.dbstat[db][1]);
   const float xn2 = __uint_as_float(p.dbstat[db][2]);
-  if (streamed) {
-    // k_prep_rows finished before the scoring kernel let this grid launch; the candidate lines of
-    // this query's tile are acquired through the tile's counter. Bounded: a scoring kernel that
-    // died must not leave this grid spinning.
-    if (tid == 0) {
-      const unsigned int* cnt = p.qt_done + db * p.n_qt + qt;
-      unsigned long long t0 = 0ull;
-      bcast[0] = 0u;
-      while (ld_acquire_gpu(cnt) < p.done_target) {
-        __nanosleep(200);
-        const unsigned long long now = global_timer_ns();
-        if (t0 == 0ull) t0 = now;
-        else if (now - t0 > 4000000000ull) {
-          atomicCAS(p.err, 0u, 0x700u);
-          bcast[0] = 1u;
-          break;
-        }
-      }
-    }
-    __syncthreads();
-    if (bcast[0] != 0u) {
-      for (int r = tid; r < p.k; r += blockDim.x) {
-        p.D[db][static_cast<long long>(q) * p.k + r] = p.metric == METRIC_L2 ? FLT_MAX : -FLT_MAX;
-        p.I[db][static_cast<long long>(q) * p.k + r] = -1;
-      }
-      return;
-    }
-  } else {
-    griddep_wait();  // candidates (and qstat from k_prep_rows) are visible from here on
-  }
+  griddep_wait();  // candidates (and qstat from k_prep_rows) are visible from here on
   const unsigned long long t_start = ktimer_begin(p.timing);
 
   // ---- A: every slice's candidate line, count and threshold in one round trip.
@@ -402,14 +352,12 @@ k_select_rerank(const RerankParams p) {
     __syncthreads();  // (7)
     if (p.peer.n > 1 && db == 0)
       push_row_to_peers(p.peer, q, p.k, top_id, top_d, p.id_offset[db], p.metric);
+    if (p.cons.enabled && p.cons.host_D[db] != nullptr)
+      mirror_row_to_host(p.cons, db, q, p.k, top_id, top_d, p.id_offset[db], p.metric);
     if (p.cons.enabled)
       consume_query<(R >= 2 ? 2 : 1)>(p.cons, xbase, db, q, p.k, p.d, p.metric, top_id, top_d, top_w, part);
   }
   ktimer_end(p.timing, t_start);
-  // Streamed: no block has waited for the scoring GRID, only for its counters. The last block does
-  // so now (the scoring CTAs are past their last arrival and about to exit), so that "this grid
-  // has completed" still implies "the scoring grid has completed" for whatever follows in the stream.
-  if (streamed && blockIdx.x == gridDim.x - 1) griddep_wait();
 }
 
 }  // namespace keds

@@ -77,11 +77,7 @@ struct ScoreParams {
   int n_qt;          // query tiles of BM
   int n_qg;          // query groups per (db, slice): n_qt (single CTA) or ceil(n_qt / 2) (pair)
   int S;             // row slices per (db, query tile); the pair variant writes 2 candidate lines per slice
-  int n_items;       // n_db * S * n_qg ; item order: (wave of W query groups, db, slice, group in the wave)
-  int W;             // query groups per wave. W = n_qg: every list of a query finishes near the end of the
-                     // kernel (rows stream from HBM once). Small W: query groups finish one after the
-                     // other, so the re-rank of the early ones runs under the scoring of the later ones
-                     // (qt_done), at the price of one pass over the rows per wave.
+  int n_items;       // n_db * S * n_qg ; item = ((db * S) + s) * n_qg + qg
   int kblocks;       // d_pad / BK
   uint32_t fmt_bits; // operand format bits of the instruction descriptor (kIdescBf16Bits, or 0 = fp16)
   int nq;            // live queries
@@ -93,8 +89,6 @@ struct ScoreParams {
   float* cand_theta; // [..][BM]  everything the slice dropped scored <= theta
   float* theta0;     // [n_db][theta_ld] running per-query drop threshold shared by all lists of a query (see epilogue)
   int theta_ld;
-  unsigned int* qt_done;  // nullable: [n_db][n_qt] finished epilogue warps per query tile (release counters
-                          // the streamed re-rank acquires: S * kEpiWarps arrivals = every list of the tile is out)
   uint32_t* err;     // device error word (0 = ok)
   float* dump;       // debug: full approx scores [n_db][nq][ld_dump], or nullptr
   long long ld_dump;
@@ -113,14 +107,8 @@ struct ItemCoord {
 
 __device__ __forceinline__ ItemCoord decode_item(const ScoreParams& p, int item) {
   ItemCoord c;
-  // full waves come first, so the wave index needs no special case for the ragged last one
-  const int W = p.W > 0 ? p.W : p.n_qg;
-  const int per_wave = p.n_db * p.S * W;
-  const int w = item / per_wave;
-  const int r = item - w * per_wave;
-  const int ww = min(W, p.n_qg - w * W);
-  c.qg = w * W + r % ww;
-  const int t = r / ww;
+  c.qg = item % p.n_qg;
+  const int t = item / p.n_qg;
   c.s = t % p.S;
   c.db = t / p.S;
   const long long T = p.n_tiles[c.db];
@@ -556,15 +544,6 @@ k_score_topk(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
             if (theta >= 0.f) atomicMax(reinterpret_cast<int*>(th0), __float_as_int(theta));
             else atomicMin(reinterpret_cast<unsigned int*>(th0), __float_as_uint(theta));
           }
-        }
-      }
-      if constexpr (!kRank) {
-        // streamed re-rank: this warp's lines of the item are out -- release them to the re-rank
-        // block that spins on the tile's counter (every lane fences its own stores, then one arrival)
-        if (p.qt_done != nullptr) {
-          __threadfence();
-          __syncwarp();
-          if (lane == 0 && (!kPair || qt < p.n_qt)) atomicAdd(p.qt_done + c.db * p.n_qt + qt, 1u);
         }
       }
       __syncwarp();

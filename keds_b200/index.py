@@ -153,10 +153,6 @@ class GpuIndexFlat:
     def set_pdl(self, enable: bool) -> None:
         _capi.check(self._lib.keds_index_set_pdl(self._h, int(bool(enable))))
 
-    def set_stream_rerank(self, enable: bool) -> None:
-        """Large batches: re-rank blocks start on their query tile's completion counter (default on)."""
-        _capi.check(self._lib.keds_index_set_stream_rerank(self._h, int(bool(enable))))
-
     def set_eps_scale(self, scale: float) -> None:
         _capi.check(self._lib.keds_index_set_eps_scale(self._h, float(scale)))
 
@@ -259,7 +255,6 @@ class GpuIndexFlat:
             "exact_only": int(st.exact_only),
             "launches": int(st.launches),
             "err_word": int(st.err_word),
-            "streamed": int(st.streamed),
         }
 
     def set_profiling(self, mode: int) -> None:

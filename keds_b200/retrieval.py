@@ -19,6 +19,7 @@ tensors + database_names.txt) and builds one native index per database on the lo
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -144,14 +145,26 @@ POOL_NONE, POOL_MEAN, POOL_SOFTMAX = 0, 1, 2
 def retrieve2(image_index: GpuIndexFlat, text_index: GpuIndexFlat, q: torch.Tensor, topk: int = 16,
               perm_img: Optional[torch.Tensor] = None, perm_txt: Optional[torch.Tensor] = None,
               want_feats: bool = True, pool_mode: int = POOL_NONE, tau: float = 100.0, flags: int = 0,
-              out: Optional[dict] = None) -> dict:
+              out: Optional[dict] = None, host_out: Optional[dict] = None) -> dict:
     """One native call for the whole operator: fused two-database search, then for each stream the
     gathered neighbours [B, k, d] (image stream permuted by perm_img) and/or the pooled stream
     [B, d].  `out` may carry preallocated tensors from a previous call (keys as returned) so a
-    steady-state loop allocates nothing."""
+    steady-state loop allocates nothing.
+
+    Host I/O without copies (keds_retrieve2_hostio): `q` may be a pinned CPU tensor -- the first
+    kernel reads it through the device mapping -- and `host_out` may hold pinned CPU tensors
+    D_img / I_img / D_txt / I_txt ([B, k]) that the kernels fill next to the device results; they
+    are complete once the stream has been synchronised."""
     lib = _capi.load()
-    q = image_index._check_q_tensor(q)
-    dev, B, d, k = q.device, q.shape[0], image_index.d, int(topk)
+    hostio = host_out is not None or not q.is_cuda
+    if q.is_cuda:
+        q = image_index._check_q_tensor(q)
+        dev = q.device
+    else:
+        if not q.is_pinned() or q.dtype != torch.float32 or q.dim() != 2 or q.shape[1] != image_index.d or not q.is_contiguous():
+            raise TypeError("retrieve2: a host query must be a pinned, contiguous float32 [B, d] tensor")
+        dev = torch.device("cuda", image_index.device)
+    B, d, k = q.shape[0], image_index.d, int(topk)
     o = out if out is not None else {}
 
     def buf(name, shape, dtype):
@@ -179,6 +192,21 @@ def retrieve2(image_index: GpuIndexFlat, text_index: GpuIndexFlat, q: torch.Tens
     pi_ptr, _keep1 = perm_ptr(perm_img)
     pt_ptr, _keep2 = perm_ptr(perm_txt)
     ptr = lambda t: 0 if t is None else t.data_ptr()
+    if hostio:
+        ho = host_out or {}
+        hp = []
+        for name, dt in (("D_img", torch.float32), ("I_img", torch.int64), ("D_txt", torch.float32), ("I_txt", torch.int64)):
+            t = ho.get(name)
+            if t is not None and not (t.is_pinned() and t.dtype == dt and t.is_contiguous() and t.numel() == B * k):
+                raise TypeError(f"retrieve2: host_out[{name!r}] must be a pinned contiguous {dt} tensor of {B * k} elements")
+            hp.append(0 if t is None else t.data_ptr())
+        _capi.check(
+            lib.keds_retrieve2_hostio(image_index._h, text_index._h, q.data_ptr(), B, k, pi_ptr, pt_ptr, int(pool_mode),
+                                      float(tau), Di.data_ptr(), Ii.data_ptr(), Dt.data_ptr(), It.data_ptr(),
+                                      hp[0], hp[1], hp[2], hp[3], ptr(fi), ptr(ft), ptr(pi), ptr(pt), int(flags),
+                                      _stream_ptr(image_index.device))
+        )
+        return o
     _capi.check(
         lib.keds_retrieve2(image_index._h, text_index._h, q.data_ptr(), B, k, pi_ptr, pt_ptr, int(pool_mode),
                            float(tau), Di.data_ptr(), Ii.data_ptr(), Dt.data_ptr(), It.data_ptr(), ptr(fi),
@@ -200,8 +228,15 @@ class RetrievalStep:
 
     def __init__(self, image_index: GpuIndexFlat, text_index: GpuIndexFlat, batch: int, topk: int = 16,
                  perm_img: Optional[torch.Tensor] = None, want_feats: bool = True,
-                 pool_mode: int = POOL_NONE, tau: float = 100.0) -> None:
+                 pool_mode: int = POOL_NONE, tau: float = 100.0, copy_nodes: Optional[bool] = None) -> None:
         self.ia, self.ib = image_index, text_index
+        # copy_nodes=False (default): no copies in the graph -- the first kernel reads the pinned
+        # queries through the mapping and the ranking blocks store (D, I) into the pinned result
+        # block next to the device one (keds_retrieve2_hostio). True: H2D + D2H copy nodes around
+        # the search (the round-1 layout; KEDS_STEP_COPY_NODES=1 selects it for A/B runs).
+        if copy_nodes is None:
+            copy_nodes = os.environ.get("KEDS_STEP_COPY_NODES", "0") == "1"
+        self.copy_nodes = bool(copy_nodes)
         dev = torch.device("cuda", image_index.device)
         d, k = image_index.d, int(topk)
         self.q_host = torch.empty((batch, d), dtype=torch.float32).pin_memory()
@@ -221,6 +256,7 @@ class RetrievalStep:
         Ii, It, Di, Dt = views(self._res_dev)
         self.perm = None if perm_img is None else perm_img.to(device=dev, dtype=torch.int32).contiguous()
         self.out: dict = {"I_img": Ii, "I_txt": It, "D_img": Di, "D_txt": Dt}
+        self._host_out = {"I_img": self.I_img, "I_txt": self.I_txt, "D_img": self.D_img, "D_txt": self.D_txt}
         self._args = dict(topk=k, perm_img=self.perm, want_feats=want_feats, pool_mode=pool_mode, tau=tau)
         self.h2d_bytes = self.q_host.numel() * 4
         self.d2h_bytes = sum(t.numel() * t.element_size() for t in (self.D_img, self.D_txt, self.I_img, self.I_txt))
@@ -252,9 +288,12 @@ class RetrievalStep:
         self.recaptures += 1
 
     def _body(self) -> None:
-        self.q_dev.copy_(self.q_host, non_blocking=True)
-        retrieve2(self.ia, self.ib, self.q_dev, out=self.out, **self._args)
-        self._res_host.copy_(self._res_dev, non_blocking=True)
+        if self.copy_nodes:
+            self.q_dev.copy_(self.q_host, non_blocking=True)
+            retrieve2(self.ia, self.ib, self.q_dev, out=self.out, **self._args)
+            self._res_host.copy_(self._res_dev, non_blocking=True)
+        else:
+            retrieve2(self.ia, self.ib, self.q_host, out=self.out, host_out=self._host_out, **self._args)
 
     def run(self, q: Optional[torch.Tensor] = None, sync: bool = True) -> dict:
         if q is not None:

@@ -179,47 +179,11 @@ def test_config1_4096_queries_vs_50k_rows():
     assert st["exact_only"] == 0 and st["n_flagged"][0] < 64   # the tensor-core path answered
 
 
-def _plain_rerank_index(db, metric):
-    """an index whose re-rank blocks wait for the whole scoring grid"""
-    ix = build(db, metric)
-    ix.set_stream_rerank(False)
-    return ix
-
-
-@pytest.mark.parametrize("metric", ["ip", "l2"])
-@pytest.mark.parametrize("n,b,k", [(50000, 4096, 16), (30000, 1000, 16), (20000, 1408, 64), (70000, 2049, 16)])
-def test_streamed_rerank_equals_the_plain_chain_and_the_oracle(n, b, k, metric):
-    """Large batches: the scoring kernel finishes query tiles wave by wave and the re-rank blocks of
-    a tile start on its counter instead of the scoring grid's completion (rerank.cuh). Same lists,
-    same arithmetic: the answer must equal the plain chain's bit for bit, ragged batches (1000
-    queries: the last CTA pair works on one tile; 2049: a tile with a single query) included, and
-    both must satisfy the oracle."""
-    db, q = unit(n, 768, 4000 + n % 97), unit(b, 768, 4100 + b % 89)
-    ix = build(db, metric)
-    qd = torch.from_numpy(q).cuda()
-    D, I = ix.search(qd, k)
-    ix.sync()
-    st = ix.last_stats()
-    assert st["streamed"] >= 1 and st["exact_only"] == 0 and st["err_word"] == 0, st
-    ref = _plain_rerank_index(db, metric)
-    D0, I0 = ref.search(qd, k)
-    ref.sync()
-    assert ref.last_stats()["streamed"] == 0
-    assert torch.equal(I, I0) and torch.equal(D, D0)
-    sub = np.linspace(0, b - 1, 96).astype(np.int64)
-    Dr, Ir = orc.search(db, q[sub], k, metric)
-    c = orc.compare_topk(Dr, Ir, D.cpu().numpy()[sub], I.cpu().numpy()[sub], db, q[sub], metric, TIE_GAP, D_TOL)
-    assert c["ok"], (c, st)
-    for _ in range(3):   # the counters are re-armed by every search
-        D2, I2 = ix.search(qd, k)
-    ix.sync()
-    assert torch.equal(I2, I) and torch.equal(D2, D) and ix.last_stats()["err_word"] == 0
-
-
-def test_streamed_rerank_two_databases_with_the_consumer_and_several_passes():
-    """The streamed chain under the fused two-database retrieval (gather + pool inside the re-rank
-    blocks) and across the passes of a 17,000-query call, which now queue without a host round trip
-    (one status block per pass): flagged counts add up over the passes."""
+def test_passes_queue_without_a_host_round_trip_and_their_status_adds_up():
+    """A 17,000-query call runs as two passes that queue on the stream (one status block per pass,
+    read once at the end): the fused two-database retrieval with the consumer across the seam,
+    flagged counts summed over the passes, and the large-batch chain on ragged batches (1000
+    queries: the last CTA pair works on one tile; 2049: a tile with a single query)."""
     a, b = unit(40000, 768, 4200), unit(40000, 768, 4201)
     q = unit(17000, 768, 4202)
     ia, ib = build(a, "ip"), build(b, "ip")
@@ -228,7 +192,7 @@ def test_streamed_rerank_two_databases_with_the_consumer_and_several_passes():
     o = kr.retrieve2(ia, ib, qd, 16, perm_img=perm, want_feats=True, pool_mode=kr.POOL_SOFTMAX, tau=50.0)
     ia.sync()
     st = ia.last_stats()
-    assert st["streamed"] >= 1 and st["err_word"] == 0, st
+    assert st["err_word"] == 0 and st["exact_only"] == 0, st
     sub = np.concatenate([np.arange(0, 17000, 173), [16383, 16384, 16385, 16999]])
     for name, db, ix_perm in (("img", a, perm.numpy()), ("txt", b, None)):
         D, I = o[f"D_{name}"].cpu().numpy()[sub], o[f"I_{name}"].cpu().numpy()[sub]
@@ -244,6 +208,16 @@ def test_streamed_rerank_two_databases_with_the_consumer_and_several_passes():
     assert ia.last_stats()["n_flagged"][0] == 17000
     ia.set_eps_scale(1.0)
     assert torch.equal(I1, o["I_img"])
+    for n, nb, k, metric in ((30000, 1000, 16, "l2"), (70000, 2049, 16, "ip"), (20000, 1408, 64, "l2")):
+        db, qq = unit(n, 768, 4000 + n % 97), unit(nb, 768, 4100 + nb % 89)
+        ix = build(db, metric)
+        D, I = ix.search(torch.from_numpy(qq).cuda(), k)
+        ix.sync()
+        assert ix.last_stats()["exact_only"] == 0
+        sub = np.linspace(0, nb - 1, 64).astype(np.int64)
+        Dr, Ir = orc.search(db, qq[sub], k, metric)
+        c = orc.compare_topk(Dr, Ir, D.cpu().numpy()[sub], I.cpu().numpy()[sub], db, qq[sub], metric, TIE_GAP, D_TOL)
+        assert c["ok"], (n, nb, k, metric, c)
 
 
 def test_more_queries_than_one_pass_holds():
@@ -602,6 +576,50 @@ def test_graph_captured_retrieval_step_matches_the_stream_path():
 
 
 # ------------------------------------------------------------------ reference-shaped operators vs golden
+def test_host_io_through_the_mapping_equals_the_copy_path():
+    """keds_retrieve2_hostio: pinned host queries read by the first kernel through the mapping and
+    (D, I) mirrored into pinned host blocks by the ranking blocks -- same answers as device queries
+    + copies, for certified queries, for flagged ones (mirrored by the exact fallback), for a
+    database small enough to go to the exact kernels only, and across a pass seam."""
+    a, b = unit(9000, 768, 191), unit(9000, 768, 192)
+    ia, ib = build(a, "l2"), build(b, "l2")
+    perm = torch.randperm(16, generator=torch.Generator().manual_seed(5))
+
+    def both(ia, ib, q, eps=1.0):
+        qh = torch.from_numpy(q).pin_memory()
+        B = q.shape[0]
+        ho = {"D_img": torch.zeros((B, 16)).pin_memory(), "I_img": torch.zeros((B, 16), dtype=torch.int64).pin_memory(),
+              "D_txt": torch.zeros((B, 16)).pin_memory(), "I_txt": torch.zeros((B, 16), dtype=torch.int64).pin_memory()}
+        ia.set_eps_scale(eps)
+        o = kr.retrieve2(ia, ib, qh, 16, perm_img=perm, want_feats=True, pool_mode=kr.POOL_SOFTMAX, tau=50.0, host_out=ho)
+        ia.sync()
+        st = ia.last_stats()
+        r = kr.retrieve2(ia, ib, torch.from_numpy(q).cuda(), 16, perm_img=perm, want_feats=True, pool_mode=kr.POOL_SOFTMAX, tau=50.0)
+        ia.sync()
+        ia.set_eps_scale(1.0)
+        for key in ("D_img", "I_img", "D_txt", "I_txt"):
+            assert torch.equal(o[key], r[key]), key
+            assert torch.equal(ho[key], r[key].cpu()), key
+        for key in ("feat_img", "feat_txt", "pool_img", "pool_txt"):
+            assert torch.equal(o[key], r[key]), key
+        return st, ho
+
+    q = unit(70, 768, 193)
+    st, ho = both(ia, ib, q)
+    assert st["n_flagged"] == [0, 0] and st["exact_only"] == 0
+    Dr, Ir = orc.search(a, q, 16, "l2")
+    assert orc.compare_topk(Dr, Ir, ho["D_img"].numpy(), ho["I_img"].numpy(), a, q, "l2", TIE_GAP, D_TOL)["ok"]
+    st, _ = both(ia, ib, q, eps=1e4)              # every query flagged: the fallback mirrors the rows
+    assert st["n_flagged"] == [70, 70]
+    sa, sb = build(a[:200], "ip"), build(b[:200], "ip")
+    st, _ = both(sa, sb, q)                       # exact kernels only (no k_prep_rows in the chain)
+    assert st["exact_only"] == 1
+    ca, cb = build(unit(3000, 64, 194), "ip"), build(unit(3000, 64, 195), "ip")
+    both(ca, cb, unit(16384 + 300, 64, 196))      # two passes: the mirrors follow the pass offsets
+    with pytest.raises(Exception):
+        kr.retrieve2(ia, ib, torch.from_numpy(q), 16)   # pageable host memory is refused
+
+
 def test_get_retrieved_features_matches_the_reference_outputs(golden_dir):
     z = np.load(os.path.join(golden_dir, "retrieval.npz"))
     ib, tb = torch.from_numpy(z["image_base"]), torch.from_numpy(z["text_base"])

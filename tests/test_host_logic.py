@@ -126,9 +126,7 @@ def test_planner_large_k_buys_slices_against_fallbacks():
     prefer 74 lists -- 37 slices in the CTA-pair kernel, which keeps one list per column half."""
     assert _plan(1, 4096, 64, 1_000_000)["S"] == 37
     assert _plan(1, 4096, 16, 500_000)["S"] == 23           # small k: unchanged by the fallback term
-    # short database, streamed re-rank: four rounds of work items instead of two (same longest CTA), so
-    # that three quarters of the queries are re-ranked under the scoring of the rest
-    assert _plan(1, 4096, 16, 50_000)["S"] == 18
+    assert _plan(1, 4096, 16, 50_000)["S"] == 9             # short database: few, long slices (two rounds of items)
 
 
 def test_parallel_runner_keeps_order_and_raises_the_first_error():
