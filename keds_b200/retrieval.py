@@ -65,6 +65,24 @@ def weighted_pool(index: GpuIndexFlat, I: torch.Tensor, W: torch.Tensor) -> torc
     return out
 
 
+def search_gather(index: GpuIndexFlat, q: torch.Tensor, k: int, bases: Optional[GpuIndexFlat] = None,
+                  weights: Optional[torch.Tensor] = None, perm: Optional[torch.Tensor] = None):
+    """Search, then consume the neighbours on the device (the extension SURVEY.md section 8(b) names
+    next to the Faiss surface): returns (D, I, out) with
+        out[b, j, :] = rows[I[b, perm[j]], :]                 weights is None   ([B, k, d])
+        out[b, h, :] = sum_j weights[b, h, j] rows[I[b, j], :]   weights [B, H, k]  ([B, H, d])
+    `rows` are the resident fp32 rows of `bases` (an index aligned row for row with `index`, e.g. the
+    text database for an image search -- src/trainer.py:214-216 gathers both bases with one label
+    set) or of `index` itself. q: CUDA float32 [B, d]."""
+    q = index._check_q_tensor(q)
+    D, I = index.search(q, int(k))
+    src = bases if bases is not None else index
+    if src.ntotal != index.ntotal:
+        raise ValueError("search_gather: `bases` must be aligned row for row with the searched index")
+    out = weighted_pool(src, I, weights) if weights is not None else gather_rows(src, I, perm)
+    return D, I, out
+
+
 class KnowledgeBase:
     """The `database` object of the reference as a sequence:
     [image_bases, text_bases, basenames, image_gpu_index, text_gpu_index]  (src/main.py:95-96).

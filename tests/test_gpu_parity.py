@@ -397,6 +397,36 @@ def test_clustered_1024_centroids_stays_on_the_certified_path():
     assert ix.last_stats()["n_flagged"][0] <= 4
 
 
+def test_anisotropic_clip_like_embeddings_stay_on_the_certified_path():
+    """Embeddings shaped like a real CLIP tower's rather than i.i.d. directions: a strong common
+    component (random pairs have cosine ~0.5, so all scores crowd into half the range), power-law
+    sized topic clusters on top, per-row noise, plus image->text style queries that sit off the row
+    manifold. Exact answers, L2 (the reference's index type), flag rate below 5 %."""
+    rng = np.random.default_rng(720)
+    n, d, nc = 150_000, 768, 600
+    common = unit(1, d, 721)[0]
+    cent = unit(nc, d, 722)
+    size = rng.zipf(1.5, nc).clip(1, 2000).astype(np.float64)
+    assign = rng.choice(nc, size=n, p=size / size.sum())
+    db = 1.0 * common[None, :] + 0.7 * cent[assign] + 0.7 * unit(n, d, 723)
+    db = (db / np.linalg.norm(db, axis=1, keepdims=True)).astype(np.float32)
+    cos = float(np.mean(np.sum(db[:2000] * db[2000:4000], axis=1)))
+    assert 0.35 < cos < 0.65, cos
+    qa = rng.choice(nc, size=128)
+    q = 0.8 * common[None, :] + 0.7 * cent[qa] + 0.9 * unit(128, d, 724)     # a modality gap: off-manifold queries
+    q = (q / np.linalg.norm(q, axis=1, keepdims=True)).astype(np.float32)
+    ix = build(db, "l2")
+    qd = torch.from_numpy(q).cuda()
+    for _ in range(3):
+        D, I = ix.search(qd, 16)
+        ix.sync()
+    st = ix.last_stats()
+    assert st["exact_only"] == 0 and st["n_flagged"][0] <= 6, st
+    Dr, Ir = orc.search(db, q, 16, "l2")
+    c = orc.compare_topk(Dr, Ir, D.cpu().numpy(), I.cpu().numpy(), db, q, "l2", TIE_GAP, D_TOL)
+    assert c["ok"], c
+
+
 def test_clustered_database_certificate_and_fallback():
     """8 tight clusters of 2,500 rows put thousands of rows inside the error band around the k-th
     score -- more than any candidate list holds -- so the certificate must hand queries to the
@@ -576,6 +606,24 @@ def test_graph_captured_retrieval_step_matches_the_stream_path():
 
 
 # ------------------------------------------------------------------ reference-shaped operators vs golden
+def test_search_gather_returns_neighbours_or_their_weighted_pool():
+    a, b, q = unit(7000, 768, 291), unit(7000, 768, 292), unit(50, 768, 293)
+    ia, ib = build(a, "ip"), build(b, "ip")
+    qd = torch.from_numpy(q).cuda()
+    perm = torch.randperm(16, generator=torch.Generator().manual_seed(7))
+    D, I, feats = kr.search_gather(ia, qd, 16, perm=perm)
+    Dr, Ir = orc.search(a, q, 16, "ip")
+    assert orc.compare_topk(Dr, Ir, D.cpu().numpy(), I.cpu().numpy(), a, q, "ip", TIE_GAP, D_TOL)["ok"]
+    assert np.array_equal(feats.cpu().numpy(), orc.gather(a, I.cpu().numpy(), perm.numpy()))
+    W = torch.softmax(100.0 * D, dim=1).unsqueeze(1).contiguous()
+    _, I2, pooled = kr.search_gather(ia, qd, 16, bases=ib, weights=W)     # image labels, text rows
+    assert torch.equal(I2, I)
+    ref = orc.weighted_pool(b, I.cpu().numpy(), W.cpu().numpy())
+    assert np.abs(pooled.cpu().numpy() - ref).max() < 1e-5
+    with pytest.raises(ValueError):
+        kr.search_gather(ia, qd, 16, bases=build(b[:100], "ip"))
+
+
 def test_host_io_through_the_mapping_equals_the_copy_path():
     """keds_retrieve2_hostio: pinned host queries read by the first kernel through the mapping and
     (D, I) mirrored into pinned host blocks by the ranking blocks -- same answers as device queries
