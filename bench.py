@@ -386,6 +386,17 @@ def run_extras(dev, pk, ia, ib, img_rows):
         glab = torch.from_numpy(rng.integers(0, 7000, NG))
         qlab = torch.from_numpy(rng.integers(0, 7000, NQ))
         qq = make_db_gpu(NQ, DIM, 1009, dev)
+        # what get_metrics_imgnet actually needs from that gallery: label hits at the six cut points,
+        # not ranked rows with distances -- search and counting fused (keds_index_label_hits), exact
+        # fp32 scores only for the rows inside the error band around a cut
+        ks = [1, 5, 10, 50, 100, 200]
+        gl_d, ql_d = glab.to(dev), qlab.to(dev)
+        hits_fn = lambda: km.index_label_hits(ix, qq, gl_d, ql_d, ks)
+        rh = measure_search("cfg4h", [ix], None, qq, 200, 5, pk, fn=hits_fn, check=False)
+        _, I200 = ix.search(qq, 200)
+        rh["hits_equal_search_then_count"] = bool(torch.equal(hits_fn(), km.label_hits(I200, gl_d, ql_d, ks)))
+        rh["note"] = "same GEMM roofline as the top-200 search; the chain's third kernel is k_select_hits"
+        r["imgnet_10000x50k_label_hits"] = rh
         km.get_metrics_imgnet(qq, rows, qlab, glab)
         t0 = time.perf_counter()
         km.get_metrics_imgnet(qq, rows, qlab, glab)

@@ -238,6 +238,19 @@ int keds_index_rank(keds_index_t* idx, const float* q, int64_t nq, const int64_t
 int keds_label_hits(const int64_t* I, int64_t nq, int kmax, const int64_t* labels,
                     const int64_t* qlabel, const int32_t* ks, int nks, int32_t* hits,
                     void* cuda_stream);
+/* The same hits straight from the index, without materialising the ranked rows: the whole counting
+ * core of get_metrics_imgnet (feats @ G.t(), argsort, top-k masks, label products;
+ * src/eval_utils.py:1101-1118) in one call. hits[q][i] = #{ rows of the index among the exact
+ * top-ks[i] of query q (score descending, then lower row id: the order keds_index_search returns)
+ * whose row_labels entry equals qlabel[q] }. Neither distances nor the order inside a top-k set are
+ * needed, so only the rows whose 16-bit-operand score lies inside the certificate's error band
+ * around a cut point are re-scored in fp32 (about 65 instead of 200+ at the 50k-gallery shape);
+ * the sets, and therefore the counts, are those of an exact fp32 search.
+ * ks: HOST array, ascending, nks <= 8, ks[nks-1] <= 2048. q, row_labels [ntotal], qlabel [nq],
+ * hits [nq][nks]: device. Asynchronous on cuda_stream. */
+int keds_index_label_hits(keds_index_t* idx, const float* q, int64_t nq, const int64_t* row_labels,
+                          const int64_t* qlabel, const int32_t* ks, int nks, int32_t* hits,
+                          void* cuda_stream);
 
 /* ---- neighbour consumer (eval forward here, training entry points below) ------
  * The modules that consume the retrieved neighbours, evaluated in one launch sequence:

@@ -204,6 +204,15 @@ constexpr int64_t Q_PASS_MAX = 16384;
 constexpr size_t TIMING_RING = 8192;
 constexpr size_t TIMING_PAIRS = 5;  // k_prep_rows, k_score_topk, k_select_rerank, k_exact_fallback, (reserved)
 
+// keds_index_label_hits: the search chain with the hit-counting kernel in the re-rank's place
+struct HitsMode {
+  int nks;
+  int ks[HITS_MAX_CUTS];
+  const long long* row_labels;
+  const long long* qlabel;  // already offset to the pass's first query
+  int* hits;                // [nq][nks], likewise
+};
+
 struct Plan {
   int exact_only = 0;
   bool pair = false;  // CTA-pair scoring kernel (two query tiles per work item)
@@ -276,6 +285,7 @@ int set_kernel_attrs(keds_index* ix) {
   CK(cudaFuncSetAttribute(k_select_rerank<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaFuncSetAttribute(k_select_rerank<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaFuncSetAttribute(k_exact_fallback, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  CK(cudaFuncSetAttribute(k_select_hits<2, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   const char* no_pdl = getenv("KEDS_NO_PDL");
   ix->use_pdl = !(no_pdl && no_pdl[0] == '1');
   if (const char* ws = getenv("KEDS_NO_WARM_START")) ix->warm_start = !(ws[0] == '1');
@@ -521,7 +531,7 @@ int launch_exact(keds_index* ix, keds_index* dbs[2], int n_db, const float* q_de
 int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int k, float* D[2],
                 long long* I[2], uint32_t flags, cudaStream_t st, float* dump, int64_t ld_dump,
                 const ConsumeParams* cons_in, const PeerOut* peer = nullptr, int pass_idx = 0,
-                const float* q_src = nullptr) {
+                const float* q_src = nullptr, const HitsMode* hm = nullptr) {
   // q_src (nullable): the queries in page-locked host memory, addressed through the mapping;
   // k_prep_rows reads them there once and leaves the fp32 copy the other kernels use in q_dev
   keds_index* a = ix[0];
@@ -626,6 +636,48 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
     CK(cudaGetLastError());
     if (dump) return 0;
 
+    if (hm) {
+      // label hits at the cut points instead of the ranked rows (label_hits.cuh): same lists, same
+      // certificate, exact scores only for the rows inside the error band around a cut
+      HitsParams hp;
+      memset(&hp, 0, sizeof hp);
+      hp.n_qt = pl.n_qt;
+      hp.S = pl.S * pl.sub;
+      hp.nq = static_cast<int>(nq);
+      hp.d = a->d;
+      hp.metric = metric;
+      hp.nks = hm->nks;
+      for (int j = 0; j < hm->nks; ++j) hp.ks[j] = hm->ks[j];
+      unsigned int want = std::max<unsigned int>(static_cast<unsigned int>(k + k / 2 + 64), band_hint + band_hint / 2);
+      int rmax = 256;
+      while (rmax < static_cast<int>(std::min<unsigned int>(want, R_MAX))) rmax *= 2;
+      hp.rmax = rmax;
+      hp.cand = sp.cand;
+      hp.cand_cnt = sp.cand_cnt;
+      hp.cand_theta = sp.cand_theta;
+      hp.q_f32 = q_dev;
+      hp.qstat = a->qstat.as<float4>();
+      hp.x_f32 = a->x_f32.as<float>();
+      hp.dbstat = a->dbstat.as<unsigned int>();
+      hp.row_labels = hm->row_labels;
+      hp.qlabel = hm->qlabel;
+      hp.hits = hm->hits;
+      hp.flagged = a->flagged[0].as<int>();
+      hp.n_flagged = reinterpret_cast<int*>(a->ctrl_cur);
+      hp.eps_scale = a->eps_scale;
+      hp.band_max = a->ctrl_cur + CTRL_BAND;
+      hp.timing = tchain ? tchain + 4 : nullptr;
+      const size_t hslots = static_cast<size_t>(pl.S) * pl.sub * LKEEP;
+      // qvec | keys, ids | c_key, c_id, c_sc, c_info, amb | hist | red | bcast | counters | kth, n_cert, n_hit
+      const size_t hsmem = static_cast<size_t>((a->d + 3) & ~3) * 4 + hslots * 8 + static_cast<size_t>(rmax) * 20 +
+                           256 * 4 + 32 * 4 + 16 + 16 + 3 * HITS_MAX_CUTS * 4;
+      if (hsmem > 200 * 1024) return fail(KEDS_ERR_ARG, "label-hits shared memory %zu too large", hsmem);
+      // <2 rows in flight per warp, 6 blocks per SM>: measured 0.55 ms at 10,000 x 50k against 0.68 (<3, 4>) / 0.57 (<1, 8>)
+      CKS(launch_k(a->use_pdl, k_select_hits<2, 6>, dim3(static_cast<unsigned>(nq)), dim3(HITS_THREADS), hsmem, st, hp));
+      CKS(prof_mark(a, st, 3));
+      a->stats.launches++;
+      CK(cudaGetLastError());
+    } else {
     RerankParams rp;
     memset(&rp, 0, sizeof rp);
     rp.n_db = n_db;
@@ -682,10 +734,24 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
     CKS(prof_mark(a, st, 3));
     a->stats.launches++;
     CK(cudaGetLastError());
+    }
   }
   if (!(flags & KEDS_SEARCH_NO_FALLBACK) || pl.exact_only) {
     CKS(launch_exact(a, ix, n_db, q_dev, nq, k, D, I, metric, cons, tchain ? tchain + 6 : nullptr, st, peer));
     CKS(prof_mark(a, st, 4));
+  }
+  if (hm) {
+    // the queued queries' exact rows (written by the fallback just now) -> their hits
+    HitsParams hp;
+    memset(&hp, 0, sizeof hp);
+    hp.nks = hm->nks;
+    for (int j = 0; j < hm->nks; ++j) hp.ks[j] = hm->ks[j];
+    hp.hits = hm->hits;
+    CKS(launch_k(a->use_pdl, k_hits_from_rows, dim3(static_cast<unsigned>(std::min<int64_t>((nq + 127) / 128, 64))),
+                 dim3(128), 0, st, static_cast<const int*>(a->flagged[0].as<int>()),
+                 static_cast<const int*>(reinterpret_cast<int*>(a->ctrl_cur)), static_cast<const long long*>(I[0]), k,
+                 static_cast<long long>(a->id_offset), hm->row_labels, hm->qlabel, hp));
+    a->stats.launches++;
   }
   CK(cudaGetLastError());
   return 0;
@@ -1773,6 +1839,46 @@ int keds_index_rank(keds_index_t* ix, const float* q, int64_t nq, const int64_t*
     ix->stats.items = n_items;
     ix->stats.grid = grid;
     if (q0 + nb < nq) CKS(finish_sync(ix, st));  // the scratch is reused by the next pass
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int keds_index_label_hits(keds_index_t* ix, const float* q, int64_t nq, const int64_t* row_labels,
+                          const int64_t* qlabel, const int32_t* ks, int nks, int32_t* hits, void* stream) {
+  if (!ix || !q || !row_labels || !qlabel || !ks || !hits || nq < 0 || nks <= 0 || nks > HITS_MAX_CUTS)
+    return fail(KEDS_ERR_ARG, "index_label_hits: null argument, bad nq or more than %d cut points", HITS_MAX_CUTS);
+  for (int j = 0; j < nks; ++j)
+    if (ks[j] <= 0 || (j > 0 && ks[j] <= ks[j - 1])) return fail(KEDS_ERR_ARG, "index_label_hits: ks must be ascending and positive");
+  if (ks[nks - 1] > K_MAX) return fail(KEDS_ERR_ARG, "index_label_hits: k=%d exceeds the maximum %d", ks[nks - 1], K_MAX);
+  if (nq == 0) return 0;
+  if (ix->n == 0) return fail(KEDS_ERR_ARG, "index_label_hits: empty index");
+  if (!is_device_ptr(q) || !is_device_ptr(row_labels) || !is_device_ptr(qlabel) || !is_device_ptr(hits))
+    return fail(KEDS_ERR_ARG, "index_label_hits: device pointers only");
+  DeviceGuard g(ix->device);
+  if (!g.ok) return fail(KEDS_ERR_NO_GPU, "cannot select CUDA device %d", ix->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  memset(&ix->stats, 0, sizeof ix->stats);
+  const int kmax = ks[nks - 1];
+  const int n_passes = static_cast<int>((nq + Q_PASS_MAX - 1) / Q_PASS_MAX);
+  CKS(ix->ctrl.ensure(static_cast<size_t>(n_passes) * CTRL_STRIDE * 4));
+  // exact rows of the queries the certificate queues (the fallback writes them, k_hits_from_rows counts them)
+  const int64_t nb_max = std::min<int64_t>(nq, Q_PASS_MAX);
+  CKS(ix->D_stage[0].ensure(static_cast<size_t>(nb_max) * kmax * 4));
+  CKS(ix->I_stage[0].ensure(static_cast<size_t>(nb_max) * kmax * 8));
+  keds_index* v[2] = {ix, nullptr};
+  for (int64_t q0 = 0; q0 < nq; q0 += Q_PASS_MAX) {
+    const int64_t nb = std::min<int64_t>(Q_PASS_MAX, nq - q0);
+    HitsMode hm;
+    hm.nks = nks;
+    for (int j = 0; j < nks; ++j) hm.ks[j] = ks[j];
+    hm.row_labels = reinterpret_cast<const long long*>(row_labels);
+    hm.qlabel = reinterpret_cast<const long long*>(qlabel) + q0;
+    hm.hits = hits + q0 * nks;
+    float* Dp[2] = {ix->D_stage[0].as<float>(), nullptr};
+    long long* Ip[2] = {ix->I_stage[0].as<long long>(), nullptr};
+    CKS(search_pass(v, 1, q + q0 * ix->d, nb, kmax, Dp, Ip, 0u, st, nullptr, 0, nullptr, nullptr,
+                    static_cast<int>(q0 / Q_PASS_MAX), nullptr, &hm));
   }
   CK(cudaGetLastError());
   return 0;

@@ -208,6 +208,29 @@ def label_hits(I: torch.Tensor, labels: torch.Tensor, qlabel: torch.Tensor, ks: 
     return hits
 
 
+def index_label_hits(ix: GpuIndexFlat, Q: torch.Tensor, labels: torch.Tensor, qlabel: torch.Tensor,
+                     ks: Sequence[int]) -> torch.Tensor:
+    """hits[q, i] = #{ rows of `ix` among the exact top-ks[i] of Q[q] whose label equals qlabel[q] }
+    (device int32 [Q, len(ks)]) in one native call (keds_index_label_hits): search and counting
+    fused, fp32 re-scores only for the rows inside the error band around a cut point."""
+    lib = _capi.load()
+    dev = Q.device
+    ks = [int(k) for k in ks]
+    ks_arr = (C.c_int32 * len(ks))(*ks)
+    labels = labels.to(device=dev, dtype=torch.int64).contiguous()
+    qlabel = qlabel.to(device=dev, dtype=torch.int64).contiguous()
+    if labels.numel() != ix.ntotal or qlabel.numel() != Q.shape[0]:
+        raise ValueError("one label per index row and one per query")
+    Q = ix._check_q_tensor(Q)
+    hits = torch.empty((Q.shape[0], len(ks)), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _capi.check(
+            lib.keds_index_label_hits(ix._h, Q.data_ptr(), Q.shape[0], labels.data_ptr(), qlabel.data_ptr(),
+                                      ks_arr, len(ks), hits.data_ptr(), _stream_ptr(dev.index))
+        )
+    return hits
+
+
 def get_metrics_imgnet(query_features, image_features, query_labels, target_labels) -> Dict[str, float]:
     """src/eval_utils.py:1090-1134: R@k = hits_in_top_k / (num_relevant + 1e-5) (:1115),
     P@k = hits_in_top_k / k (:1116), averaged over the queries; k in {1,5,10,50,100,200}."""
@@ -218,9 +241,11 @@ def get_metrics_imgnet(query_features, image_features, query_labels, target_labe
     tl = torch.as_tensor(target_labels).to(device=dev, dtype=torch.int64)
     ix = gallery_index(image_features, dev)
     n_gallery = ix.ntotal
-    kmax = max(ks)
-    _, I = ix.search(Q, kmax)
-    hits = label_hits(I, tl, ql, ks).to(torch.float32)
+    if n_gallery >= max(ks):
+        hits = index_label_hits(ix, Q, tl, ql, ks).to(torch.float32)
+    else:  # a gallery smaller than the largest cut: the padded search defines what "top-k" means
+        _, I = ix.search(Q, max(ks))
+        hits = label_hits(I, tl, ql, ks).to(torch.float32)
     n_cls = int(max(int(tl.max()), int(ql.max()))) + 1
     num_total = torch.bincount(tl, minlength=n_cls)[ql].to(torch.float32)
     metrics: Dict[str, float] = {}

@@ -1,6 +1,7 @@
 """A few searches of one shape, for ncu captures:  python scripts/prof_shapes.py <shape> [iters]
 shapes: cfg1 (4096 x 50k, CTA-pair kernel), b4096 (4096 x 0.5M), cfg2 (128 x 2 x 0.5M, retrieve2),
-cfg5 (128 x 1M, k = 64), imgnet (10000 x 50k, k = 200), cirr (gallery rank 4181 x 2297)"""
+cfg5 (128 x 1M, k = 64), imgnet (10000 x 50k, k = 200), hits (the same shape through
+keds_index_label_hits), cirr (gallery rank 4181 x 2297)"""
 from __future__ import annotations
 
 import os
@@ -34,6 +35,15 @@ if shape == "cirr":
     q = q / q.norm(dim=1, keepdim=True)
     for _ in range(iters):
         km.gallery_rank(q, gal, tgt, ref)
+elif shape == "hits":
+    ix = GpuIndexFlat(D, METRIC_INNER_PRODUCT, 0)
+    ix.add(db(50_000, 1000))
+    q = db(10_000, 1001)
+    rng = np.random.default_rng(1008)
+    gl = torch.from_numpy(rng.integers(0, 7000, 50_000)).cuda()
+    ql = torch.from_numpy(rng.integers(0, 7000, 10_000)).cuda()
+    for _ in range(iters):
+        km.index_label_hits(ix, q, gl, ql, [1, 5, 10, 50, 100, 200])
 elif shape == "cfg2":
     ia, ib = GpuIndexFlat(D, METRIC_INNER_PRODUCT, 0), GpuIndexFlat(D, METRIC_INNER_PRODUCT, 0)
     ia.add(db(500_000, 1002))

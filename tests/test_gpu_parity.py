@@ -776,6 +776,55 @@ def test_gallery_rank_tensor_core_path_equals_the_exact_count():
     km.clear_gallery_cache()
 
 
+def test_index_label_hits_equal_the_search_then_count_path():
+    """keds_index_label_hits (get_metrics_imgnet's core in one call): the hit counts at every cut
+    point must equal those of an exact search followed by counting -- bit for bit against the native
+    search (same fp32 scores, same tie rule) and against the float64 oracle wherever no near-tie
+    sits on a cut. Few classes, so that hits are plentiful; duplicated gallery rows with different
+    labels, so that ties straddle the cuts; both metrics; every query through the fallback."""
+    rng = np.random.default_rng(810)
+    g = unit(30000, 768, 811)
+    g[5000:5600] = g[:600]                       # exact duplicates: equal scores, the lower row id wins
+    q = unit(700, 768, 812)
+    q[:300] = g[rng.integers(0, 600, 300)] + 0.6 * q[:300]   # queries near duplicated rows
+    q = (q / np.linalg.norm(q, axis=1, keepdims=True)).astype(np.float32)
+    glab = torch.from_numpy(rng.integers(0, 40, 30000))
+    qlab = torch.from_numpy(rng.integers(0, 40, 700))
+    qd = torch.from_numpy(q).cuda()
+    for metric in ("ip", "l2"):
+        ix = build(g, metric)
+        for ks in ([1, 5, 10, 50, 100, 200], [3], [16, 64]):
+            hits = km.index_label_hits(ix, qd, glab, qlab, ks)
+            ix.sync()
+            st = ix.last_stats()
+            assert st["exact_only"] == 0 and st["err_word"] == 0 and st["n_flagged"][0] <= 35, st
+            _, I = ix.search(qd, max(ks))
+            want = km.label_hits(I, glab, qlab, ks)
+            assert torch.equal(hits, want), (metric, ks, (hits != want).sum().item())
+        # float64 oracle: equal except where a near-tie sits on a cut point
+        ks = [1, 5, 10, 50, 100, 200]
+        hits = km.index_label_hits(ix, qd, glab, qlab, ks).cpu().numpy()
+        Dr, Ir = orc.search(g, q, 201, metric)
+        lab = glab.numpy()[Ir] == qlab.numpy()[:, None]
+        for i, k in enumerate(ks):
+            ref = lab[:, :k].sum(1)
+            bad = np.nonzero(ref != hits[:, i])[0]
+            gap = np.abs(Dr[bad, k - 1].astype(np.float64) - Dr[bad, k].astype(np.float64))
+            assert (gap < TIE_GAP * (2.0 if metric == "l2" else 1.0)).all(), (metric, k, bad[:5], gap[:5])
+        # every query through the exact fallback: same counts
+        ix.set_eps_scale(1e4)
+        h2 = km.index_label_hits(ix, qd, glab, qlab, ks)
+        ix.sync()
+        assert ix.last_stats()["n_flagged"][0] == 700
+        ix.set_eps_scale(1.0)
+        assert np.array_equal(h2.cpu().numpy(), hits)
+    # a gallery too small for the tensor-core path, and cut points beyond its size
+    small = build(g[:150], "ip")
+    hs = km.index_label_hits(small, qd, glab[:150], qlab, [1, 100, 200])
+    _, I = small.search(qd, 200)
+    assert torch.equal(hs, km.label_hits(I, glab[:150], qlab, [1, 100, 200]))
+
+
 def test_imgnet_shaped_recall_50k_gallery():
     """configs[3]: 50k-row gallery with labels < 7000, top-200 label hits."""
     rng = np.random.default_rng(1008)
