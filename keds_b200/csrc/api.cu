@@ -284,6 +284,7 @@ int set_kernel_attrs(keds_index* ix) {
   ix->use_pair = !(no_pair && no_pair[0] == '1');
   CK(cudaFuncSetAttribute(k_select_rerank<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaFuncSetAttribute(k_select_rerank<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(k_select_rerank<2, 6, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaFuncSetAttribute(k_exact_fallback, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   CK(cudaFuncSetAttribute(k_select_hits<2, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   const char* no_pdl = getenv("KEDS_NO_PDL");
@@ -728,6 +729,12 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
     if (small_batch)
       CKS(launch_k(a->use_pdl, k_select_rerank<3, 2>, dim3(static_cast<unsigned>(nq), n_db),
                    dim3(RERANK_THREADS), smem, st, rp));
+    else if (k >= 128 && a->rerank_threads_large == 128)
+      // hundreds of fp32 rows per query: two rows per warp in flight (80 registers, six blocks per
+      // SM) measured 0.82-0.87 ms against 0.95-1.0 at 10,000 x 50k, k = 200; at k = 16 / 64 the
+      // 64-register variant below is 5-10 % faster
+      CKS(launch_k(a->use_pdl, k_select_rerank<2, 6, 128>, dim3(static_cast<unsigned>(nq), n_db),
+                   dim3(128), smem, st, rp));
     else
       CKS(launch_k(a->use_pdl, k_select_rerank<1, 4>, dim3(static_cast<unsigned>(nq), n_db),
                    dim3(a->rerank_threads_large), smem, st, rp));

@@ -577,16 +577,24 @@ __device__ unsigned int block_kth_largest(const unsigned int* keys, int n, int k
   for (int shift = 24; shift >= 0; shift -= 8) {
     for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
     __syncthreads();
-    // Scores of one query share their leading bytes, so in the first passes a whole warp lands in
-    // ONE bin: lanes with the same bin elect a leader that adds their count (one shared-memory
-    // atomic per distinct bin and warp instead of 32 serialised ones on a single address).
-    for (int i0 = 0; i0 < n; i0 += blockDim.x) {
-      const int i = i0 + static_cast<int>(threadIdx.x);
-      const unsigned int key = i < n ? keys[i] : 0u;
-      const bool live = i < n && (key & mask) == prefix;
-      const unsigned int bin = live ? ((key >> shift) & 255u) : 256u;
-      const unsigned int peers = __match_any_sync(0xffffffffu, bin);
-      if (live && (threadIdx.x & 31) == static_cast<unsigned int>(__ffs(peers) - 1)) atomicAdd(&hist[bin], __popc(peers));
+    // Scores of one query share their leading bytes, so in the first two passes a whole warp lands
+    // in ONE or two bins: lanes with the same bin elect a leader that adds their count (one
+    // shared-memory atomic per distinct bin and warp instead of 32 serialised ones on one address).
+    // The low bytes spread over the bins; there plain atomics are cheaper than the matching loop.
+    if (shift >= 16) {
+      for (int i0 = 0; i0 < n; i0 += blockDim.x) {
+        const int i = i0 + static_cast<int>(threadIdx.x);
+        const unsigned int key = i < n ? keys[i] : 0u;
+        const bool live = i < n && (key & mask) == prefix;
+        const unsigned int bin = live ? ((key >> shift) & 255u) : 256u;
+        const unsigned int peers = __match_any_sync(0xffffffffu, bin);
+        if (live && (threadIdx.x & 31) == static_cast<unsigned int>(__ffs(peers) - 1)) atomicAdd(&hist[bin], __popc(peers));
+      }
+    } else {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const unsigned int key = keys[i];
+        if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+      }
     }
     __syncthreads();
     block_find_bin(hist, need, bcast);

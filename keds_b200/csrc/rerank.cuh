@@ -43,8 +43,8 @@ constexpr unsigned int PAD_ID = 0xFFFFFFFFu;
 // R = candidate rows per warp in flight during the fp32 re-score. <3, 2>: small batches, shortest
 // dependency chain (two blocks per SM). <1, 4>: large batches, four blocks per SM so that many
 // queries overlap their phases.
-template <int R, int MINB>
-__global__ void __launch_bounds__(RERANK_THREADS, MINB)
+template <int R, int MINB, int THREADS = RERANK_THREADS>
+__global__ void __launch_bounds__(THREADS, MINB)
 k_select_rerank(const RerankParams p) {
   extern __shared__ uint8_t rr_smem[];
   const int q = blockIdx.x, db = blockIdx.y;
