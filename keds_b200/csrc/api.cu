@@ -669,9 +669,9 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
       hp.band_max = a->ctrl_cur + CTRL_BAND;
       hp.timing = tchain ? tchain + 4 : nullptr;
       const size_t hslots = static_cast<size_t>(pl.S) * pl.sub * LKEEP;
-      // qvec | keys, ids | c_key, c_id, c_sc, c_info, amb | hist | red | bcast | counters | kth, n_cert, n_hit
+      // qvec | cs | keys, ids | c_sc, c_info, amb | hist | red | bcast | counters | n_cert, band_end, n_hit
       const size_t hsmem = static_cast<size_t>((a->d + 3) & ~3) * 4 + hslots * 8 + static_cast<size_t>(rmax) * 20 +
-                           256 * 4 + 32 * 4 + 16 + 16 + 3 * HITS_MAX_CUTS * 4;
+                           1024 * 4 + 32 * 4 + 16 + 16 + 3 * HITS_MAX_CUTS * 4;
       if (hsmem > 200 * 1024) return fail(KEDS_ERR_ARG, "label-hits shared memory %zu too large", hsmem);
       // <2 rows in flight per warp, 6 blocks per SM>: measured 0.55 ms at 10,000 x 50k against 0.68 (<3, 4>) / 0.57 (<1, 8>)
       CKS(launch_k(a->use_pdl, k_select_hits<2, 6>, dim3(static_cast<unsigned>(nq)), dim3(HITS_THREADS), hsmem, st, hp));
