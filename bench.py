@@ -557,14 +557,19 @@ def run_ours(args, rank, world, local):
     # pinned queries through the mapping, the ranking blocks store (D, I) into the pinned result block
     # (keds_retrieve2_hostio); the same bytes cross PCIe. copy_nodes=True (H2D + D2H nodes around the
     # search, the round-1 layout) is timed beside it.
+    e2e_checks = {}
+
     def graph_leg(copy_nodes):
         rstep = kr.RetrievalStep(ia, ib, BATCH, K, perm_img=perm, want_feats=True, pool_mode=kr.POOL_SOFTMAX, tau=TAU,
                                  copy_nodes=copy_nodes)
         rstep.q_host.copy_(q_host)
         for _ in range(3):
             rstep.run()
-        assert torch.equal(rstep.I_img, lab_host[0]) and torch.equal(rstep.I_txt, lab_host[1])
-        assert torch.equal(rstep.D_img, d_host[0]) and torch.equal(rstep.D_txt, d_host[1])
+        # (recorded in the line, not asserted: a mismatch must show up as `results_match: false`,
+        # not as a bench run without a line)
+        e2e_checks[copy_nodes] = bool(
+            torch.equal(rstep.I_img, lab_host[0]) and torch.equal(rstep.I_txt, lab_host[1])
+            and torch.equal(rstep.D_img, d_host[0]) and torch.equal(rstep.D_txt, d_host[1]))
         barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
@@ -572,7 +577,8 @@ def run_ours(args, rank, world, local):
             rstep.run()
         g1.record()
         barrier()
-        assert rstep.h2d_bytes == h2d and rstep.d2h_bytes == d2h and rstep.recaptures == 0
+        e2e_checks[copy_nodes] = (e2e_checks[copy_nodes] and rstep.h2d_bytes == h2d and rstep.d2h_bytes == d2h
+                                  and rstep.recaptures == 0)
         return g0.elapsed_time(g1)
 
     e2e_copy_ms = graph_leg(True)
@@ -678,6 +684,7 @@ def run_ours(args, rank, world, local):
                         "(D, I) of both DBs stored into pinned host memory by the ranking blocks, stream sync every step; "
                         "gathered/pooled streams stay on the device for the model",
                 "copy_nodes_ms_per_step": e2e_copy_ms / e2e_steps,
+                "results_match": bool(e2e_checks.get(False)) and bool(e2e_checks.get(True)),
                 "stream_launched_ms_per_step": e2e_stream_ms / e2e_steps,
                 "stream_launched_value": world * BATCH / (e2e_stream_ms / e2e_steps * 1e-3)},
         "dropin_numpy": {"value": world * BATCH / (dropin_ms * 1e-3), "unit": "queries/s", "ms_per_step": dropin_ms,
