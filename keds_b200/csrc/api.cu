@@ -240,7 +240,6 @@ struct keds_index {
   CUtensorMap tm_xh;  // {64 x 128}-row boxes (CTA pair: half a tile each)
   bool tm_x_ok = false;
   bool use_pair = true;
-  bool use_resq = false;  // CTA-pair kernel with four resident query k-blocks (KEDS_RESQ=1)
   // per-call scratch (one search in flight per handle)
   DevBuf q_f32, q_bf16, qstat, cand, cand_cnt, cand_theta, flagged[2], ctrl, exact_scratch, rk, theta0;
   bool warm_start = true;  // lists start at a finished list's threshold (KEDS_NO_WARM_START=1: every list cold)
@@ -281,9 +280,6 @@ int set_kernel_attrs(keds_index* ix) {
 
   CK(cudaFuncSetAttribute(k_score_topk<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)SCORE_PAIR_SMEM_BYTES));
-  CK(cudaFuncSetAttribute(k_score_topk<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                          (int)SCORE_PAIR_RESQ_SMEM_BYTES));
-  if (const char* rq = getenv("KEDS_RESQ")) ix->use_resq = rq[0] == '1';
   const char* no_pair = getenv("KEDS_NO_PAIR");
   ix->use_pair = !(no_pair && no_pair[0] == '1');
   CK(cudaFuncSetAttribute(k_select_rerank<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -630,10 +626,7 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
     sp.ld_dump = ld_dump;
     sp.timing = tchain ? tchain + 2 : nullptr;
     CKS(prof_mark(a, st, 1));
-    if (pl.pair && (a->use_resq || (getenv("KEDS_RESQ_DYN") && getenv("KEDS_RESQ_DYN")[0] == '1')))
-      CKS(launch_kc(a->use_pdl, 2, k_score_topk<true, false, true>, dim3(pl.grid), dim3(SCORE_PAIR_THREADS),
-                    SCORE_PAIR_RESQ_SMEM_BYTES, st, a->tm_q, ix[0]->tm_xh, n_db > 1 ? ix[1]->tm_xh : ix[0]->tm_xh, sp));
-    else if (pl.pair)
+    if (pl.pair)
       CKS(launch_kc(a->use_pdl, 2, k_score_topk<true>, dim3(pl.grid), dim3(SCORE_PAIR_THREADS), SCORE_PAIR_SMEM_BYTES,
                     st, a->tm_q, ix[0]->tm_xh, n_db > 1 ? ix[1]->tm_xh : ix[0]->tm_xh, sp));
     else

@@ -44,16 +44,8 @@ constexpr int SCORE_PAIR_THREADS = 320;  // CTA-pair variant: 8 epilogue warps
 constexpr uint32_t Q_STAGE_BYTES = BM * BK * 2;
 constexpr uint32_t TMEM_COLS = 512;
 
-// kResQ (CTA-pair variant only): part of the query tile stays RESIDENT in shared memory for a whole
-// work item instead of being re-streamed from L2 with every row tile. The pair kernel sits on the
-// SM's L2 ingress (32 KB per k-block at full MMA rate = 64 B/clk against ~50 measured): with four
-// of the twelve 16-KB query k-blocks resident a row tile costs 320 KB of ingress instead of 384.
-// Layout: [4 resident query k-blocks][4-stage ring of 16-KB row boxes][2-stage ring of streamed
-// query k-blocks]; resident k-blocks are every third one, so the query ring is asked for two
-// k-blocks out of three at an even pace.
-template <bool kPair, bool kResQ = false>
+template <bool kPair>
 struct ScoreCfg {
-  static_assert(!kResQ || kPair, "resident query k-blocks exist in the CTA-pair variant only");
   // Single CTA (HBM-bound, one query tile): the kernel lives on bytes in flight, so the candidate
   // slots are cut to 32 per query (32 KB) to make room for a fourth 48-KB stage; the slot count
   // is then checked every 8 scores. CTA pair (compute-bound): 64 slots, checked every 32 scores --
@@ -70,21 +62,15 @@ struct ScoreCfg {
   static constexpr uint32_t kCandWarpBytes = kCap * 32 * 8;
   static constexpr int kRowsPerCta = kPair ? BN / 2 : BN;           // row-tile rows this CTA loads
   static constexpr uint32_t kXBytes = kRowsPerCta * BK * 2;
-  static constexpr int kRes = kResQ ? 4 : 0;      // resident query k-blocks (k-block 3 r for r < kRes)
-  static constexpr int kQStages = kResQ ? 2 : 0;  // ring of the streamed query k-blocks
-  static constexpr uint32_t kStageBytes = kResQ ? kXBytes : Q_STAGE_BYTES + kXBytes;  // 48 KB / 32 KB / 16 KB (rows only)
+  static constexpr uint32_t kStageBytes = Q_STAGE_BYTES + kXBytes;  // 48 KB / 32 KB
   // dynamic shared memory map (offsets from a 1024-aligned base)
-  static constexpr uint32_t kOffRing = kRes * Q_STAGE_BYTES;                 // stage ring (kResQ: row boxes only)
-  static constexpr uint32_t kOffQRing = kOffRing + kStages * kStageBytes;    // kResQ: streamed query k-blocks
-  static constexpr uint32_t kOffCand = kOffQRing + kQStages * Q_STAGE_BYTES;
+  static constexpr uint32_t kOffCand = kStages * kStageBytes;
   static constexpr uint32_t kOffBias = kOffCand + kEpiWarps * kCandWarpBytes;
   static constexpr uint32_t kOffBars = kOffBias + 2 * BN * 4;
   static constexpr uint32_t kSmemBytes = kOffBars + 256 + 768;      // barriers + alignment slack (227 KB exactly for the single-CTA variant)
 };
 constexpr uint32_t SCORE_SMEM_BYTES = ScoreCfg<false>::kSmemBytes;
 constexpr uint32_t SCORE_PAIR_SMEM_BYTES = ScoreCfg<true>::kSmemBytes;
-constexpr uint32_t SCORE_PAIR_RESQ_SMEM_BYTES = ScoreCfg<true, true>::kSmemBytes;
-static_assert(SCORE_PAIR_RESQ_SMEM_BYTES <= 227u * 1024u, "resident-query layout exceeds the shared memory of an SM");
 
 struct ScoreParams {
   int n_db;          // 1 or 2 databases scored against the same queries
@@ -206,11 +192,11 @@ __device__ __noinline__ CandState compact_candidates(uint32_t slot0, int cnt, fl
 //                overflow mark and the query is recounted exactly). The target and the excluded row
 //                are skipped by id. Output: the same 128-byte lines (band rows), cand_cnt = band
 //                rows or -1 (overflow), cand_theta = the certain count (as int bits).
-template <bool kPair, bool kRank = false, bool kResQ = false>
-__global__ void __launch_bounds__(ScoreCfg<kPair, kResQ>::kThreads, 1)
+template <bool kPair, bool kRank = false>
+__global__ void __launch_bounds__(ScoreCfg<kPair>::kThreads, 1)
 k_score_topk(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_x0,
              const __grid_constant__ CUtensorMap tm_x1, const ScoreParams p) {
-  using Cfg = ScoreCfg<kPair, kResQ>;
+  using Cfg = ScoreCfg<kPair>;
   constexpr int NSTAGE = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -231,12 +217,6 @@ k_score_topk(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
   auto empty_bar = [&](int s) { return bars + 8u * (NSTAGE + s); };
   auto tfull_bar = [&](int a) { return bars + 8u * (2 * NSTAGE + a); };
   auto tempty_bar = [&](int a) { return bars + 8u * (2 * NSTAGE + 2 + a); };
-  // kResQ: the streamed-query ring's release barriers and the hand-over of the resident region
-  auto qempty_bar = [&](int s) { return bars + 8u * (2 * NSTAGE + 4 + s); };
-  const uint32_t qres_full = bars + 8u * (2 * NSTAGE + 4 + 2);
-  const uint32_t qres_empty = bars + 8u * (2 * NSTAGE + 4 + 3);
-  // is k-block kb of the query tile resident, and where
-  auto res_slot = [&](int kb) { return (Cfg::kRes > 0 && kb % 3 == 0 && kb / 3 < Cfg::kRes) ? kb / 3 : -1; };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + Cfg::kOffBars + 200);
   volatile uint32_t* dead = reinterpret_cast<volatile uint32_t*>(gbase + Cfg::kOffBars + 204);
 
@@ -257,11 +237,6 @@ k_score_topk(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), kPair ? 2 * Cfg::kEpiWarps : Cfg::kEpiWarps);  // pair: the leader collects both CTAs' epilogue warps
-    }
-    if constexpr (kResQ) {
-      for (int s = 0; s < Cfg::kQStages; ++s) mbar_init(qempty_bar(s), 1);
-      mbar_init(qres_full, 1);
-      mbar_init(qres_empty, 1);
     }
     *dead = 0;
     fence_mbar_init();
@@ -311,50 +286,13 @@ k_score_topk(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      [[maybe_unused]] int qstage = 0;
-      [[maybe_unused]] uint32_t qphase = 0, rphase = 0;
       for (int item = unit; item < p.n_items; item += n_units) {
         const ItemCoord c = decode_item(p, item);
         const CUtensorMap* tmx = c.db == 0 ? &tm_x0 : &tm_x1;
         const int qt = kPair ? c.qg * 2 + static_cast<int>(crank) : c.qg;
-        if constexpr (kResQ) {
-          // the resident k-blocks of this item's query tile, once the MMAs of the previous item have
-          // let go of the region (committed by the issuer behind its last tile)
-          mbar_wait(qres_empty, rphase ^ 1u, dead, p.err, 0x180u);
-          rphase ^= 1u;
-          int nres = 0;
-          for (int kb = 0; kb < p.kblocks; ++kb) nres += res_slot(kb) >= 0;
-          if (crank == 0) mbar_arrive_expect_tx(qres_full, 2u * nres * Q_STAGE_BYTES);
-          for (int kb = 0; kb < p.kblocks; ++kb)
-            if (res_slot(kb) >= 0)
-              tma_load_2d_2sm(sbase + res_slot(kb) * Q_STAGE_BYTES, &tm_q, qres_full, kb * BK, qt * BM, kEvictLast);
-        }
         for (int tile = c.t0; tile < c.t1; ++tile) {
           for (int kb = 0; kb < p.kblocks; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1u, dead, p.err, 0x100u + stage);
-            if constexpr (kResQ) {
-              // row box always; the query k-block only when it is not resident (its bytes are counted
-              // on the same barrier, its slot is released through the query ring's own barrier)
-              const bool streamed = res_slot(kb) < 0;
-              if (streamed) mbar_wait(qempty_bar(qstage), qphase ^ 1u, dead, p.err, 0x140u + qstage);
-              if (crank == 0)
-                mbar_arrive_expect_tx(full_bar(stage), 2u * Cfg::kXBytes + (streamed ? 2u * Q_STAGE_BYTES : 0u));
-              if (streamed) {
-                tma_load_2d_2sm(sbase + Cfg::kOffQRing + qstage * Q_STAGE_BYTES, &tm_q, full_bar(stage), kb * BK,
-                                qt * BM, kEvictLast);
-                if (++qstage == Cfg::kQStages) {
-                  qstage = 0;
-                  qphase ^= 1u;
-                }
-              }
-              tma_load_2d_2sm(sbase + Cfg::kOffRing + stage * Cfg::kStageBytes, tmx, full_bar(stage), kb * BK,
-                              tile * BN + static_cast<int>(crank) * Cfg::kRowsPerCta, kEvictNormal);
-              if (++stage == NSTAGE) {
-                stage = 0;
-                phase ^= 1u;
-              }
-              continue;
-            }
             const uint32_t sq = sbase + stage * Cfg::kStageBytes;
             const uint32_t sx = sq + Q_STAGE_BYTES;
             if constexpr (kPair) {
@@ -389,15 +327,8 @@ k_score_topk(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      [[maybe_unused]] int qstage = 0;
-      [[maybe_unused]] uint32_t rphase = 0;
       for (int item = unit; item < p.n_items; item += n_units) {
         const ItemCoord c = decode_item(p, item);
-        if constexpr (kResQ) {
-          mbar_wait(qres_full, rphase, dead, p.err, 0x380u);
-          tc_fence_after();
-          rphase ^= 1u;
-        }
         for (int tile = c.t0; tile < c.t1; ++tile) {
           mbar_wait(tempty_bar(acc), acc_phase ^ 1u, dead, p.err, 0x200u + acc);
           tc_fence_after();
@@ -405,17 +336,9 @@ k_score_topk(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
           for (int kb = 0; kb < p.kblocks; ++kb) {
             mbar_wait(full_bar(stage), phase, dead, p.err, 0x300u + stage);
             tc_fence_after();
-            uint32_t sq = sbase + stage * Cfg::kStageBytes;       // query k-block
-            uint32_t sxa = sq + Q_STAGE_BYTES;                    // row box
-            [[maybe_unused]] bool streamed = false;
-            if constexpr (kResQ) {
-              sxa = sbase + Cfg::kOffRing + stage * Cfg::kStageBytes;
-              const int rs = res_slot(kb);
-              streamed = rs < 0;
-              sq = streamed ? sbase + Cfg::kOffQRing + qstage * Q_STAGE_BYTES : sbase + rs * Q_STAGE_BYTES;
-            }
+            const uint32_t sq = sbase + stage * Cfg::kStageBytes;
             const uint64_t adesc = smem_desc_sw128(sq);
-            const uint64_t bdesc = smem_desc_sw128(sxa);
+            const uint64_t bdesc = smem_desc_sw128(sq + Q_STAGE_BYTES);
 #pragma unroll
             for (int k = 0; k < BK / UK; ++k) {
               // +32 bytes per K=16 step inside the 128-byte swizzle row: +2 in 16-byte units
@@ -425,12 +348,6 @@ k_score_topk(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
                 umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
             }
             if constexpr (kPair) umma_commit_2sm(empty_bar(stage), 0x3); else umma_commit(empty_bar(stage));
-            if constexpr (kResQ) {
-              if (streamed) {
-                umma_commit_2sm(qempty_bar(qstage), 0x3);
-                if (++qstage == Cfg::kQStages) qstage = 0;
-              }
-            }
             if (++stage == NSTAGE) {
               stage = 0;
               phase ^= 1u;
@@ -440,8 +357,6 @@ k_score_topk(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
           acc ^= 1;
           if (acc == 0) acc_phase ^= 1u;
         }
-        // kResQ: the resident region may be refilled once every MMA of this item has read it
-        if constexpr (kResQ) umma_commit_2sm(qres_empty, 0x3);
       }
     }
   } else {
