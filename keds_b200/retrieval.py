@@ -20,6 +20,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import time
 from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -248,13 +249,19 @@ class RetrievalStep:
                  perm_img: Optional[torch.Tensor] = None, want_feats: bool = True,
                  pool_mode: int = POOL_NONE, tau: float = 100.0, copy_nodes: Optional[bool] = None) -> None:
         self.ia, self.ib = image_index, text_index
-        # copy_nodes=False (default): no copies in the graph -- the first kernel reads the pinned
-        # queries through the mapping and the ranking blocks store (D, I) into the pinned result
-        # block next to the device one (keds_retrieve2_hostio). True: H2D + D2H copy nodes around
-        # the search (the round-1 layout; KEDS_STEP_COPY_NODES=1 selects it for A/B runs).
-        if copy_nodes is None:
-            copy_nodes = os.environ.get("KEDS_STEP_COPY_NODES", "0") == "1"
+        # copy_nodes=False: no copies in the graph -- the first kernel reads the pinned queries through
+        # the mapping and the ranking blocks store (D, I) into the pinned result block next to the
+        # device one (keds_retrieve2_hostio). True: H2D + D2H copy nodes around the search (the
+        # round-1 layout). None (default): capture both once and keep the faster on THIS box -- SM
+        # loads over PCIe beat the copy engines' set-up cost on most boxes (7 of 8 measured), but how
+        # the pinned pages sit relative to the GPU's root complex decides it; the answers are the same.
+        # KEDS_STEP_COPY_NODES=0|1 pins the choice.
+        env = os.environ.get("KEDS_STEP_COPY_NODES")
+        if copy_nodes is None and env in ("0", "1"):
+            copy_nodes = env == "1"
+        self._auto_layout = copy_nodes is None
         self.copy_nodes = bool(copy_nodes)
+        self.layout_probe_us = None
         dev = torch.device("cuda", image_index.device)
         d, k = image_index.d, int(topk)
         self.q_host = torch.empty((batch, d), dtype=torch.float32).pin_memory()
@@ -287,6 +294,32 @@ class RetrievalStep:
         self._capture()
 
     def _capture(self) -> None:
+        if self._auto_layout:
+            # time a few synchronised replays of both layouts (what run() does), keep the faster one
+            probe = {}
+            for cn in (False, True):
+                self.copy_nodes = cn
+                self._capture_one()
+                dev = self.q_dev.device
+                st = torch.cuda.current_stream(dev)
+                for _ in range(3):
+                    self.graph.replay()
+                    st.synchronize()
+                best = float("inf")
+                for _ in range(3):
+                    t0 = time.perf_counter()
+                    for _ in range(8):
+                        self.graph.replay()
+                        st.synchronize()
+                    best = min(best, (time.perf_counter() - t0) / 8)
+                probe[cn] = best * 1e6
+            self.layout_probe_us = {"host_io": probe[False], "copy_nodes": probe[True]}
+            self.copy_nodes = probe[True] < probe[False]
+            self._auto_layout = False   # a re-capture (moved scratch) keeps the choice
+            self.recaptures -= 2
+        self._capture_one()
+
+    def _capture_one(self) -> None:
         dev = self.q_dev.device
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
