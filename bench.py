@@ -515,24 +515,6 @@ def run_ours(args, rank, world, local):
     stats = ia.last_stats()
     ia.set_profiling(0)
 
-    # ---- the same loop for >= 1000 steps: what the step costs once the box has warmed up / power-capped
-    sustained = None
-    if not args.no_extras:
-        s_steps = max(1000, args.steps)
-        barrier()
-        ia.set_profiling(1)
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0.record()
-        for _ in range(s_steps):
-            step(q_dev)
-        s1.record()
-        barrier()
-        s_ms = s0.elapsed_time(s1)
-        ia.sync()
-        s_score_ms, s_score_n = ia.profile()
-        ia.set_profiling(0)
-        sustained = (s_steps, s_ms, s_score_ms / max(1, s_score_n))
-
     # ---- end to end: pinned host queries in; (D, I) of both databases -- what index.search hands
     # the host in the reference -- read back every step; gathered / pooled streams stay on the
     # device, where the model consumes them (src/trainer.py:229-230 moves them there anyway)
@@ -553,15 +535,16 @@ def run_ours(args, rank, world, local):
 
     e2e_steps = max(10, min(args.steps, 1000))
     for _ in range(3):
-        e2e_step()
-    barrier()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    for _ in range(e2e_steps):
-        e2e_step()
-    f1.record()
-    barrier()
-    e2e_stream_ms = f0.elapsed_time(f1)
+        e2e_step()   # (also leaves the reference (D, I) in d_host / lab_host for the legs' checks)
+
+    # Every leg below starts from the same state as the `value` loop did: its own warm-up steps after
+    # a short idle. Without it the legs inherit the clock the power cap has reached by then (this
+    # kernel's time follows the SM clock) and their order in this file decides their numbers.
+    LEG_PAUSE_S = 0.25
+
+    def settle():
+        barrier()
+        time.sleep(LEG_PAUSE_S)
 
     # the same step through the public RetrievalStep API, captured once into a CUDA graph: one graph
     # launch + one stream sync per step. Default layout: no copy nodes -- the first kernel reads the
@@ -575,7 +558,8 @@ def run_ours(args, rank, world, local):
         rstep = kr.RetrievalStep(ia, ib, BATCH, K, perm_img=perm, want_feats=True, pool_mode=kr.POOL_SOFTMAX, tau=TAU,
                                  copy_nodes=copy_nodes)
         rstep.q_host.copy_(q_host)
-        for _ in range(3):
+        settle()
+        for _ in range(max(3, min(W, 10))):
             rstep.run()
         # (recorded in the line, not asserted: a mismatch must show up as `results_match: false`,
         # not as a bench run without a line)
@@ -596,10 +580,75 @@ def run_ours(args, rank, world, local):
             e2e_layout["probe_us"] = rstep.layout_probe_us
         return g0.elapsed_time(g1)
 
-    e2e_copy_ms = graph_leg(True)
+    e2e_ms = graph_leg(None)   # the headline: RetrievalStep as a user gets it (it keeps whichever layout is faster on this box)
     e2e_hostio_ms = graph_leg(False)
-    e2e_ms = graph_leg(None)   # the default: RetrievalStep keeps whichever layout is faster on this box
+    e2e_copy_ms = graph_leg(True)
+    # two steps in flight (RetrievalPipeline): the next batch is submitted before the previous one's
+    # host results are consumed, as a training loop may do -- every step still reads its queries from
+    # pinned host memory and returns its (D, I) there. Reported beside the strict per-step-sync figure.
+    pipe_ms = None
+    try:
+        pipe = kr.RetrievalPipeline(ia, ib, BATCH, topk=K, perm_img=perm, want_feats=True, pool_mode=kr.POOL_SOFTMAX, tau=TAU)
+        for stp in pipe.steps:
+            stp.q_host.copy_(q_host)
+        t_prev = pipe.submit()
+        for _ in range(4):
+            t_new = pipe.submit()
+            pipe.wait(t_prev)
+            t_prev = t_new
+        pipe.wait(t_prev)
+        settle()
+        for _ in range(3):
+            pipe.wait(pipe.submit())
+        barrier()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        t_prev = pipe.submit()
+        for _ in range(e2e_steps - 1):
+            t_new = pipe.submit()
+            stp = pipe.wait(t_prev)
+            t_prev = t_new
+        stp = pipe.wait(t_prev)
+        p1.record()
+        barrier()
+        pipe_ok = bool(torch.equal(stp.I_img, lab_host[0]) and torch.equal(stp.D_txt, d_host[1]))
+        pipe_ms = (p0.elapsed_time(p1), pipe_ok)
+        del pipe
+    except Exception as e:  # an extra figure must not take the line down
+        pipe_ms = None
+        sys.stderr.write(f"pipelined e2e leg failed: {e!r}\n")
+    # the same step launched operation by operation on the stream (no graph): copies, chain, sync
+    settle()
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    f1.record()
+    barrier()
+    e2e_stream_ms = f0.elapsed_time(f1)
     clocks = sampler.stop() if sampler else None
+
+    # ---- the same loop for >= 1000 steps: what the step costs once the box has warmed up / power-capped
+    sustained = None
+    if not args.no_extras:
+        s_steps = max(1000, args.steps)
+        barrier()
+        ia.set_profiling(1)
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(s_steps):
+            step(q_dev)
+        s1.record()
+        barrier()
+        s_ms = s0.elapsed_time(s1)
+        ia.sync()
+        s_score_ms, s_score_n = ia.profile()
+        ia.set_profiling(0)
+        sustained = (s_steps, s_ms, s_score_ms / max(1, s_score_n))
+
 
     # ---- the Faiss-shaped numpy call exactly as the reference issues it (two searches, numpy out)
     q_np = q_host.numpy()
@@ -642,6 +691,7 @@ def run_ours(args, rank, world, local):
     e2e_ms = rmax(e2e_ms)
     e2e_copy_ms = rmax(e2e_copy_ms)
     e2e_hostio_ms = rmax(e2e_hostio_ms)
+    pipe_total_ms = rmax(pipe_ms[0] if pipe_ms is not None else -1.0)   # every rank takes part in the reduction
     e2e_stream_ms = rmax(e2e_stream_ms)
     dropin_ms = rmax(dropin_ms)
     if sustained is not None:
@@ -703,6 +753,11 @@ def run_ours(args, rank, world, local):
                         "the pinned block (keds_retrieve2_hostio, no copy nodes); 'copy_nodes': H2D + D2H copies around the "
                         "search. RetrievalStep probes both at capture time and keeps the faster on this box",
                 "layout": e2e_layout,
+                "leg_pause_s": LEG_PAUSE_S,
+                "two_steps_in_flight": None if (pipe_ms is None or pipe_total_ms <= 0) else {
+                    "ms_per_step": pipe_total_ms / e2e_steps, "value": world * BATCH / (pipe_total_ms / e2e_steps * 1e-3),
+                    "results_match": pipe_ms[1],
+                    "what": "RetrievalPipeline: batch i+1 submitted before batch i's host results are consumed"},
                 "host_io_ms_per_step": e2e_hostio_ms / e2e_steps,
                 "copy_nodes_ms_per_step": e2e_copy_ms / e2e_steps,
                 "results_match": all(bool(e2e_checks.get(kk)) for kk in (None, False, True)),

@@ -295,26 +295,29 @@ class RetrievalStep:
 
     def _capture(self) -> None:
         if self._auto_layout:
-            # time a few synchronised replays of both layouts (what run() does), keep the faster one
-            probe = {}
+            # time synchronised replays of both layouts (what run() does), alternating between them so
+            # that clock drift hits both alike; keep the mapped layout unless the copy nodes are
+            # clearly (> 2 %) faster on this box
+            graphs = {}
             for cn in (False, True):
                 self.copy_nodes = cn
                 self._capture_one()
-                dev = self.q_dev.device
-                st = torch.cuda.current_stream(dev)
-                for _ in range(3):
-                    self.graph.replay()
+                graphs[cn] = self.graph
+            st = torch.cuda.current_stream(self.q_dev.device)
+            probe = {False: float("inf"), True: float("inf")}
+            for rnd in range(5):
+                for cn in (False, True):
+                    g = graphs[cn]
+                    g.replay()
                     st.synchronize()
-                best = float("inf")
-                for _ in range(3):
                     t0 = time.perf_counter()
-                    for _ in range(8):
-                        self.graph.replay()
+                    for _ in range(12):
+                        g.replay()
                         st.synchronize()
-                    best = min(best, (time.perf_counter() - t0) / 8)
-                probe[cn] = best * 1e6
-            self.layout_probe_us = {"host_io": probe[False], "copy_nodes": probe[True]}
-            self.copy_nodes = probe[True] < probe[False]
+                    probe[cn] = min(probe[cn], (time.perf_counter() - t0) / 12)
+            self.layout_probe_us = {"host_io": probe[False] * 1e6, "copy_nodes": probe[True] * 1e6}
+            self.copy_nodes = probe[True] < 0.98 * probe[False]
+            del graphs
             self._auto_layout = False   # a re-capture (moved scratch) keeps the choice
             self.recaptures -= 2
         self._capture_one()
@@ -355,6 +358,45 @@ class RetrievalStep:
         if sync:
             torch.cuda.current_stream(self.q_dev.device).synchronize()
         return self.out
+
+
+class RetrievalPipeline:
+    """Two `RetrievalStep`s over the same pair of indices, used alternately: `submit(q)` starts the
+    step for one batch and returns at once, `wait(ticket)` hands back that batch's host results.
+    The retrieval of batch i+1 does not depend on the results of batch i (the queries come from the
+    encoder's forward of the new batch, src/trainer.py:52-58), so a loop may submit it before it
+    consumes batch i: the graph launch and the completion wake-up of one step then hide under the
+    GPU work of the other. Both graphs run on the caller's current stream, one after the other (the
+    handles' scratch is shared: one search in flight per handle, as ever); queries and results are
+    double-buffered, every step still reads its own queries from pinned host memory and returns
+    its own (D, I) there."""
+
+    def __init__(self, image_index: GpuIndexFlat, text_index: GpuIndexFlat, batch: int, **kw) -> None:
+        self.steps = [RetrievalStep(image_index, text_index, batch, **kw) for _ in range(2)]
+        self._events = [None, None]
+        self._n = 0
+
+    def submit(self, q: Optional[torch.Tensor] = None) -> int:
+        slot = self._n & 1
+        if self._events[slot] is not None:      # the slot's previous batch must be done with its buffers
+            self._events[slot].synchronize()
+        st = self.steps[slot]
+        st.run(q, sync=False)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(st.q_dev.device))
+        self._events[slot] = ev
+        self._n += 1
+        return self._n - 1
+
+    def wait(self, ticket: int) -> "RetrievalStep":
+        """Block until the batch submitted as `ticket` is complete; returns the step object whose
+        D_img / I_img / D_txt / I_txt (pinned host) and `out` (device) hold its results. They stay
+        valid until the second submit after this one."""
+        slot = ticket & 1
+        if ticket < self._n - 2 or ticket >= self._n:
+            raise ValueError("ticket is not in flight (results are kept for the last two submits)")
+        self._events[slot].synchronize()
+        return self.steps[slot]
 
 
 def get_extra_cap_features(feature, database, args=None, topk: int = 2):

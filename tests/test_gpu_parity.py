@@ -668,6 +668,31 @@ def test_host_io_through_the_mapping_equals_the_copy_path():
         kr.retrieve2(ia, ib, torch.from_numpy(q), 16)   # pageable host memory is refused
 
 
+def test_retrieval_pipeline_two_steps_in_flight():
+    """RetrievalPipeline: batch i+1 submitted before batch i is consumed; every batch's host and
+    device results equal the plain call's."""
+    a, b = unit(12000, 768, 391), unit(12000, 768, 392)
+    ia, ib = build(a, "l2"), build(b, "l2")
+    perm = torch.randperm(16, generator=torch.Generator().manual_seed(9))
+    pipe = kr.RetrievalPipeline(ia, ib, 64, topk=16, perm_img=perm, want_feats=True, pool_mode=kr.POOL_MEAN)
+    qs = [torch.from_numpy(unit(64, 768, 400 + i)) for i in range(5)]
+    tickets, got = [], []
+    tickets.append(pipe.submit(qs[0]))
+    for i in range(1, 5):
+        tickets.append(pipe.submit(qs[i]))                 # batch i goes in ...
+        st = pipe.wait(tickets[i - 1])                     # ... before batch i-1 is read
+        got.append((st.I_img.clone(), st.D_txt.clone(), st.out["feat_img"].clone(), st.out["pool_txt"].clone()))
+    st = pipe.wait(tickets[4])
+    got.append((st.I_img.clone(), st.D_txt.clone(), st.out["feat_img"].clone(), st.out["pool_txt"].clone()))
+    with pytest.raises(ValueError):
+        pipe.wait(tickets[1])
+    for i in range(5):
+        r = kr.retrieve2(ia, ib, qs[i].cuda(), 16, perm_img=perm, want_feats=True, pool_mode=kr.POOL_MEAN)
+        ia.sync()
+        assert torch.equal(got[i][0], r["I_img"].cpu()) and torch.equal(got[i][1], r["D_txt"].cpu())
+        assert torch.equal(got[i][2], r["feat_img"]) and torch.equal(got[i][3], r["pool_txt"])
+
+
 def test_get_retrieved_features_matches_the_reference_outputs(golden_dir):
     z = np.load(os.path.join(golden_dir, "retrieval.npz"))
     ib, tb = torch.from_numpy(z["image_base"]), torch.from_numpy(z["text_base"])
