@@ -862,13 +862,13 @@ int search_impl(keds_index* ix[2], int n_db, const float* q, int64_t nq, int k, 
   bool any_empty = false;
   for (int i = 0; i < n_db; ++i) any_empty = any_empty || ix[i]->n == 0;
   // Host in, host out (the reference's numpy call): the call synchronises before it returns, so
-  // page-locked staging buffers can be reused call after call -- and the kernels work on them
-  // through the mapping: k_prep_rows reads the staged queries, the ranking blocks store their rows
-  // into the staged result block. No copy in front of the search and none behind it.
+  // page-locked staging buffers can be reused call after call (one real DMA each way instead of
+  // the driver's chunked pageable copies). Letting the kernels work on those buffers through the
+  // mapping (as keds_retrieve2_hostio does for RetrievalStep) was measured here too and is no
+  // faster for this path (two searches of 128 queries: 403-411 us with copies, 413-425 us mapped):
+  // the call is dominated by its host side.
   // one database's I (8 B) and D (4 B) blocks in the staged result, labels first (8-byte aligned)
   const size_t res_per = (static_cast<size_t>(nq) * k * 12 + 15) & ~size_t(15);
-  ConsumeParams host_cons;
-  bool staged_io = false;
   if (!q_dev) {
     const size_t qb = static_cast<size_t>(nq) * a->d * 4;
     CKS(a->q_f32.ensure(qb));
@@ -877,29 +877,8 @@ int search_impl(keds_index* ix[2], int n_db, const float* q, int64_t nq, int k, 
       CKS(a->h_q.ensure(qb));
       memcpy(a->h_q.p, q, qb);
       src = a->h_q.p;
-      // (without the fallback a flagged query keeps the re-rank's provisional row, which only the
-      // device block holds: that diagnostic mode takes the copies)
-      staged_io = !cons && !peer && !any_empty && !(flags & KEDS_SEARCH_NO_FALLBACK) &&
-                  res_per * n_db <= (size_t(256) << 20);
     }
-    if (staged_io) {
-      const size_t ctrl_bytes = static_cast<size_t>((nq + Q_PASS_MAX - 1) / Q_PASS_MAX) * CTRL_STRIDE * 4;
-      CKS(a->h_out.ensure(res_per * n_db + ctrl_bytes));
-      float* qalias = nullptr;
-      uint8_t* oalias = nullptr;
-      CKS(mapped_alias(static_cast<float*>(a->h_q.p), &qalias));
-      CKS(mapped_alias(static_cast<uint8_t*>(a->h_out.p), &oalias));
-      q_map = qalias;
-      memset(&host_cons, 0, sizeof host_cons);
-      host_cons.enabled = 1;
-      for (int i = 0; i < n_db; ++i) {
-        host_cons.host_I[i] = reinterpret_cast<long long*>(oalias + res_per * i);
-        host_cons.host_D[i] = reinterpret_cast<float*>(oalias + res_per * i + static_cast<size_t>(nq) * k * 8);
-      }
-      cons = &host_cons;
-    } else {
-      CK(cudaMemcpyAsync(a->q_f32.p, src, qb, cudaMemcpyHostToDevice, st));
-    }
+    CK(cudaMemcpyAsync(a->q_f32.p, src, qb, cudaMemcpyHostToDevice, st));
     qd = a->q_f32.as<float>();
   }
   float* Dd[2] = {nullptr, nullptr};
@@ -992,11 +971,9 @@ int search_impl(keds_index* ix[2], int n_db, const float* q, int64_t nq, int k, 
     const size_t ctrl_bytes = static_cast<size_t>(a->ctrl_passes) * CTRL_STRIDE * 4;
     CKS(a->h_out.ensure(per * n_db + ctrl_bytes));
     uint8_t* h = static_cast<uint8_t*>(a->h_out.p);
-    if (!staged_io) {  // (staged_io: the kernels have written the rows here themselves)
-      for (int i = 0; i < n_db; ++i) {
-        CK(cudaMemcpyAsync(h + per * i, Id[i], ib_, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(h + per * i + ib_, Dd[i], db_, cudaMemcpyDeviceToHost, st));
-      }
+    for (int i = 0; i < n_db; ++i) {
+      CK(cudaMemcpyAsync(h + per * i, Id[i], ib_, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(h + per * i + ib_, Dd[i], db_, cudaMemcpyDeviceToHost, st));
     }
     uint32_t* hall = reinterpret_cast<uint32_t*>(h + per * n_db);
     memset(hall, 0, ctrl_bytes);
