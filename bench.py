@@ -21,7 +21,15 @@ the L2 variant of the headline (the reference constructs IndexFlatL2), the clust
 
 Timing: W >= 3 warm-ups; K steps bracketed by barrier + synchronize; CUDA events on the launching
 stream; max over ranks.  Inputs (2 x 768 MB of 16-bit rows + fp32 re-rank rows) exceed the 126 MB
-L2, so every step streams from HBM.
+L2, so every step streams from HBM.  Every timed leg (value, the end-to-end legs) starts from the
+same state: a 0.25-s idle, then its own warm-up steps -- the boxes are power-capped and this kernel's
+time follows the SM clock, so a leg measured behind another one would otherwise inherit its clock;
+the >= 1000-step `sustained` loop (run last) is the figure for the capped regime.
+
+e2e: `RetrievalStep.run()` (pinned host queries in, (D, I) of both databases in pinned host memory
+out, one stream synchronisation per step); `e2e.host_io_ms_per_step` / `copy_nodes_ms_per_step` time
+its two graph layouts, `two_steps_in_flight` the pipelined use, `stream_launched_*` the same step
+without a graph.
 """
 from __future__ import annotations
 
