@@ -1837,6 +1837,7 @@ int keds_index_label_hits(keds_index_t* ix, const float* q, int64_t nq, const in
   if (ks[nks - 1] > K_MAX) return fail(KEDS_ERR_ARG, "index_label_hits: k=%d exceeds the maximum %d", ks[nks - 1], K_MAX);
   if (nq == 0) return 0;
   if (ix->n == 0) return fail(KEDS_ERR_ARG, "index_label_hits: empty index");
+  if (ix->n > 0x7fffffffll - BN) return fail(KEDS_ERR_ARG, "index too large for 32-bit row ids");
   if (!is_device_ptr(q) || !is_device_ptr(row_labels) || !is_device_ptr(qlabel) || !is_device_ptr(hits))
     return fail(KEDS_ERR_ARG, "index_label_hits: device pointers only");
   DeviceGuard g(ix->device);
