@@ -22,7 +22,7 @@ the L2 variant of the headline (the reference constructs IndexFlatL2), the clust
 Timing: W >= 3 warm-ups; K steps bracketed by barrier + synchronize; CUDA events on the launching
 stream; max over ranks.  Inputs (2 x 768 MB of 16-bit rows + fp32 re-rank rows) exceed the 126 MB
 L2, so every step streams from HBM.  Every timed leg (value, the end-to-end legs) starts from the
-same state: a 0.25-s idle, then its own warm-up steps -- the boxes are power-capped and this kernel's
+same state: a 1-s idle, then its own warm-up steps -- the boxes are power-capped and this kernel's
 time follows the SM clock, so a leg measured behind another one would otherwise inherit its clock;
 the >= 1000-step `sustained` loop (run last) is the figure for the capped regime.
 
@@ -505,7 +505,7 @@ def run_ours(args, rank, world, local):
     # idle a leg inherits the clock the power cap has reached by then (this kernel's time follows
     # the SM clock) -- the index build in front of the first leg, the earlier legs in front of the
     # others -- and the order of the legs in this file decides their numbers.
-    LEG_PAUSE_S = 0.25
+    LEG_PAUSE_S = 1.0
 
     def settle():
         barrier()
