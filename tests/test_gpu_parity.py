@@ -843,6 +843,16 @@ def test_index_label_hits_equal_the_search_then_count_path():
         assert ix.last_stats()["n_flagged"][0] == 700
         ix.set_eps_scale(1.0)
         assert np.array_equal(h2.cpu().numpy(), hits)
+    # more queries than one pass holds: hits, labels and status follow the pass offsets
+    gm, qm = unit(6000, 64, 813), unit(16384 + 500, 64, 814)
+    lm, qlm = torch.from_numpy(rng.integers(0, 20, 6000)), torch.from_numpy(rng.integers(0, 20, 16884))
+    im = build(gm, "ip")
+    qmd = torch.from_numpy(qm).cuda()
+    hm = km.index_label_hits(im, qmd, lm, qlm, [1, 10, 100])
+    im.sync()
+    assert im.last_stats()["err_word"] == 0
+    _, I = im.search(qmd, 100)
+    assert torch.equal(hm, km.label_hits(I, lm, qlm, [1, 10, 100]))
     # a gallery too small for the tensor-core path, and cut points beyond its size
     small = build(g[:150], "ip")
     hs = km.index_label_hits(small, qd, glab[:150], qlab, [1, 100, 200])
