@@ -666,6 +666,11 @@ def test_host_io_through_the_mapping_equals_the_copy_path():
     both(ca, cb, unit(16384 + 300, 64, 196))      # two passes: the mirrors follow the pass offsets
     with pytest.raises(Exception):
         kr.retrieve2(ia, ib, torch.from_numpy(q), 16)   # pageable host memory is refused
+    # fewer rows than k: the padding (-1, -/+FLT_MAX) reaches the host mirror as well
+    ta, tb = build(a[:10], "ip"), build(b[:10], "ip")
+    _, ho = both(ta, tb, q[:5])
+    assert (ho["I_img"][:, 10:] == -1).all() and (ho["D_txt"][:, 10:] == -orc.FLT_MAX).all()
+    assert (ho["I_img"][:, :10] >= 0).all()
 
 
 def test_retrieval_pipeline_two_steps_in_flight():
