@@ -743,6 +743,40 @@ __global__ void k_gather_rows(const float* __restrict__ base, long long n_base, 
   }
 }
 
+// The neighbour consumer's MLP input in one launch: rows [queries | image neighbours | text
+// neighbours] = [B | B k | B k] x d (src/trainer.py:59-65 feeds the same three blocks through
+// IM2TEXT). One warp per row; image neighbours follow the shared permutation; ids outside their
+// base give zero rows.
+__global__ void k_consumer_rows(const float* __restrict__ q, const float* __restrict__ base_img, long long n_img,
+                                const float* __restrict__ base_txt, long long n_txt,
+                                const long long* __restrict__ I_img, const long long* __restrict__ I_txt,
+                                const int* __restrict__ perm, long long B, int k, int d, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long w = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long Bk = B * k;
+  if (w >= B + 2 * Bk) return;
+  const float* src = nullptr;   // nullptr: zero row
+  if (w < B) {
+    src = q + w * d;
+  } else {
+    const bool img = w < B + Bk;
+    const long long r = img ? w - B : w - B - Bk;
+    const long long b = r / k;
+    const int j = static_cast<int>(r % k);
+    const int pj = (img && perm) ? perm[j] : j;
+    const long long id = static_cast<unsigned int>(pj) < static_cast<unsigned int>(k) ? (img ? I_img : I_txt)[b * k + pj] : -1;
+    if (id >= 0 && id < (img ? n_img : n_txt)) src = (img ? base_img : base_txt) + id * d;
+  }
+  float* o = out + w * d;
+  if ((d & 3) == 0 && src != nullptr && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(o)) & 15) == 0) {
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4* o4 = reinterpret_cast<float4*>(o);
+    for (int c = lane; c < (d >> 2); c += 32) o4[c] = __ldg(s4 + c);
+  } else {
+    for (int c = lane; c < d; c += 32) o[c] = src != nullptr ? src[c] : 0.f;
+  }
+}
+
 __global__ void k_weighted_pool(const float* __restrict__ base, long long n_base, const long long* __restrict__ I,
                                 const float* __restrict__ W, long long B, int k, int H, int d,
                                 float* __restrict__ out) {

@@ -405,18 +405,14 @@ int consumer_forward_impl(keds_consumer_t* c, const float* q, const float* base_
     CK(cudaMemsetAsync(c->tdump.p, 0, c->tdump.cap, st));
   }
 
-  // rows of the MLP input: [queries | image neighbours | text neighbours]
+  // rows of the MLP input: [queries | image neighbours | text neighbours], one launch
   float* xin = c->xin.as<float>();
-  CK(cudaMemcpyAsync(xin, q, static_cast<size_t>(B) * c->d_in * 4, cudaMemcpyDeviceToDevice, st));
-  const unsigned gblocks = static_cast<unsigned>((Bk * 32 + 255) / 256);
-  k_gather_rows<<<gblocks, 256, 0, st>>>(base_img, static_cast<long long>(n_img),
-                                         reinterpret_cast<const long long*>(I_img), perm, B, k, c->d_in,
-                                         xin + B * c->d_in);
-  k_gather_rows<<<gblocks, 256, 0, st>>>(base_txt, static_cast<long long>(n_txt),
-                                         reinterpret_cast<const long long*>(I_txt), nullptr, B, k, c->d_in,
-                                         xin + (B + Bk) * c->d_in);
+  const unsigned gblocks = static_cast<unsigned>(((B + 2 * Bk) * 32 + 255) / 256);
+  k_consumer_rows<<<gblocks, 256, 0, st>>>(q, base_img, static_cast<long long>(n_img), base_txt,
+                                           static_cast<long long>(n_txt), reinterpret_cast<const long long*>(I_img),
+                                           reinterpret_cast<const long long*>(I_txt), perm, B, k, c->d_in, xin);
   CK(cudaGetLastError());
-  c->launches += 2;
+  c->launches += 1;
 
   // IM2TEXT: hidden layers (Linear + ReLU; dropout is the identity in eval), then fc_out
   const float* cur = xin;
