@@ -191,13 +191,16 @@ int device_of(const void* p) {
   return (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) ? a.device : -1;
 }
 
-// [0],[1] n_flagged per db, [2] err word, [3..5] work counters of the exact fallback, [6] largest
-// candidate band |C| of the search (planner feedback), [7] spare
+// [0],[1] n_flagged per db, [2] err word, [3..5] spare, [6] largest candidate band |C| of the search
+// (planner feedback), [7] spare
 constexpr int CTRL_WORDS = 8;
 constexpr int CTRL_BAND = 6;
-// one block of status words per pass of a multi-pass call, so that no pass has to be read back
-// before the next one starts
-constexpr int CTRL_STRIDE = CTRL_WORDS;
+// One block of status words per pass of a multi-pass call, so that no pass has to be read back
+// before the next one starts. Behind the status words: the exact fallback's work counters, one set
+// of four words per launch of that kernel (k_prep_rows zeroes the whole block, so the launches of a
+// search need no memset between them).
+constexpr int EXACT_CTR_SETS = 64;
+constexpr int CTRL_STRIDE = CTRL_WORDS + 4 * EXACT_CTR_SETS;
 constexpr int S_MAX = 192;
 constexpr size_t CAND_BUDGET = size_t(1) << 30;
 constexpr int64_t Q_PASS_MAX = 16384;
@@ -464,10 +467,15 @@ int launch_exact(keds_index* ix, keds_index* dbs[2], int n_db, const float* q_de
   ep.metric = metric;
   ep.k = k;
   ep.q_f32 = q_dev;
-  // queries per pass: as many as a 512 MB score scratch holds (all of a 128-query batch at 0.5M rows)
+  // Queries per launch: as many as the score scratch holds. 512 MB covers all of a 128-query batch
+  // at 2 x 0.5M rows; large batches get up to 4 GB so that a search is followed by about eight
+  // launches of this kernel, not sixty (each of them costs a few microseconds even when nothing is
+  // queued: at 65,536 x 0.5M they added up to 2 ms of a 40-ms call).
   int64_t rows_sum = 0;
   for (int i = 0; i < n_db; ++i) rows_sum += dbs[i]->n;
-  long long fc = (512ll << 20) / (4 * std::max<int64_t>(rows_sum, 1));
+  const long long row_bytes = 4 * std::max<int64_t>(rows_sum, 1);
+  long long budget = std::max(512ll << 20, std::min(4ll << 30, static_cast<long long>(nq) * row_bytes / 8));
+  long long fc = budget / row_bytes;
   fc = std::max(1ll, std::min<long long>(fc, nq));
   ep.f_cap = static_cast<int>(fc);
   // row chunks (phase-1 work units): about four per block, at least one 32-row group per warp
@@ -506,9 +514,6 @@ int launch_exact(keds_index* ix, keds_index* dbs[2], int n_db, const float* q_de
   const size_t smem = std::max(smem_sc, smem_sel);
   if (smem > 160 * 1024) return fail(KEDS_ERR_ARG, "d=%d / k=%d too large for the exact fallback", ix->d, k);
   const unsigned blocks = blocks_;
-  // status words [3..5]: work counters of the fallback, zero at the start of every search
-  ep.work = ix->ctrl_cur + 3;
-  ep.done = ix->ctrl_cur + 5;
   ep.err = ix->ctrl_cur + 2;
   ep.band_dev = ix->ctrl_cur + CTRL_BAND;
   const int passes = static_cast<int>((nq + fc - 1) / fc);
@@ -520,7 +525,12 @@ int launch_exact(keds_index* ix, keds_index* dbs[2], int n_db, const float* q_de
       ep.peer.publish = peer->publish && pass == passes - 1;  // only the step's very last launch publishes
     }
     ep.timing = pass == 0 ? timing : nullptr;
-    if (pass > 0) CK(cudaMemsetAsync(ix->ctrl_cur + 3, 0, 12, st));
+    // work counters of this launch: its own zeroed set (the last set is shared, with a memset, by
+    // launches beyond EXACT_CTR_SETS)
+    const int set = std::min(pass, EXACT_CTR_SETS - 1);
+    ep.work = ix->ctrl_cur + CTRL_WORDS + 4 * set;
+    ep.done = ep.work + 2;
+    if (pass >= EXACT_CTR_SETS) CK(cudaMemsetAsync(ep.work, 0, 16, st));
     CKS(launch_k(ix->use_pdl, k_exact_fallback, dim3(blocks), dim3(EXACT_THREADS), smem, st, ep));
     ix->stats.launches += 1;
   }
@@ -569,7 +579,7 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
 
   if (pl.exact_only) {
     if (q_src) CK(cudaMemcpyAsync(const_cast<float*>(q_dev), q_src, static_cast<size_t>(nq) * a->d * 4, cudaMemcpyDefault, st));
-    CK(cudaMemsetAsync(a->ctrl_cur, 0, CTRL_WORDS * 4, st));
+    CK(cudaMemsetAsync(a->ctrl_cur, 0, CTRL_STRIDE * 4, st));
     for (int i = 0; i < n_db; ++i) {
       k_flag_all<<<static_cast<unsigned>((nq + 255) / 256), 256, 0, st>>>(
           a->flagged[i].as<int>(), reinterpret_cast<int*>(a->ctrl_cur) + i, static_cast<int>(nq));
@@ -591,7 +601,7 @@ int search_pass(keds_index* ix[2], int n_db, const float* q_dev, int64_t nq, int
       CKS(launch_k(a->use_pdl, k_prep_rows, dim3(blocks), dim3(threads), 0, st, q_src ? q_src : q_dev,
                    static_cast<long long>(nq), a->d, a->d_pad, a->fmt, a->q_bf16.as<uint16_t>(),
                    a->qstat.as<float4>(), static_cast<float*>(nullptr), static_cast<unsigned int*>(nullptr),
-                   a->ctrl_cur, CTRL_WORDS, a->theta0.as<float>(), static_cast<int>(n_db * theta_ld), tchain,
+                   a->ctrl_cur, CTRL_STRIDE, a->theta0.as<float>(), static_cast<int>(n_db * theta_ld), tchain,
                    q_src ? const_cast<float*>(q_dev) : static_cast<float*>(nullptr)));
       a->stats.launches++;
     }
@@ -1758,7 +1768,8 @@ int keds_index_rank(keds_index_t* ix, const float* q, int64_t nq, const int64_t*
     const int n_items = n_qg * S;
     const int grid = std::min(n_items, units) * (pair ? 2 : 1);
     const int n_lists = S * sub;
-    CKS(ix->ctrl.ensure(CTRL_WORDS * 4));
+    CKS(ix->ctrl.ensure(CTRL_STRIDE * 4));  // (finish_sync reads whole status blocks)
+    ix->ctrl_passes = 1;
     CKS(ix->flagged[0].ensure(static_cast<size_t>(nb) * 4));
     CKS(ensure_q_map(ix, static_cast<int64_t>(n_qt) * BM, st));
     CKS(ix->qstat.ensure(static_cast<size_t>(nb) * sizeof(float4)));
