@@ -467,14 +467,15 @@ int launch_exact(keds_index* ix, keds_index* dbs[2], int n_db, const float* q_de
   ep.metric = metric;
   ep.k = k;
   ep.q_f32 = q_dev;
-  // Queries per launch: as many as the score scratch holds. 512 MB covers all of a 128-query batch
-  // at 2 x 0.5M rows; large batches get up to 4 GB so that a search is followed by about eight
-  // launches of this kernel, not sixty (each of them costs a few microseconds even when nothing is
-  // queued: at 65,536 x 0.5M they added up to 2 ms of a 40-ms call).
+  // Queries per launch: as many as the score scratch holds (it is allocated for the batch at hand,
+  // never beyond the budget). Up to 1 GB always -- all of a 128-query batch at 2 x 0.5M rows, all of
+  // 4,096 queries at 50k rows in ONE launch; large batches get up to 4 GB so that a search is followed
+  // by about eight launches of this kernel, not sixty (each of them costs a few microseconds even
+  // when nothing is queued: at 65,536 x 0.5M they added up to 2 ms of a 40-ms call).
   int64_t rows_sum = 0;
   for (int i = 0; i < n_db; ++i) rows_sum += dbs[i]->n;
   const long long row_bytes = 4 * std::max<int64_t>(rows_sum, 1);
-  long long budget = std::max(512ll << 20, std::min(4ll << 30, static_cast<long long>(nq) * row_bytes / 8));
+  long long budget = std::max(1ll << 30, std::min(4ll << 30, static_cast<long long>(nq) * row_bytes / 8));
   long long fc = budget / row_bytes;
   fc = std::max(1ll, std::min<long long>(fc, nq));
   ep.f_cap = static_cast<int>(fc);
