@@ -392,9 +392,14 @@ def run_extras(dev, pk, ia, ib, img_rows):
         rn, tn = [f"dev-{i}.png" for i in ref], [f"dev-{i}.png" for i in tgt]
         t0 = time.perf_counter()
         m = km.get_metrics_cirr(gal, qf, rn, names, tn)
-        call_ms = (time.perf_counter() - t0) * 1e3
+        first_call_ms = (time.perf_counter() - t0) * 1e3   # builds the gallery index and the name table
+        t0 = time.perf_counter()
+        for _ in range(5):   # the eval loops score 30 checkpoints x 3 feature sets against one gallery
+            m = km.get_metrics_cirr(gal, qf, rn, names, tn)
+        call_ms = (time.perf_counter() - t0) / 5 * 1e3
         flops = 2.0 * Q * G * DIM
-        r["cirr_4181x2297"] = {"rank_kernel_ms": ms, "get_metrics_cirr_call_ms": call_ms, "tflops": flops / ms / 1e9,
+        r["cirr_4181x2297"] = {"rank_kernel_ms": ms, "get_metrics_cirr_call_ms": call_ms,
+                               "get_metrics_cirr_first_call_ms": first_call_ms, "tflops": flops / ms / 1e9,
                                "note": "8.9 us of math at the tensor peak: latency-bound, reported, not graded on roofline",
                                "recall_R@1": m["recall_R@1"], "recall_R@50": m["recall_R@50"]}
         NG, NQ = 50_000, 10_000
@@ -418,8 +423,9 @@ def run_extras(dev, pk, ia, ib, img_rows):
         r["imgnet_10000x50k_label_hits"] = rh
         km.get_metrics_imgnet(qq, rows, qlab, glab)
         t0 = time.perf_counter()
-        km.get_metrics_imgnet(qq, rows, qlab, glab)
-        r["imgnet_10000x50k_k200"]["get_metrics_imgnet_call_ms"] = (time.perf_counter() - t0) * 1e3
+        for _ in range(5):
+            km.get_metrics_imgnet(qq, rows, qlab, glab)
+        r["imgnet_10000x50k_k200"]["get_metrics_imgnet_call_ms"] = (time.perf_counter() - t0) / 5 * 1e3
         return r
     guard("cfg4_gallery", cfg4)
 

@@ -246,10 +246,14 @@ def get_metrics_imgnet(query_features, image_features, query_labels, target_labe
     else:  # a gallery smaller than the largest cut: the padded search defines what "top-k" means
         _, I = ix.search(Q, max(ks))
         hits = label_hits(I, tl, ql, ks).to(torch.float32)
-    n_cls = int(max(int(tl.max()), int(ql.max()))) + 1
-    num_total = torch.bincount(tl, minlength=n_cls)[ql].to(torch.float32)
+    # relevant rows per query (the one-hot product of :1103) from the sorted gallery labels, and all
+    # twelve means in one tensor: one device-to-host transfer for the whole call, no sync in between
+    tl_sorted = torch.sort(tl).values
+    num_total = (torch.searchsorted(tl_sorted, ql, right=True) - torch.searchsorted(tl_sorted, ql, right=False)).to(torch.float32)
+    denom_p = torch.tensor([float(min(k, n_gallery)) for k in ks], dtype=torch.float32, device=dev)
+    both = torch.cat([(hits / (num_total + 1e-5).unsqueeze(1)).mean(0), (hits / denom_p.unsqueeze(0)).mean(0)]).cpu().tolist()
     metrics: Dict[str, float] = {}
     for i, k in enumerate(ks):
-        metrics[f"Real2Sketch_R@{k}"] = float((hits[:, i] / (num_total + 1e-5)).mean())
-        metrics[f"Real2Sketch_P@{k}"] = float((hits[:, i] / float(min(k, n_gallery))).mean())
+        metrics[f"Real2Sketch_R@{k}"] = both[i]
+        metrics[f"Real2Sketch_P@{k}"] = both[len(ks) + i]
     return metrics
